@@ -1,0 +1,117 @@
+/*
+ * percepnet_b200.h -- C-ABI of the B200-native PercepNet enhancement hot path.
+ *
+ * Plain pointers and sizes only (no torch / C++ types).  Two layers of entry points:
+ *
+ *  1. the batched-streams engine (pnb_*): S independent 48 kHz streams advance together,
+ *     F hops of 480 samples per call.  This is what a host integrates for throughput.
+ *  2. the reference's own single-stream API (rnnoise_create / rnnoise_process_frame /
+ *     rnnoise_destroy, C++ linkage like /root/reference/src/rnnoise.h:52-60) lives in
+ *     librnnoise_b200.so (percepnet_b200/csrc/rnnoise_shim.cpp) on top of this ABI, so the
+ *     unmodified /root/reference/src/main.cpp links against it.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *   pnb_create          rnnoise_create + rnnoise_init            src/denoise.cpp:252-280
+ *                       + check_init table construction           src/denoise.cpp:186-214
+ *                       + weight ingest of `const RNNModel*`      src/nnet_data.h:6-26
+ *   pnb_process_*       rnnoise_process_frame for S streams x F hops   src/denoise.cpp:508-547
+ *                       (compute_frame_features :372, compute_rnn src/rnn.cpp:42,
+ *                        pitch_filter :436, interp_band_gain :162, frame_synthesis :352)
+ *   pnb_process_*_i16   the int16 I/O conversions of the CLI      src/main.cpp:30-39
+ *   pnb_destroy         rnnoise_destroy                           src/denoise.cpp:326-331
+ *   pnb_reset           the memset in rnnoise_init                src/denoise.cpp:260
+ *
+ * Frame contract (src/rnnoise.h:60): hops of exactly 480 float samples at
+ * 48 kHz, any amplitude scale; output hop t carries input hop t-6.  Streams are laid out
+ * stream-major: sample n of stream s is at base[s*stride + n].
+ *
+ * All functions return PNB_OK (0) or a negative error code; pnb_last_error() gives text.
+ * There is no CPU fallback: without a usable CUDA device pnb_create fails with
+ * PNB_ERR_NO_DEVICE.
+ */
+#ifndef PERCEPNET_B200_H
+#define PERCEPNET_B200_H
+
+#include <stddef.h>
+#include "pnb_nnet_layout.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNB_FRAME 480        /* FRAME_SIZE, src/denoise.cpp:19 */
+#define PNB_BANDS 34         /* NB_BANDS,   src/denoise.cpp:35 */
+#define PNB_FEATURES 70      /* NB_FEATURES, src/denoise.cpp:40 */
+#define PNB_LATENCY_FRAMES 6 /* 5 hops look-ahead + 1 hop overlap-add */
+
+enum {
+  PNB_OK = 0,
+  PNB_ERR_ARG = -1,
+  PNB_ERR_CUDA = -2,
+  PNB_ERR_NO_DEVICE = -3,
+  PNB_ERR_ALLOC = -4
+};
+
+/* pnb_create flags */
+enum {
+  PNB_NN_FP32 = 0,       /* network contraction in fp32 FMA (BASELINE.json config 2)                  */
+  PNB_NN_TENSOR = 1,     /* network contraction on tcgen05 tensor cores, split-fp16 operands, fp32 accumulate */
+  PNB_POSTFILTER = 2,    /* apply the envelope post-filter (src/denoise.cpp:216-250) to g; off in the reference */
+  PNB_KEEP_TAPS = 4      /* keep per-frame intermediates of the last call readable through pnb_read_tap    */
+};
+
+typedef struct pnb_engine pnb_engine;
+
+/* model: the reference's weight layout (a `const RNNModel*` from a compiled nnet_data.cpp may be
+ * passed as is); the weights are copied to the device, the caller's arrays are not retained. */
+int pnb_create(pnb_engine **out, int n_streams, int max_frames_per_call, const pnb_model *model,
+               unsigned flags, int device);
+void pnb_destroy(pnb_engine *e);
+int pnb_reset(pnb_engine *e);
+
+/* Host buffers (pageable or pinned).  in/out: n_streams rows of n_frames*480 samples, row strides
+ * in elements.  in may equal out.  gr (NULL ok) receives the raw network outputs the reference
+ * fwrite()s per frame (src/denoise.cpp:533-534) as [n_frames][n_streams][68] = 34 g then 34 r.
+ * Blocking: returns when out (and gr) are complete. */
+int pnb_process_host_f32(pnb_engine *e, const float *in, size_t in_stride, float *out, size_t out_stride,
+                         int n_frames, float *gr);
+
+/* int16 PCM wire format with the CLI's conversions (src/main.cpp:34,36): x = s/32768.f in,
+ * (short)(y*32768) out (C truncation).  The first-hop drop of main.cpp:37-38 is the caller's. */
+int pnb_process_host_i16(pnb_engine *e, const short *in, size_t in_stride, short *out, size_t out_stride,
+                         int n_frames, float *gr);
+
+/* Device buffers on the engine's device; asynchronous on cuda_stream (a cudaStream_t, NULL = default
+ * stream).  d_gr (NULL ok) as above, in device memory. */
+int pnb_process_device_f32(pnb_engine *e, const float *d_in, size_t in_stride, float *d_out, size_t out_stride,
+                           int n_frames, float *d_gr, void *cuda_stream);
+int pnb_process_device_i16(pnb_engine *e, const short *d_in, size_t in_stride, short *d_out, size_t out_stride,
+                           int n_frames, float *d_gr, void *cuda_stream);
+
+/* Per-frame intermediates of the LAST call (requires PNB_KEEP_TAPS); copies to host memory.
+ * Layouts are [n_frames][n_streams][...]:                                                   */
+enum {
+  PNB_TAP_FEATURES = 0, /* float[70]  network input (src/denoise.cpp:487-496)                */
+  PNB_TAP_PITCH = 1,    /* int[4]     {pitch_search lag, final period T, silence, 0}          */
+  PNB_TAP_PITCHF = 2,   /* float[2]   {pitch_corr, pitch_gain}                                */
+  PNB_TAP_X = 3,        /* float[800] analysis spectrum bins 0..399 (re,im)                   */
+  PNB_TAP_P = 4,        /* float[800] comb-filtered spectrum bins 0..399 (re,im)              */
+  PNB_TAP_EX = 5,       /* float[34]  band energy of X                                        */
+  PNB_TAP_GR = 6        /* float[68]  g, r                                                    */
+};
+int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes);
+
+/* Number of kernels this library has launched on behalf of e since creation. */
+long long pnb_launch_count(const pnb_engine *e);
+/* Kernel launches one pnb_process_* call with n_frames hops issues. */
+int pnb_launches_per_call(const pnb_engine *e, int n_frames);
+
+int pnb_n_streams(const pnb_engine *e);
+int pnb_max_frames(const pnb_engine *e);
+const char *pnb_last_error(void);
+const char *pnb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PERCEPNET_B200_H */

@@ -75,7 +75,7 @@ class Oracle:
     # -- engine -------------------------------------------------------------------------
     def create(self, model):
         self._model = model  # keep the weight arrays alive
-        return self.lib.pn_oracle_create(C.addressof(model.as_c_model()))
+        return self.lib.pn_oracle_create(C.byref(model.as_c_model()))
 
     def destroy(self, h):
         self.lib.pn_oracle_destroy(h)
@@ -106,7 +106,7 @@ class Oracle:
         n = pcm16.size // 480
         out = np.zeros((n - 1) * 480, np.int16)
         gr = np.empty((n, 68), np.float32)
-        self.lib.pn_oracle_run_pcm16(C.addressof(model.as_c_model()), pcm16.ctypes.data_as(I16P), n,
+        self.lib.pn_oracle_run_pcm16(C.byref(model.as_c_model()), pcm16.ctypes.data_as(I16P), n,
                                      out.ctypes.data_as(I16P), gr.ctypes.data_as(F32P))
         return out, gr
 
@@ -115,7 +115,7 @@ class Oracle:
         x = np.ascontiguousarray(x, dtype=np.float32)
         S, T = x.shape
         out = np.empty_like(x)
-        self.lib.pn_oracle_process_streams(C.addressof(model.as_c_model()), S, T // 480,
+        self.lib.pn_oracle_process_streams(C.byref(model.as_c_model()), S, T // 480,
                                            x.ctypes.data_as(F32P), out.ctypes.data_as(F32P), n_threads, flags)
         return out
 
@@ -228,7 +228,7 @@ class Oracle:
     def compute_rnn(self, model, state, features):
         f, fp = _f(features)
         g, r = np.empty(34, np.float32), np.empty(34, np.float32)
-        self.lib.pn_oracle_compute_rnn(C.addressof(model.as_c_model()), state.ctypes.data_as(F32P),
+        self.lib.pn_oracle_compute_rnn(C.byref(model.as_c_model()), state.ctypes.data_as(F32P),
                                        g.ctypes.data_as(F32P), r.ctypes.data_as(F32P), fp)
         return g, r
 
@@ -254,7 +254,7 @@ class Reference:
 
     def set_model(self, model):
         self._model = model
-        self.lib.ref_set_model(C.addressof(model.as_c_model()))
+        self.lib.ref_set_model(C.byref(model.as_c_model()))
 
     def create(self):
         return self.lib.ref_create()

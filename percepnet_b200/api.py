@@ -1,0 +1,142 @@
+"""Python host mirror of the C-ABI in include/percepnet_b200.h (ctypes; no compute here).
+
+``Engine`` is the batched-streams counterpart of the reference's ``DenoiseState``
+(/root/reference/src/rnnoise.h:49-60): ``Engine.process`` advances S independent 48 kHz streams by F
+hops of 480 samples, i.e. S x F calls of ``rnnoise_process_frame``.  The CUDA library is mandatory:
+there is no CPU path, and a missing ``libpercepnet_b200.so`` raises at import of the symbol table.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .weights import PackedModel
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpercepnet_b200.so")
+
+FRAME = 480
+NN_FP32, NN_TENSOR, POSTFILTER, KEEP_TAPS = 0, 1, 2, 4
+TAPS = {"features": (0, np.float32, 70), "pitch": (1, np.int32, 4), "pitchf": (2, np.float32, 2),
+        "X": (3, np.float32, 800), "P": (4, np.float32, 800), "Ex": (5, np.float32, 34), "gr": (6, np.float32, 68)}
+
+_lib = None
+
+
+class PnbError(RuntimeError):
+    pass
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PnbError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a).  There is no CPU implementation to fall back to.")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
+    L.pnb_create.argtypes = [C.POINTER(vp), i, i, vp, C.c_uint, i]
+    L.pnb_destroy.argtypes = [vp]
+    L.pnb_destroy.restype = None
+    L.pnb_reset.argtypes = [vp]
+    L.pnb_process_host_f32.argtypes = [vp, vp, sz, vp, sz, i, vp]
+    L.pnb_process_host_i16.argtypes = [vp, vp, sz, vp, sz, i, vp]
+    L.pnb_process_device_f32.argtypes = [vp, vp, sz, vp, sz, i, vp, vp]
+    L.pnb_process_device_i16.argtypes = [vp, vp, sz, vp, sz, i, vp, vp]
+    L.pnb_read_tap.argtypes = [vp, i, vp, sz]
+    L.pnb_launch_count.argtypes = [vp]
+    L.pnb_launch_count.restype = C.c_longlong
+    L.pnb_launches_per_call.argtypes = [vp, i]
+    L.pnb_n_streams.argtypes = [vp]
+    L.pnb_max_frames.argtypes = [vp]
+    L.pnb_last_error.restype = C.c_char_p
+    L.pnb_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+EXPORTS = ("pnb_create", "pnb_destroy", "pnb_reset", "pnb_process_host_f32", "pnb_process_host_i16",
+           "pnb_process_device_f32", "pnb_process_device_i16", "pnb_read_tap", "pnb_launch_count",
+           "pnb_launches_per_call", "pnb_n_streams", "pnb_max_frames", "pnb_last_error", "pnb_version")
+
+
+class Engine:
+    def __init__(self, n_streams: int, max_frames: int, model: PackedModel, flags: int = NN_FP32, device: int = 0):
+        self.L = load_library()
+        self.n_streams, self.max_frames, self.flags, self.device = n_streams, max_frames, flags, device
+        self._model = model
+        h = C.c_void_p()
+        rc = self.L.pnb_create(C.byref(h), n_streams, max_frames, C.addressof(model.as_c_model()), flags, device)
+        if rc != 0:
+            raise PnbError(f"pnb_create failed ({rc}): {self.L.pnb_last_error().decode()}")
+        self.h = h
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise PnbError(f"{what} failed ({rc}): {self.L.pnb_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pnb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self._ck(self.L.pnb_reset(self.h), "pnb_reset")
+
+    def process(self, x: np.ndarray, want_gr: bool = False):
+        """x: [S, F*480] float32 (C-API scale) or int16 (CLI wire format) host array.
+        Returns (out like x, gr [F, S, 68] or None)."""
+        assert x.ndim == 2 and x.shape[0] == self.n_streams and x.shape[1] % FRAME == 0
+        F = x.shape[1] // FRAME
+        x = np.ascontiguousarray(x)
+        out = np.empty_like(x)
+        gr = np.empty((F, self.n_streams, 68), np.float32) if want_gr else None
+        grp = gr.ctypes.data if want_gr else None
+        if x.dtype == np.float32:
+            rc = self.L.pnb_process_host_f32(self.h, x.ctypes.data, x.shape[1], out.ctypes.data, x.shape[1], F, grp)
+        elif x.dtype == np.int16:
+            rc = self.L.pnb_process_host_i16(self.h, x.ctypes.data, x.shape[1], out.ctypes.data, x.shape[1], F, grp)
+        else:
+            raise TypeError("x must be float32 or int16")
+        self._ck(rc, "pnb_process_host")
+        return out, gr
+
+    def process_stream_chunks(self, x: np.ndarray, want_gr: bool = False):
+        """Any number of hops: walks x in calls of at most max_frames hops."""
+        F = x.shape[1] // FRAME
+        outs, grs = [], []
+        for t0 in range(0, F, self.max_frames):
+            t1 = min(F, t0 + self.max_frames)
+            o, g = self.process(x[:, t0 * FRAME:t1 * FRAME], want_gr)
+            outs.append(o)
+            grs.append(g)
+        return np.concatenate(outs, axis=1), (np.concatenate(grs, axis=0) if want_gr else None)
+
+    def process_device(self, d_in: int, in_stride: int, d_out: int, out_stride: int, n_frames: int,
+                       d_gr: int = 0, stream: int = 0, int16: bool = False):
+        f = self.L.pnb_process_device_i16 if int16 else self.L.pnb_process_device_f32
+        self._ck(f(self.h, d_in, in_stride, d_out, out_stride, n_frames, d_gr or None, stream or None),
+                 "pnb_process_device")
+
+    def read_tap(self, name: str, n_frames: int) -> np.ndarray:
+        code, dt, width = TAPS[name]
+        a = np.empty((n_frames, self.n_streams, width), dt)
+        self._ck(self.L.pnb_read_tap(self.h, code, a.ctypes.data, a.nbytes), f"pnb_read_tap({name})")
+        return a
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.pnb_launch_count(self.h))
+
+    def launches_per_call(self, n_frames: int) -> int:
+        return int(self.L.pnb_launches_per_call(self.h, n_frames))

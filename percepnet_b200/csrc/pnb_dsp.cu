@@ -1,0 +1,754 @@
+// pnb_dsp.cu -- analysis and synthesis kernels of the PercepNet hot path for sm_100a.
+//
+// One warp owns one utterance stream and walks the hops of the call in order, carrying the
+// per-stream scalar state (last pitch period / gain, overlap-add memory) in registers.
+// What it replaces in the reference (paths relative to /root/reference/src):
+//   analysis_kernel : compute_frame_features (denoise.cpp:372-434), frame_analysis (:333),
+//                     apply_window (:282), forward_transform (:291) + opus_fft_c (kiss_fft.cpp:566),
+//                     compute_band_energy/corr (:89,:125), pitch_downsample / pitch_search /
+//                     remove_doubling (pitch.cpp:148,283,424), _celt_autocorr/_celt_lpc
+//                     (celt_lpc.cpp:198,37), comb filter (:416-427), compute_lookahead_band_energy
+//                     (:498), create_features (:487)
+//   synthesis_kernel: pitch_filter (:436), interp_band_gain (:162), gain apply (:539-544),
+//                     post_filtering (:216), frame_synthesis (:352) + inverse_transform (:306)
+//
+// Numerics: this translation unit is compiled with -fmad=false and every decision-critical sum is a
+// strict ascending multiply-then-add chain, so pitch decisions, spectra and features are bit-identical
+// to the reference (whose objects contain no FMA and no re-associated sums).
+// The two double-precision islands (denoise.cpp:427, celt_lpc.cpp:61) run in fp64 here as well.
+#include "pnb_kernels.h"
+
+namespace pnb {
+
+// ------------------------------------------------------------------------------------------
+// warp-level FFT-960 over a shared-memory line (kiss_fft.cpp:518-586: factors 5,3,4,4,4 executed
+// as radix-4 (m=1,4,16), radix-3 (m=64), radix-5 (m=192) on a digit-reversed, 1/960-scaled input)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// position of input sample i after the digit reversal of the 5.3.4.4.4 factorisation
+__device__ __forceinline__ int fft_slot(int i) {
+  int n0 = i % 5; i /= 5;
+  int n1 = i % 3; i /= 3;
+  int n2 = i & 3; i >>= 2;
+  int n3 = i & 3; i >>= 2;
+  return 192 * n0 + 64 * n1 + 16 * n2 + 4 * n3 + i;
+}
+
+__device__ void fft960_warp(float2 *f, const float2 *tw, int lane) {
+  __syncwarp();
+  // radix-4, m = 1: 240 butterflies on adjacent quads (kiss_fft.cpp:112-131)
+  for (int b = lane; b < 240; b += 32) {
+    float2 *q = f + 4 * b;
+    float2 a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3];
+    float2 d02 = csub(a0, a2);
+    a0 = cadd(a0, a2);
+    float2 s13 = cadd(a1, a3);
+    a2 = csub(a0, s13);
+    a0 = cadd(a0, s13);
+    float2 d13 = csub(a1, a3);
+    q[0] = a0;
+    q[2] = a2;
+    q[1] = make_float2(d02.x + d13.y, d02.y - d13.x);
+    q[3] = make_float2(d02.x - d13.y, d02.y + d13.x);
+  }
+  __syncwarp();
+  // radix-4 with twiddles, m = 4 (60 groups, twiddle stride 60) then m = 16 (15 groups, stride 15)
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    const int m = pass ? 16 : 4, tws = pass ? 15 : 60, sh = pass ? 4 : 2;
+    for (int q = lane; q < 240; q += 32) {
+      int g = q >> sh, j = q & (m - 1);
+      float2 *p = f + g * 4 * m + j;
+      float2 a = cmul(p[m], tw[j * tws]);
+      float2 b = cmul(p[2 * m], tw[2 * j * tws]);
+      float2 c = cmul(p[3 * m], tw[3 * j * tws]);
+      float2 f0 = p[0];
+      float2 d0b = csub(f0, b);
+      f0 = cadd(f0, b);
+      float2 sac = cadd(a, c);
+      float2 dac = csub(a, c);
+      p[2 * m] = csub(f0, sac);
+      p[0] = cadd(f0, sac);
+      p[m] = make_float2(d0b.x + dac.y, d0b.y - dac.x);
+      p[3 * m] = make_float2(d0b.x - dac.y, d0b.y + dac.x);
+    }
+    __syncwarp();
+  }
+  // radix-3, m = 64, 5 groups, twiddle stride 5 (kiss_fft.cpp:173-228); epi3 = tw[320]
+  {
+    const float w3i = tw[320].y;
+    for (int q = lane; q < 320; q += 32) {
+      int g = q >> 6, j = q & 63;
+      float2 *p = f + g * 192 + j;
+      float2 a = cmul(p[64], tw[j * 5]);
+      float2 b = cmul(p[128], tw[j * 10]);
+      float2 s = cadd(a, b);
+      float2 d = csub(a, b);
+      float2 f0 = p[0];
+      float2 f1 = make_float2(f0.x - s.x * .5f, f0.y - s.y * .5f);
+      d.x *= w3i;
+      d.y *= w3i;
+      p[0] = cadd(f0, s);
+      p[128] = make_float2(f1.x + d.y, f1.y - d.x);
+      p[64] = make_float2(f1.x - d.y, f1.y + d.x);
+    }
+  }
+  __syncwarp();
+  // radix-5, m = 192, twiddle stride 1 (kiss_fft.cpp:232-305); ya = tw[192], yb = tw[384]
+  {
+    const float2 ya = tw[192], yb = tw[384];
+    for (int u = lane; u < 192; u += 32) {
+      float2 z0 = f[u];
+      float2 z1 = cmul(f[u + 192], tw[u]);
+      float2 z2 = cmul(f[u + 384], tw[2 * u]);
+      float2 z3 = cmul(f[u + 576], tw[3 * u]);
+      float2 z4 = cmul(f[u + 768], tw[4 * u]);
+      float2 s14 = cadd(z1, z4), d14 = csub(z1, z4);
+      float2 s23 = cadd(z2, z3), d23 = csub(z2, z3);
+      f[u] = make_float2(z0.x + (s14.x + s23.x), z0.y + (s14.y + s23.y));
+      float2 p = make_float2(z0.x + (s14.x * ya.x + s23.x * yb.x), z0.y + (s14.y * ya.x + s23.y * yb.x));
+      float2 q = make_float2(d14.y * ya.y + d23.y * yb.y, -(d14.x * ya.y + d23.x * yb.y));
+      f[u + 192] = csub(p, q);
+      f[u + 768] = cadd(p, q);
+      p = make_float2(z0.x + (s14.x * yb.x + s23.x * ya.x), z0.y + (s14.y * yb.x + s23.y * ya.x));
+      q = make_float2(d23.y * ya.y - d14.y * yb.y, d14.x * yb.y - d23.x * ya.y);
+      f[u + 384] = cadd(p, q);
+      f[u + 576] = csub(p, q);
+    }
+  }
+  __syncwarp();
+}
+
+// window a real 960-sample block (denoise.cpp:282-289) and place it, scaled by 1/960, in FFT order
+__device__ __forceinline__ void load_real_windowed(float2 *f, const float *src, const float *hw, int lane) {
+  const float scale = 1.f / kWin;
+  for (int i = lane; i < kWin; i += 32) {
+    float w = hw[i < kFrame ? i : kWin - 1 - i];
+    float v = src[i] * w;
+    f[fft_slot(i)] = make_float2(scale * v, 0.f);
+  }
+}
+
+// ERB band pooling (denoise.cpp:89-123 / 125-160): v[bin] is |X|^2 or Re(X conj P) for bins 0..399.
+// Accumulator b receives, in the reference's order, first the frac-weighted bins of band b-1 and then
+// the (1-frac)-weighted bins of band b; ends are doubled.
+__device__ void band_pool_warp(const float *v, float *out, const float *frac, const float *omf,
+                               const short *border, int lane) {
+  __syncwarp();
+  for (int b = lane; b < kBands; b += 32) {
+    float acc = 0.f;
+    if (b > 0) {
+      int lo = border[b - 1], hi = border[b];
+      for (int k = lo; k < hi; k++) acc = acc + frac[k] * v[k];
+    }
+    if (b < kBands - 1) {
+      int lo = border[b], hi = border[b + 1];
+      for (int k = lo; k < hi; k++) acc = acc + omf[k] * v[k];
+    }
+    if (b == 0 || b == kBands - 1) acc *= 2;
+    out[b] = acc;
+  }
+  __syncwarp();
+}
+
+// pitch.cpp:46-104 (float build): best two lags by xcorr^2/Syy with the reference's update rule.
+// y has element stride `ys` in shared memory.  Runs on one lane.
+__device__ void best_two(const float *xcorr, const float *y, int ys, int len, int max_pitch, float syy,
+                         int &b0, int &b1) {
+  float num0 = -1.f, num1 = -1.f, den0 = 0.f, den1 = 0.f;
+  b0 = 0;
+  b1 = 1;
+  for (int i = 0; i < max_pitch; i++) {
+    float xc = xcorr[i];
+    if (xc > 0.f) {
+      float c = xc * 1e-12f;
+      float num = c * c;
+      if (num * den1 > num1 * syy) {
+        if (num * den0 > num0 * syy) {
+          num1 = num0; den1 = den0; b1 = b0;
+          num0 = num;  den0 = syy;  b0 = i;
+        } else {
+          num1 = num; den1 = syy; b1 = i;
+        }
+      }
+    }
+    float yn = y[(i + len) * ys], yo = y[i * ys];
+    syy = syy + (yn * yn - yo * yo);
+    syy = 1.f > syy ? 1.f : syy;
+  }
+}
+
+__device__ __forceinline__ float pitch_gain(float xy, float xx, float yy) {
+  return xy / sqrtf(1.f + xx * yy);  // pitch.cpp:417-420 (float sqrt overload)
+}
+
+struct WarpSmem {
+  float2 fft[kWin];    // FFT work line
+  float lp[kLp];       // decimated, whitened pitch buffer
+  float xc[400];       // xcorr (147 / 294) -- doubles as the per-bin scratch of band pooling
+  float yy[392];       // yy_lookup of remove_doubling (385 used)
+  float Ex[kBands], Ep[kBands], Exp[kBands], Ey[kBands];
+  float cand_xy[32];   // per-candidate cross products of remove_doubling
+};
+
+struct BlockSmem {
+  float2 tw[kWin];
+  float hw[kFrame];
+  float frac[kBins];
+  float omf[kBins];
+  short border[kBands + 2];
+  float comb_w[8];
+};
+
+constexpr int kAnaWarps = 4;
+
+__global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BlockSmem &B = *reinterpret_cast<BlockSmem *>(smem_raw);
+  WarpSmem *Wall = reinterpret_cast<WarpSmem *>(smem_raw + ((sizeof(BlockSmem) + 15) / 16) * 16);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const Tables *T = A.tab;
+  for (int i = threadIdx.x; i < kWin; i += blockDim.x) B.tw[i] = T->tw[i];
+  for (int i = threadIdx.x; i < kFrame; i += blockDim.x) B.hw[i] = T->half_window[i];
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) { B.frac[i] = T->frac[i]; B.omf[i] = T->omf[i]; }
+  if (threadIdx.x < kBands + 2) B.border[threadIdx.x] = T->border[threadIdx.x];
+  if (threadIdx.x < 8) B.comb_w[threadIdx.x] = T->comb_w[threadIdx.x];
+  __syncthreads();
+
+  const int s = blockIdx.x * kAnaWarps + wib;
+  if (s >= A.n_streams) return;
+  WarpSmem &W = Wall[wib];
+  const float *row = A.pcm + (size_t)s * A.pcm_stride;
+  int last_period = A.last_period[s];
+  float last_gain = A.last_gain[s];
+
+  for (int t = 0; t < A.n_frames; t++) {
+    const float *line = row + (size_t)t * kFrame;  // line[j] == reference comb_buf[j] at this hop
+    const size_t fs = (size_t)t * A.n_streams + s;
+
+    // ---- analysis spectrum X of the hop delayed by five (denoise.cpp:402, :333-346) ----
+    load_real_windowed(W.fft, line + kOffAnalysis, B.hw, lane);
+    fft960_warp(W.fft, B.tw, lane);
+    {
+      float2 *Xg = A.X + fs * kBins;
+      for (int k = lane; k < kBins; k += 32) {
+        float2 x = W.fft[k];
+        Xg[k] = x;
+        float e = x.x * x.x;
+        e += x.y * x.y;
+        W.xc[k] = e;
+      }
+      band_pool_warp(W.xc, W.Ex, B.frac, B.omf, B.border, lane);
+    }
+
+    // ---- look-ahead band energies from the newest 960 samples (denoise.cpp:498-506) ----
+    load_real_windowed(W.fft, line + kOffLook, B.hw, lane);
+    fft960_warp(W.fft, B.tw, lane);
+    for (int k = lane; k < kBins; k += 32) {
+      float2 x = W.fft[k];
+      float e = x.x * x.x;
+      e += x.y * x.y;
+      W.xc[k] = e;
+    }
+    band_pool_warp(W.xc, W.Ey, B.frac, B.omf, B.border, lane);
+
+    // ---- pitch_downsample (pitch.cpp:148-216) ----
+    {
+      const float *src = line + kOffPitch;
+      for (int i = lane; i < kLp; i += 32) {
+        float v;
+        if (i == 0) v = .5f * (.5f * src[1] + src[0]);
+        else v = .5f * (.5f * (src[2 * i - 1] + src[2 * i + 1]) + src[2 * i]);
+        W.lp[i] = v;
+      }
+      __syncwarp();
+      // autocorrelation, 5 lags: bulk over 860 samples then the 4-sample tail (celt_lpc.cpp:250-256)
+      float ac = 0.f;
+      if (lane < 5) {
+        const float *a = W.lp, *b = W.lp + lane;
+#pragma unroll 4
+        for (int j = 0; j < 860; j++) ac = ac + a[j] * b[j];
+        float d = 0.f;
+        for (int i = lane + 860; i < kLp; i++) d = d + W.lp[i] * W.lp[i - lane];
+        ac += d;
+      }
+      float ac0 = __shfl_sync(0xffffffffu, ac, 0), ac1 = __shfl_sync(0xffffffffu, ac, 1),
+            ac2 = __shfl_sync(0xffffffffu, ac, 2), ac3 = __shfl_sync(0xffffffffu, ac, 3),
+            ac4 = __shfl_sync(0xffffffffu, ac, 4);
+      float fir0 = 0, fir1 = 0, fir2 = 0, fir3 = 0, fir4 = 0;
+      if (lane == 0) {
+        float a[5] = {ac0, ac1, ac2, ac3, ac4};
+        a[0] *= 1.0001f;                                                        // pitch.cpp:190
+        for (int i = 1; i <= 4; i++) a[i] -= a[i] * (.008f * i) * (.008f * i);  // :199
+        float lpc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a[0] != 0.f) {  // Levinson, celt_lpc.cpp:53-83, the divide in double (:61)
+          float err = a[0];
+          for (int i = 0; i < 4; i++) {
+            float rr = 0.f;
+            for (int j = 0; j < i; j++) rr += lpc[j] * a[i - j];
+            rr += a[i + 1];
+            float r = (float)(-(double)rr / ((double)err + 0.00001));
+            lpc[i] = r;
+            for (int j = 0; j < (i + 1) >> 1; j++) {
+              float t1 = lpc[j], t2 = lpc[i - 1 - j];
+              lpc[j] = t1 + r * t2;
+              lpc[i - 1 - j] = t2 + r * t1;
+            }
+            err = err - (r * r) * err;
+            if (err < .001f * a[0]) break;
+          }
+        }
+        float tmp = 1.f;
+        for (int i = 0; i < 4; i++) { tmp = .9f * tmp; lpc[i] = lpc[i] * tmp; }  // :204-208
+        fir0 = lpc[0] + .8f;                                                     // :210-214
+        fir1 = lpc[1] + .8f * lpc[0];
+        fir2 = lpc[2] + .8f * lpc[1];
+        fir3 = lpc[3] + .8f * lpc[2];
+        fir4 = .8f * lpc[3];
+      }
+      fir0 = __shfl_sync(0xffffffffu, fir0, 0);
+      fir1 = __shfl_sync(0xffffffffu, fir1, 0);
+      fir2 = __shfl_sync(0xffffffffu, fir2, 0);
+      fir3 = __shfl_sync(0xffffffffu, fir3, 0);
+      fir4 = __shfl_sync(0xffffffffu, fir4, 0);
+      // 5-tap FIR in place with zero history (pitch.cpp:106-145,154), walked from the end so the taps
+      // still see unfiltered samples
+      for (int base = kLp - 32; base >= 0; base -= 32) {
+        int i = base + lane;
+        float x0 = W.lp[i];
+        float m0 = i >= 1 ? W.lp[i - 1] : 0.f, m1 = i >= 2 ? W.lp[i - 2] : 0.f, m2 = i >= 3 ? W.lp[i - 3] : 0.f,
+              m3 = i >= 4 ? W.lp[i - 4] : 0.f, m4 = i >= 5 ? W.lp[i - 5] : 0.f;
+        float sum = x0;
+        sum = sum + fir0 * m0;
+        sum = sum + fir1 * m1;
+        sum = sum + fir2 * m2;
+        sum = sum + fir3 * m3;
+        sum = sum + fir4 * m4;
+        __syncwarp();
+        W.lp[i] = sum;
+        __syncwarp();
+      }
+    }
+
+    // ---- pitch_search (pitch.cpp:283-386): x = lp+384, y = lp, len 960, max_pitch 588 ----
+    int pitch_lag, T;
+    float pitch_corr, gain;
+    {
+      // coarse: 4x-decimated signals are stride-2 views of lp; lag L = lane + 32 q
+      float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      const bool syy_lane = (lane == 31);  // q = 4 is unused there (lag 159 > 146): it accumulates Syy
+      if (syy_lane) acc[4] = 1.f;
+      const float *x4 = W.lp + 384;
+#pragma unroll 2
+      for (int j = 0; j < 240; j++) {
+        float xj = x4[2 * j];
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[q] = acc[q] + xj * W.lp[2 * (j + lane + 32 * q)];
+        if (lane < 19) acc[4] = acc[4] + xj * W.lp[2 * (j + lane + 128)];
+        else if (syy_lane) { float y = W.lp[2 * j]; acc[4] = acc[4] + y * y; }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) W.xc[lane + 32 * q] = acc[q];
+      if (lane < 19) W.xc[lane + 128] = acc[4];
+      float syy_c = __shfl_sync(0xffffffffu, acc[4], 31);
+      __syncwarp();
+      int b0 = 0, b1 = 0;
+      if (lane == 0) best_two(W.xc, W.lp, 2, 240, 147, syy_c, b0, b1);
+      b0 = __shfl_sync(0xffffffffu, b0, 0);
+      b1 = __shfl_sync(0xffffffffu, b1, 0);
+      __syncwarp();
+      // fine: at most ten lags around 2*b0 and 2*b1 (pitch.cpp:344-361); lane 10 accumulates Syy of the
+      // second find_best_pitch, lane 11 the xx of remove_doubling (pitch.cpp:448)
+      for (int i = lane; i < 294; i += 32) W.xc[i] = 0.f;
+      __syncwarp();
+      int fl = -1;
+      if (lane < 5) fl = 2 * b0 - 2 + lane;
+      else if (lane < 10) fl = 2 * b1 - 2 + (lane - 5);
+      const bool fine_ok = (fl >= 0 && fl < 294);
+      float s = (lane == 10) ? 1.f : 0.f;
+      {
+        const float *a, *b;
+        int n = 480;
+        if (lane < 10) { a = W.lp + 384; b = W.lp + (fine_ok ? fl : 0); if (!fine_ok) n = 0; }
+        else if (lane == 10) { a = W.lp; b = W.lp; }
+        else if (lane == 11) { a = W.lp + 384; b = W.lp + 384; }
+        else { a = W.lp; b = W.lp; n = 0; }
+#pragma unroll 4
+        for (int j = 0; j < n; j++) s = s + a[j] * b[j];
+      }
+      if (fine_ok) W.xc[fl] = (-1.f > s) ? -1.f : s;
+      float syy_f = __shfl_sync(0xffffffffu, s, 10);
+      float xx = __shfl_sync(0xffffffffu, s, 11);
+      __syncwarp();
+      int off = 0;
+      float corr = 0.f;
+      if (lane == 0) {
+        int c0, c1;
+        best_two(W.xc, W.lp, 1, 480, 294, syy_f, c0, c1);
+        if (c0 > 0 && c0 < 293) {
+          float a = W.xc[c0 - 1], b = W.xc[c0], c = W.xc[c0 + 1];
+          if ((c - a) > .7f * (b - a)) off = 1;
+          else if ((a - c) > .7f * (b - c)) off = -1;
+        }
+        pitch_lag = 2 * c0 - off;
+        corr = W.xc[c0];
+      }
+      pitch_lag = __shfl_sync(0xffffffffu, pitch_lag, 0);
+      pitch_corr = __shfl_sync(0xffffffffu, corr, 0);
+
+      // ---- remove_doubling (pitch.cpp:423-527) with maxperiod 384, minperiod 30, N 480 ----
+      const int second_check[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};
+      const float *x = W.lp + 384;
+      int T0 = (kMaxPeriod - pitch_lag) / 2;
+      if (T0 >= 384) T0 = 383;
+      const int prev_period = last_period / 2;
+      // lane 0: xy at T0; lane 1: the yy_lookup recurrence; lanes 2..29: (k, which) = (2 + (lane-2)/2, (lane-2)&1)
+      {
+        int lag = -1;
+        if (lane == 0) lag = T0;
+        else if (lane >= 2 && lane < 30) {
+          int k = 2 + ((lane - 2) >> 1);
+          int T1 = (2 * T0 + k) / (2 * k);
+          if (T1 >= 30) {
+            if ((lane & 1) == 0) lag = T1;
+            else if (k == 2) lag = (T1 + T0 > 384) ? T0 : T0 + T1;
+            else lag = (2 * second_check[k] * T0 + k) / (2 * k);
+          }
+        }
+        if (lane == 1) {
+          float yy = xx;
+          W.yy[0] = xx;
+          for (int i = 1; i <= 384; i++) {
+            float a = x[-i], b = x[480 - i];
+            yy = yy + a * a - b * b;
+            W.yy[i] = 0.f > yy ? 0.f : yy;
+          }
+        } else {
+          float d = 0.f;
+          if (lag >= 0) {
+            const float *b = x - lag;
+#pragma unroll 4
+            for (int j = 0; j < 480; j++) d = d + x[j] * b[j];
+          }
+          W.cand_xy[lane] = d;
+        }
+      }
+      __syncwarp();
+      int Tsel = T0;
+      float g = 0.f, best_xy = 0.f, best_yy = 0.f;
+      if (lane == 0) {
+        float xy = W.cand_xy[0];
+        float yy = W.yy[T0];
+        best_xy = xy;
+        best_yy = yy;
+        float g0 = pitch_gain(xy, xx, yy);
+        g = g0;
+        for (int k = 2; k <= 15; k++) {
+          int T1 = (2 * T0 + k) / (2 * k);
+          if (T1 < 30) break;
+          int T1b;
+          if (k == 2) T1b = (T1 + T0 > 384) ? T0 : T0 + T1;
+          else T1b = (2 * second_check[k] * T0 + k) / (2 * k);
+          float xy1 = W.cand_xy[2 + 2 * (k - 2)], xy2 = W.cand_xy[3 + 2 * (k - 2)];
+          xy = .5f * (xy1 + xy2);
+          yy = .5f * (W.yy[T1] + W.yy[T1b]);
+          float g1 = pitch_gain(xy, xx, yy);
+          float cont;
+          int dT = T1 - prev_period;
+          dT = dT < 0 ? -dT : dT;
+          if (dT <= 1) cont = last_gain;
+          else if (dT <= 2 && 5 * k * k < T0) cont = .5f * last_gain;
+          else cont = 0.f;
+          float th = .7f * g0 - cont;
+          float thresh = .3f > th ? .3f : th;
+          if (T1 < 90) {
+            th = .85f * g0 - cont;
+            thresh = .4f > th ? .4f : th;
+          }  // the T1 < 2*minperiod branch of the reference is unreachable
+          if (g1 > thresh) { best_xy = xy; best_yy = yy; Tsel = T1; g = g1; }
+        }
+      }
+      Tsel = __shfl_sync(0xffffffffu, Tsel, 0);
+      // final +-1 refinement: three dot products around the selected period (pitch.cpp:512-513)
+      {
+        float d = 0.f;
+        if (lane < 3) {
+          const float *b = x - (Tsel + lane - 1);
+#pragma unroll 4
+          for (int j = 0; j < 480; j++) d = d + x[j] * b[j];
+        }
+        float x0 = __shfl_sync(0xffffffffu, d, 0), x1 = __shfl_sync(0xffffffffu, d, 1),
+              x2 = __shfl_sync(0xffffffffu, d, 2);
+        int Tout = 0;
+        float pg = 0.f;
+        if (lane == 0) {
+          best_xy = 0.f > best_xy ? 0.f : best_xy;
+          if (best_yy <= best_xy) pg = 1.f;
+          else pg = best_xy / (best_yy + 1.f);
+          int o2;
+          if ((x2 - x0) > .7f * (x1 - x0)) o2 = 1;
+          else if ((x0 - x2) > .7f * (x1 - x2)) o2 = -1;
+          else o2 = 0;
+          if (pg > g) pg = g;
+          Tout = 2 * Tsel + o2;
+          if (Tout < kMinPeriod) Tout = kMinPeriod;
+        }
+        T = __shfl_sync(0xffffffffu, Tout, 0);
+        gain = __shfl_sync(0xffffffffu, pg, 0);
+      }
+      last_period = T;
+      last_gain = gain;
+    }
+
+    // ---- comb-filtered block, its spectrum P and the band statistics (denoise.cpp:416-427) ----
+    {
+      const float scale = 1.f / kWin;
+      for (int i = lane; i < kWin; i += 32) {
+        float p = 0.f;
+#pragma unroll
+        for (int k = -3; k <= 3; k++) p = p + line[kOffAnalysis - T * k + i] * B.comb_w[k + 3];
+        float w = B.hw[i < kFrame ? i : kWin - 1 - i];
+        float v = p * w;
+        W.fft[fft_slot(i)] = make_float2(scale * v, 0.f);
+      }
+      fft960_warp(W.fft, B.tw, lane);
+      float2 *Pg = A.P + fs * kBins;
+      const float2 *Xg = A.X + fs * kBins;
+      for (int k = lane; k < kBins; k += 32) {
+        float2 p = W.fft[k];
+        Pg[k] = p;
+        float e = p.x * p.x;
+        e += p.y * p.y;
+        W.xc[k] = e;
+      }
+      band_pool_warp(W.xc, W.Ep, B.frac, B.omf, B.border, lane);
+      for (int k = lane; k < kBins; k += 32) {
+        float2 p = W.fft[k], x = Xg[k];  // Xg was written by this warp above (same lanes, same k)
+        float e = x.x * p.x;
+        e += x.y * p.y;
+        W.xc[k] = e;
+      }
+      band_pool_warp(W.xc, W.Exp, B.frac, B.omf, B.border, lane);
+    }
+
+    // ---- features (denoise.cpp:427-433, 487-496, 528-530) ----
+    {
+      float *F = A.feat + fs * kFeat;
+      for (int b = lane; b < kBands; b += 32) {
+        float prod = W.Ex[b] * W.Ep[b];                       // float product, then double (H4)
+        double v = (double)W.Exp[b] / sqrt(1e-15 + (double)prod);
+        v = fmax(0.0, v);
+        float coh = (float)fmin(1.0, v);
+        F[b] = W.Ey[b] * 30.f;
+        F[kBands + b] = coh * 30.f;
+      }
+      if (lane == 0) {
+        float E = 0.f;
+        for (int b = 0; b < kBands; b++) E += W.Ex[b];
+        int silence = ((double)E < 0.1) ? 1 : 0;
+        A.silence[fs] = (unsigned char)silence;
+        F[68] = (float)T / 588.f;
+        F[69] = pitch_corr;
+        if (A.tap_pitch) {
+          int *tp = A.tap_pitch + fs * 4;
+          tp[0] = pitch_lag; tp[1] = T; tp[2] = silence; tp[3] = 0;
+          A.tap_pitchf[fs * 2] = pitch_corr;
+          A.tap_pitchf[fs * 2 + 1] = gain;
+        }
+      }
+      if (A.Ex) for (int b = lane; b < kBands; b += 32) A.Ex[fs * kBands + b] = W.Ex[b];
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    A.last_period[s] = last_period;
+    A.last_gain[s] = last_gain;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// synthesis: per-bin gains from band values, optional comb mix, inverse transform, overlap-add
+// ------------------------------------------------------------------------------------------
+struct SynWarpSmem {
+  float2 fft[kWin];
+  float g[kBands], r[kBands], ir[kBands], gw[kBands];
+};
+struct SynBlockSmem {
+  float2 tw[kWin];
+  float hw[kFrame];
+  float frac[kBins];
+  float omf[kBins];
+  short band_of[kBins];
+};
+constexpr int kSynWarps = 4;
+
+__global__ void __launch_bounds__(kSynWarps * 32) synthesis_kernel(SynthesisArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SynBlockSmem &B = *reinterpret_cast<SynBlockSmem *>(smem_raw);
+  SynWarpSmem *Wall = reinterpret_cast<SynWarpSmem *>(smem_raw + ((sizeof(SynBlockSmem) + 15) / 16) * 16);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const Tables *T = A.tab;
+  for (int i = threadIdx.x; i < kWin; i += blockDim.x) B.tw[i] = T->tw[i];
+  for (int i = threadIdx.x; i < kFrame; i += blockDim.x) B.hw[i] = T->half_window[i];
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
+    B.frac[i] = T->frac[i];
+    B.omf[i] = T->omf[i];
+    B.band_of[i] = T->band_of[i];
+  }
+  __syncthreads();
+  const int s = blockIdx.x * kSynWarps + wib;
+  if (s >= A.n_streams) return;
+  SynWarpSmem &W = Wall[wib];
+
+  float mem[15];  // overlap-add memory: samples lane + 32 i  (denoise.cpp:75,357-358)
+#pragma unroll
+  for (int i = 0; i < 15; i++) mem[i] = A.synth_mem[(size_t)s * kFrame + lane + 32 * i];
+
+  for (int t = 0; t < A.n_frames; t++) {
+    const size_t fs = (size_t)t * A.n_streams + s;
+    const float *gr = A.gr + fs * 68;
+    for (int b = lane; b < kBands; b += 32) {
+      float g = gr[b], r = gr[kBands + b];
+      W.g[b] = g;
+      W.r[b] = r;
+      W.ir[b] = 1.f - r;
+    }
+    __syncwarp();
+    if (A.postfilter) {  // denoise.cpp:216-250 applied to g (envelope post-filter, beta = 0.02)
+      const float *Ey = A.Ex + fs * kBands;
+      for (int b = lane; b < kBands; b += 32) W.gw[b] = W.g[b] * sinf((float)(M_PI / 2 * (double)W.g[b]));
+      __syncwarp();
+      float G = 0.f;
+      if (lane == 0) {
+        float e0 = 0.f, e1 = 0.f;
+        for (int b = 0; b < kBands; b++) e0 += W.g[b] * Ey[b];
+        for (int b = 0; b < kBands; b++) e1 += W.gw[b] * Ey[b];
+        float q = e0 / (e1 + 1e-6f);
+        G = sqrtf(((1.f + 0.02f) * q) / (1.f + 0.02f * (q * q)));
+      }
+      G = __shfl_sync(0xffffffffu, G, 0);
+      for (int b = lane; b < kBands; b += 32) W.g[b] = G * W.gw[b];
+      __syncwarp();
+    }
+    const bool silence = A.silence[fs] != 0;
+    const float2 *Xg = A.X + fs * kBins, *Pg = A.P + fs * kBins;
+    const float scale = 1.f / kWin;
+    // bins 0..399 and their mirror images; everything from 400 to 560 is zero
+    for (int i = lane; i < kWin; i += 32) {
+      int k = i <= kFrame ? i : kWin - i;
+      float2 v = make_float2(0.f, 0.f);
+      if (k < kBins) {
+        float2 x = Xg[k];
+        int b = B.band_of[k];
+        float fr = B.frac[k], om = B.omf[k];
+        if (!silence) {  // pitch_filter, denoise.cpp:436-485
+          float rf = om * W.ir[b] + fr * W.ir[b + 1];
+          x.x = rf * x.x;
+          x.y = rf * x.y;
+          rf = om * W.r[b] + fr * W.r[b + 1];
+          float2 p = Pg[k];
+          x.x += rf * p.x;
+          x.y += rf * p.y;
+        }
+        float gf = om * W.g[b] + fr * W.g[b + 1];  // interp_band_gain + gain apply, :539-544
+        x.x *= gf;
+        x.y *= gf;
+        v = (i <= kFrame) ? x : make_float2(x.x, -x.y);  // Hermitian extension, :314-317
+      }
+      W.fft[fft_slot(i)] = make_float2(scale * v.x, scale * v.y);
+    }
+    fft960_warp(W.fft, B.tw, lane);
+    // time samples are read back reversed and rescaled (denoise.cpp:318-323), windowed, overlap-added
+    float *outp = A.out ? A.out + (size_t)s * A.out_stride + (size_t)t * kFrame : nullptr;
+    short *outs = A.out16 ? A.out16 + (size_t)s * A.out_stride + (size_t)t * kFrame : nullptr;
+#pragma unroll
+    for (int i = 0; i < 15; i++) {
+      int n = lane + 32 * i;
+      float a = (float)kWin * W.fft[(kWin - n) % kWin].x;
+      a = a * B.hw[n];
+      float o = a + mem[i];
+      if (outp) outp[n] = o;
+      if (outs) outs[n] = (short)(int)(o * 32768.f);  // main.cpp:36: truncation toward zero
+      int n2 = n + kFrame;
+      float c = (float)kWin * W.fft[kWin - n2].x;
+      mem[i] = c * B.hw[kWin - 1 - n2];
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < 15; i++) A.synth_mem[(size_t)s * kFrame + lane + 32 * i] = mem[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// staging: append the new hops to each stream's PCM line / slide the history forward
+// ------------------------------------------------------------------------------------------
+__global__ void stage_in_kernel(float *pcm, size_t pcm_stride, const float *in, const short *in16, size_t in_stride,
+                                int n_streams, int n_samples) {
+  const int s = blockIdx.y;
+  float *dst = pcm + (size_t)s * pcm_stride + kKeep;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_samples; i += gridDim.x * blockDim.x) {
+    float v;
+    if (in) v = in[(size_t)s * in_stride + i];
+    else v = ((float)in16[(size_t)s * in_stride + i]) / 32768.f;  // main.cpp:34
+    dst[i] = v;
+  }
+}
+
+// keep the last 5280 samples of the line for the next call.  One block per stream; the tail is read
+// into registers before anything is overwritten.
+__global__ void __launch_bounds__(512) slide_history_kernel(float *pcm, size_t pcm_stride, int n_samples) {
+  float *row = pcm + (size_t)blockIdx.x * pcm_stride;
+  constexpr int kPer = (kKeep + 511) / 512;
+  float keep[kPer];
+#pragma unroll
+  for (int i = 0; i < kPer; i++) {
+    int j = threadIdx.x + 512 * i;
+    keep[i] = j < kKeep ? row[n_samples + j] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kPer; i++) {
+    int j = threadIdx.x + 512 * i;
+    if (j < kKeep) row[j] = keep[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------- launchers
+static size_t analysis_smem_bytes() { return ((sizeof(BlockSmem) + 15) / 16) * 16 + kAnaWarps * sizeof(WarpSmem); }
+static size_t synthesis_smem_bytes() { return ((sizeof(SynBlockSmem) + 15) / 16) * 16 + kSynWarps * sizeof(SynWarpSmem); }
+
+cudaError_t dsp_configure() {
+  cudaError_t e = cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)analysis_smem_bytes());
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)synthesis_smem_bytes());
+}
+
+int launch_analysis(const AnalysisArgs &a, cudaStream_t st) {
+  dim3 grid((a.n_streams + kAnaWarps - 1) / kAnaWarps);
+  analysis_kernel<<<grid, kAnaWarps * 32, analysis_smem_bytes(), st>>>(a);
+  return 1;
+}
+int launch_synthesis(const SynthesisArgs &a, cudaStream_t st) {
+  dim3 grid((a.n_streams + kSynWarps - 1) / kSynWarps);
+  synthesis_kernel<<<grid, kSynWarps * 32, synthesis_smem_bytes(), st>>>(a);
+  return 1;
+}
+int launch_stage_in(float *pcm, size_t pcm_stride, const float *in, const short *in16, size_t in_stride,
+                    int n_streams, int n_samples, cudaStream_t st) {
+  dim3 grid((n_samples + 1023) / 1024 > 8 ? 8 : (n_samples + 1023) / 1024, n_streams);
+  stage_in_kernel<<<grid, 256, 0, st>>>(pcm, pcm_stride, in, in16, in_stride, n_streams, n_samples);
+  return 1;
+}
+int launch_slide_history(float *pcm, size_t pcm_stride, int n_streams, int n_samples, cudaStream_t st) {
+  slide_history_kernel<<<n_streams, 512, 0, st>>>(pcm, pcm_stride, n_samples);
+  return 1;
+}
+
+}  // namespace pnb

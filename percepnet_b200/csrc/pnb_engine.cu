@@ -1,0 +1,488 @@
+// pnb_engine.cu -- host side of the C-ABI (include/percepnet_b200.h): engine lifetime, weight ingest
+// from the reference's RNNModel layout, constant tables, and the per-call kernel schedule.
+//
+// Schedule of one pnb_process_* call with F hops on S streams:
+//   stage_in -> analysis (all F hops; one warp per stream) -> F x network step -> synthesis -> slide history
+// The network step is the only part that is sequential in time across the batch; analysis and synthesis
+// need no network state, so hops are processed F at a time.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <stddef.h>
+#include <string>
+#include <vector>
+
+#include "../../include/percepnet_b200.h"
+#include "pnb_engine.h"
+
+using namespace pnb;
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) return fail(PNB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char *pnb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *pnb_version(void) { return "percepnet_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------
+// constant tables, with the reference's own expressions so that they round identically
+// ------------------------------------------------------------------------------------------
+static void build_tables(Tables &t) {
+  memset(&t, 0, sizeof t);
+  for (int i = 0; i < kFrame; i++) {  // denoise.cpp:191-192
+    double a = .5 * M_PI * (i + .5) / kFrame;
+    t.half_window[i] = (float)sin(.5 * M_PI * sin(a) * sin(a));
+  }
+  {  // denoise.cpp:200-206: float running sum
+    float acc = 0;
+    for (int i = 1; i < 8; i++) {
+      t.comb_w[i - 1] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * i / 8));
+      acc += t.comb_w[i - 1];
+    }
+    for (int i = 0; i < 7; i++) t.comb_w[i] /= acc;
+  }
+  for (int i = 0; i < kWin; i++) {  // kiss_fft.cpp:415-419
+    const double pi = 3.14159265358979323846264338327;
+    double ph = (-2 * pi / kWin) * i;
+    t.tw[i].x = (float)cos(ph);
+    t.tw[i].y = (float)sin(ph);
+  }
+  {  // erbband.h:34-99 with (960, 32, 0, 20000), denoise.cpp:87
+    auto hz2erb = [](float hz) { return (float)(9.265 * log(1 + hz / (24.7 * 9.265))); };
+    auto erb2hz = [](float e) { return (float)(24.7 * 9.265 * (exp(e / 9.265) - 1)); };
+    float lo = hz2erb(0.f), hi = hz2erb(20000.f), step = (hi - lo) / (34.f - 1);
+    int border[kBands];
+    for (int i = 0; i < kBands; i++) {
+      float cut = erb2hz(i < kBands - 1 ? lo + step * i : hi);
+      border[i] = (int)((cut + 25) / 50.f);
+    }
+    for (int i = 0; i < kBands - 2; i++)
+      if (border[i + 1] - border[i] < 2) border[i + 1] += 2 - (border[i + 1] - border[i]);
+    for (int i = 0; i < kBands; i++) t.border[i] = (short)border[i];
+    t.border[kBands] = t.border[kBands + 1] = (short)border[kBands - 1];
+    for (int b = 0; b < kBands - 1; b++) {
+      int width = border[b + 1] - border[b];
+      for (int j = 0; j < width; j++) {
+        int bin = border[b] + j;
+        if (bin >= kBins) continue;
+        float frac = (float)j / width;  // denoise.cpp:99
+        t.frac[bin] = frac;
+        t.omf[bin] = 1 - frac;
+        t.band_of[bin] = (short)b;
+      }
+    }
+  }
+  // tansig_table.h: tanh(0.04 i) to six decimals; the three entries where the shipped table is not the
+  // correctly rounded value carry the shipped value
+  for (int i = 0; i <= 200; i++) t.tansig[i] = (float)(floor(tanh(0.04 * i) * 1e6 + 0.5) / 1e6);
+  t.tansig[70] = 0.992631f;
+  t.tansig[170] = 0.999997f;
+  t.tansig[190] = 1.000000f;
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t dalloc(T **p, size_t n, bool zero = true) {
+  cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (zero) return cudaMemset(*p, 0, n * sizeof(T));
+  return cudaSuccess;
+}
+static cudaError_t upload(float **dst, const float *src, size_t n) {
+  cudaError_t e = cudaMalloc((void **)dst, n * sizeof(float));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice);
+}
+
+static int check_model(const pnb_model *m) {
+  if (!m || !m->fc || !m->conv1 || !m->conv2 || !m->gru1 || !m->gru2 || !m->gru3 || !m->gru_gb || !m->gru_rb ||
+      !m->fc_gb || !m->fc_rb)
+    return fail(PNB_ERR_ARG, "model or one of its ten layers is NULL");
+  // the architecture the hot path is built for (rnn_train.py:111-121, rnn.cpp:42-81)
+  bool ok = m->fc->nb_inputs == 70 && m->fc->nb_neurons == 128 && m->conv1->nb_inputs == 128 &&
+            m->conv1->kernel_size == 5 && m->conv1->nb_neurons == 512 && m->conv2->nb_inputs == 512 &&
+            m->conv2->kernel_size == 3 && m->conv2->nb_neurons == 512 && m->gru_rb->nb_inputs == 1024 &&
+            m->gru_rb->nb_neurons == 128 && m->fc_gb->nb_inputs == 2560 && m->fc_gb->nb_neurons == 34 &&
+            m->fc_rb->nb_inputs == 128 && m->fc_rb->nb_neurons == 34;
+  const pnb_gru_layer *g4[4] = {m->gru1, m->gru2, m->gru3, m->gru_gb};
+  for (int i = 0; i < 4; i++) ok = ok && g4[i]->nb_inputs == 512 && g4[i]->nb_neurons == 512;
+  const pnb_gru_layer *g5[5] = {m->gru1, m->gru2, m->gru3, m->gru_gb, m->gru_rb};
+  for (int i = 0; i < 5; i++) ok = ok && g5[i]->reset_after == 1 && g5[i]->activation == PNB_ACT_TANH;
+  if (!ok) return fail(PNB_ERR_ARG, "model dimensions are not PercepNet's (70-128-conv5x512-conv3x512-4xGRU512-GRU128-34/34)");
+  return PNB_OK;
+}
+
+extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const pnb_model *model, unsigned flags,
+                          int device) {
+  if (!out) return fail(PNB_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (n_streams < 1 || max_frames < 1) return fail(PNB_ERR_ARG, "n_streams and max_frames_per_call must be >= 1");
+  int rc = check_model(model);
+  if (rc) return rc;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(PNB_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU path",
+                ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail(PNB_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(PNB_ERR_NO_DEVICE, "device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major,
+                prop.minor);
+
+  pnb_engine *e = new pnb_engine();
+  e->S = n_streams;
+  e->Fmax = max_frames;
+  e->device = device;
+  e->flags = flags;
+  e->sm_count = prop.multiProcessorCount;
+  const size_t S = n_streams, F = max_frames;
+#define CKD(call)                                                                                   \
+  do {                                                                                              \
+    cudaError_t _e = (call);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      int _rc = fail(_e == cudaErrorMemoryAllocation ? PNB_ERR_ALLOC : PNB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); \
+      pnb_destroy(e);                                                                               \
+      return _rc;                                                                                   \
+    }                                                                                               \
+  } while (0)
+
+  CKD(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CKD(dsp_configure());
+  {
+    Tables *t = new Tables();
+    build_tables(*t);
+    cudaError_t r = cudaMalloc((void **)&e->d_tab, sizeof(Tables));
+    if (r == cudaSuccess) r = cudaMemcpy(e->d_tab, t, sizeof(Tables), cudaMemcpyHostToDevice);
+    delete t;
+    CKD(r);
+  }
+  // weights, in the reference's layout
+  CKD(upload(&e->fc.W, model->fc->input_weights, 70 * 128));
+  CKD(upload(&e->fc.b, model->fc->bias, 128));
+  CKD(upload(&e->conv1.W, model->conv1->input_weights, 5 * 128 * 512));
+  CKD(upload(&e->conv1.b, model->conv1->bias, 512));
+  CKD(upload(&e->conv2.W, model->conv2->input_weights, 3 * 512 * 512));
+  CKD(upload(&e->conv2.b, model->conv2->bias, 512));
+  const pnb_gru_layer *g5[5] = {model->gru1, model->gru2, model->gru3, model->gru_gb, model->gru_rb};
+  for (int i = 0; i < 5; i++) {
+    int M = g5[i]->nb_inputs, H = g5[i]->nb_neurons;
+    e->gru[i].M = M;
+    e->gru[i].H = H;
+    CKD(upload(&e->gru[i].W, g5[i]->input_weights, (size_t)M * 3 * H));
+    CKD(upload(&e->gru[i].U, g5[i]->recurrent_weights, (size_t)H * 3 * H));
+    CKD(upload(&e->gru[i].b, g5[i]->bias, 6 * (size_t)H));
+  }
+  CKD(upload(&e->fc_gb.W, model->fc_gb->input_weights, 2560 * 34));
+  CKD(upload(&e->fc_gb.b, model->fc_gb->bias, 34));
+  CKD(upload(&e->fc_rb.W, model->fc_rb->input_weights, 128 * 34));
+  CKD(upload(&e->fc_rb.b, model->fc_rb->bias, 34));
+  e->act_fc = model->fc->activation;
+  e->act_conv1 = model->conv1->activation;
+  e->act_conv2 = model->conv2->activation;
+  e->act_gb = model->fc_gb->activation;
+  e->act_rb = model->fc_rb->activation;
+
+  // stream state
+  e->pcm_stride = kKeep + F * kFrame;
+  CKD(dalloc(&e->d_pcm, S * e->pcm_stride));
+  CKD(dalloc(&e->d_synth, S * kFrame));
+  CKD(dalloc(&e->d_last_period, S));
+  CKD(dalloc(&e->d_last_gain, S));
+  // per-call buffers
+  CKD(dalloc(&e->d_feat, F * S * kFeat));
+  CKD(dalloc(&e->d_X, F * S * kBins));
+  CKD(dalloc(&e->d_P, F * S * kBins));
+  CKD(dalloc(&e->d_Ex, F * S * kBands));
+  CKD(dalloc(&e->d_sil, F * S));
+  CKD(dalloc(&e->d_gr, F * S * 68));
+  if (flags & PNB_KEEP_TAPS) {
+    CKD(dalloc(&e->d_tap_pitch, F * S * 4));
+    CKD(dalloc(&e->d_tap_pitchf, F * S * 2));
+  }
+  // network state and scratch
+  CKD(dalloc(&e->ring_fc, 5 * S * 128));
+  CKD(dalloc(&e->ring_c1, 3 * S * 512));
+  CKD(dalloc(&e->c2, S * 512));
+  for (int i = 0; i < 5; i++)
+    for (int p = 0; p < 2; p++) CKD(dalloc(&e->h[i][p], S * e->gru[i].H));
+  CKD(dalloc(&e->zr, S * 1024));
+  CKD(dalloc(&e->nx, S * 512));
+  CKD(dalloc(&e->nh, S * 512));
+  if (flags & PNB_NN_TENSOR) {
+    int trc = tc_prepare(e, model);
+    if (trc) { pnb_destroy(e); return trc; }
+  }
+  CKD(cudaDeviceSynchronize());
+  *out = e;
+  return PNB_OK;
+}
+
+extern "C" void pnb_destroy(pnb_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  tc_release(e);
+  float *fl[] = {e->fc.W, e->fc.b, e->conv1.W, e->conv1.b, e->conv2.W, e->conv2.b, e->fc_gb.W, e->fc_gb.b,
+                 e->fc_rb.W, e->fc_rb.b, e->d_pcm, e->d_synth, e->d_last_gain, e->d_feat, e->d_Ex, e->d_gr,
+                 e->d_tap_pitchf, e->ring_fc, e->ring_c1, e->c2, e->zr, e->nx, e->nh, e->d_hin, e->d_hout};
+  for (float *p : fl) if (p) cudaFree(p);
+  for (int i = 0; i < 5; i++) {
+    if (e->gru[i].W) cudaFree(e->gru[i].W);
+    if (e->gru[i].U) cudaFree(e->gru[i].U);
+    if (e->gru[i].b) cudaFree(e->gru[i].b);
+    for (int p = 0; p < 2; p++) if (e->h[i][p]) cudaFree(e->h[i][p]);
+  }
+  if (e->d_X) cudaFree(e->d_X);
+  if (e->d_P) cudaFree(e->d_P);
+  if (e->d_sil) cudaFree(e->d_sil);
+  if (e->d_last_period) cudaFree(e->d_last_period);
+  if (e->d_tap_pitch) cudaFree(e->d_tap_pitch);
+  if (e->d_tab) cudaFree(e->d_tab);
+  if (e->d_hin16) cudaFree(e->d_hin16);
+  if (e->d_hout16) cudaFree(e->d_hout16);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+extern "C" int pnb_reset(pnb_engine *e) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  const size_t S = e->S;
+  CK(cudaMemset(e->d_pcm, 0, S * e->pcm_stride * sizeof(float)));
+  CK(cudaMemset(e->d_synth, 0, S * kFrame * sizeof(float)));
+  CK(cudaMemset(e->d_last_period, 0, S * sizeof(int)));
+  CK(cudaMemset(e->d_last_gain, 0, S * sizeof(float)));
+  CK(cudaMemset(e->ring_fc, 0, 5 * S * 128 * sizeof(float)));
+  CK(cudaMemset(e->ring_c1, 0, 3 * S * 512 * sizeof(float)));
+  CK(cudaMemset(e->c2, 0, S * 512 * sizeof(float)));
+  for (int i = 0; i < 5; i++)
+    for (int p = 0; p < 2; p++) CK(cudaMemset(e->h[i][p], 0, S * e->gru[i].H * sizeof(float)));
+  e->hop = 0;
+  for (int i = 0; i < 5; i++) e->par[i] = 0;
+  int trc = tc_reset(e);
+  if (trc) return trc;
+  CK(cudaDeviceSynchronize());
+  return PNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// one network step in fp32 (rnn.cpp:42-81), hop index `c` counted since reset
+// ------------------------------------------------------------------------------------------
+static GemmSeg seg(const float *A, int lda, const float *B, int ldb, int K) {
+  GemmSeg s;
+  s.A = A; s.lda = lda; s.B = B; s.ldb = ldb; s.K = K;
+  return s;
+}
+
+static int gru_step_f32(pnb_engine *e, int li, const GemmSeg *xs, int nx_seg, cudaStream_t st) {
+  // xs: the input segments with B pointing at the start of the matching rows of W (column 0)
+  const int S = e->S, H = e->gru[li].H, ld = 3 * H;
+  const float *h_old = e->h[li][e->par[li]];
+  float *h_new = e->h[li][e->par[li] ^ 1];
+  const float *tbl = e->tansig();
+  int n = 0;
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.M = S; g.tansig = tbl; g.bias = nullptr; g.act = 0;
+  // z and r sums over input and recurrent parts
+  for (int i = 0; i < nx_seg; i++) g.seg[i] = xs[i];
+  g.seg[nx_seg] = seg(h_old, H, e->gru[li].U, ld, H);
+  g.n_seg = nx_seg + 1; g.N = 2 * H; g.C = e->zr; g.ldc = 2 * H;
+  n += launch_gemm_f32(g, st);
+  // candidate: input part
+  for (int i = 0; i < nx_seg; i++) { g.seg[i] = xs[i]; g.seg[i].B = xs[i].B + 2 * H; }
+  g.n_seg = nx_seg; g.N = H; g.C = e->nx; g.ldc = H;
+  n += launch_gemm_f32(g, st);
+  // candidate: recurrent part
+  g.seg[0] = seg(h_old, H, e->gru[li].U + 2 * H, ld, H);
+  g.n_seg = 1; g.N = H; g.C = e->nh; g.ldc = H;
+  n += launch_gemm_f32(g, st);
+  GruGateArgs gg;
+  gg.zr = e->zr; gg.nx = e->nx; gg.nh = e->nh; gg.bias = e->gru[li].b; gg.h_old = h_old; gg.h_new = h_new;
+  gg.M = S; gg.H = H; gg.tansig = tbl;
+  n += launch_gru_gates(gg, st);
+  e->par[li] ^= 1;
+  return n;
+}
+
+static int nn_step_f32(pnb_engine *e, int t, cudaStream_t st) {
+  const int S = e->S;
+  const long c = e->hop + t;
+  const float *tbl = e->tansig();
+  int n = 0;
+  float *fc_out = e->ring_fc + (size_t)(c % 5) * S * 128;
+  n += launch_fc_f32(e->d_feat + (size_t)t * S * kFeat, e->fc.W, e->fc.b, fc_out, S, 70, 128, st);
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.M = S; g.tansig = tbl;
+  // conv1: taps oldest..newest are ring slots c-4..c (nnet.cpp:182-200; weights [tap][c][n])
+  for (int q = 0; q < 5; q++)
+    g.seg[q] = seg(e->ring_fc + (size_t)(((c - 4 + q) % 5 + 5) % 5) * S * 128, 128, e->conv1.W + (size_t)q * 128 * 512, 512, 128);
+  float *c1_out = e->ring_c1 + (size_t)(c % 3) * S * 512;
+  g.n_seg = 5; g.N = 512; g.C = c1_out; g.ldc = 512; g.bias = e->conv1.b; g.act = e->act_conv1;
+  n += launch_gemm_f32(g, st);
+  for (int q = 0; q < 3; q++)
+    g.seg[q] = seg(e->ring_c1 + (size_t)(((c - 2 + q) % 3 + 3) % 3) * S * 512, 512, e->conv2.W + (size_t)q * 512 * 512, 512, 512);
+  g.n_seg = 3; g.N = 512; g.C = e->c2; g.ldc = 512; g.bias = e->conv2.b; g.act = e->act_conv2;
+  n += launch_gemm_f32(g, st);
+  // stacked GRUs: each consumes the freshly updated state of the one below
+  GemmSeg xs[2];
+  xs[0] = seg(e->c2, 512, e->gru[0].W, 1536, 512);
+  n += gru_step_f32(e, 0, xs, 1, st);
+  for (int li = 1; li < 4; li++) {
+    xs[0] = seg(e->h[li - 1][e->par[li - 1]], 512, e->gru[li].W, 1536, 512);
+    n += gru_step_f32(e, li, xs, 1, st);
+  }
+  // gru_rb input = [gru3 state, conv2 out] (rnn.cpp:69-71)
+  xs[0] = seg(e->h[2][e->par[2]], 512, e->gru[4].W, 384, 512);
+  xs[1] = seg(e->c2, 512, e->gru[4].W + (size_t)512 * 384, 384, 512);
+  n += gru_step_f32(e, 4, xs, 2, st);
+  // fc_gb on [conv2, gru1, gru2, gru3, gru_gb] (rnn.cpp:73-78), fc_rb on gru_rb (rnn.cpp:80)
+  float *gr = e->d_gr + (size_t)t * S * 68;
+  const float *cat[5] = {e->c2, e->h[0][e->par[0]], e->h[1][e->par[1]], e->h[2][e->par[2]], e->h[3][e->par[3]]};
+  for (int q = 0; q < 5; q++) g.seg[q] = seg(cat[q], 512, e->fc_gb.W + (size_t)q * 512 * 34, 34, 512);
+  g.n_seg = 5; g.N = 34; g.C = gr; g.ldc = 68; g.bias = e->fc_gb.b; g.act = e->act_gb;
+  n += launch_gemm_f32(g, st);
+  g.seg[0] = seg(e->h[4][e->par[4]], 128, e->fc_rb.W, 34, 128);
+  g.n_seg = 1; g.N = 34; g.C = gr + 34; g.ldc = 68; g.bias = e->fc_rb.b; g.act = e->act_rb;
+  n += launch_gemm_f32(g, st);
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+static int process_device(pnb_engine *e, const float *d_in, const short *d_in16, size_t in_stride, float *d_out,
+                          short *d_out16, size_t out_stride, int F, float *d_gr, cudaStream_t st) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  if (F < 1 || F > e->Fmax) return fail(PNB_ERR_ARG, "n_frames %d outside [1, %d]", F, e->Fmax);
+  if ((!d_in && !d_in16) || (!d_out && !d_out16)) return fail(PNB_ERR_ARG, "input/output pointer is NULL");
+  if (in_stride < (size_t)F * kFrame || out_stride < (size_t)F * kFrame)
+    return fail(PNB_ERR_ARG, "row stride smaller than n_frames*480");
+  CK(cudaSetDevice(e->device));
+  const int S = e->S;
+  long long n = 0;
+  n += launch_stage_in(e->d_pcm, e->pcm_stride, d_in, d_in16, in_stride, S, F * kFrame, st);
+  AnalysisArgs a;
+  a.pcm = e->d_pcm; a.pcm_stride = e->pcm_stride; a.n_streams = S; a.n_frames = F; a.tab = e->d_tab;
+  a.feat = e->d_feat; a.X = e->d_X; a.P = e->d_P; a.Ex = e->d_Ex; a.silence = e->d_sil;
+  a.last_period = e->d_last_period; a.last_gain = e->d_last_gain;
+  a.tap_pitch = e->d_tap_pitch; a.tap_pitchf = e->d_tap_pitchf;
+  n += launch_analysis(a, st);
+  for (int t = 0; t < F; t++) {
+    if (e->flags & PNB_NN_TENSOR) {
+      int k = tc_step(e, t, st);
+      if (k < 0) return k;
+      n += k;
+    } else {
+      n += nn_step_f32(e, t, st);
+    }
+  }
+  SynthesisArgs s;
+  s.X = e->d_X; s.P = e->d_P; s.gr = e->d_gr; s.Ex = e->d_Ex; s.silence = e->d_sil; s.n_streams = S; s.n_frames = F;
+  s.tab = e->d_tab; s.synth_mem = e->d_synth; s.out = d_out; s.out16 = d_out16; s.out_stride = out_stride;
+  s.postfilter = (e->flags & PNB_POSTFILTER) ? 1 : 0;
+  n += launch_synthesis(s, st);
+  n += launch_slide_history(e->d_pcm, e->pcm_stride, S, F * kFrame, st);
+  if (d_gr) CK(cudaMemcpyAsync(d_gr, e->d_gr, (size_t)F * S * 68 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(cudaGetLastError());
+  e->hop += F;
+  e->last_frames = F;
+  e->launches += n;
+  return PNB_OK;
+}
+
+extern "C" int pnb_process_device_f32(pnb_engine *e, const float *d_in, size_t in_stride, float *d_out,
+                                      size_t out_stride, int n_frames, float *d_gr, void *cuda_stream) {
+  return process_device(e, d_in, nullptr, in_stride, d_out, nullptr, out_stride, n_frames, d_gr,
+                        (cudaStream_t)cuda_stream);
+}
+extern "C" int pnb_process_device_i16(pnb_engine *e, const short *d_in, size_t in_stride, short *d_out,
+                                      size_t out_stride, int n_frames, float *d_gr, void *cuda_stream) {
+  return process_device(e, nullptr, d_in, in_stride, nullptr, d_out, out_stride, n_frames, d_gr,
+                        (cudaStream_t)cuda_stream);
+}
+
+template <typename T>
+static int process_host(pnb_engine *e, const T *in, size_t in_stride, T *out, size_t out_stride, int F, float *gr,
+                        T **d_in_p, T **d_out_p) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  if (!in || !out) return fail(PNB_ERR_ARG, "input/output pointer is NULL");
+  if (F < 1 || F > e->Fmax) return fail(PNB_ERR_ARG, "n_frames %d outside [1, %d]", F, e->Fmax);
+  if (in_stride < (size_t)F * kFrame || out_stride < (size_t)F * kFrame)
+    return fail(PNB_ERR_ARG, "row stride smaller than n_frames*480");
+  CK(cudaSetDevice(e->device));
+  const size_t S = e->S, row = (size_t)e->Fmax * kFrame;
+  if (!*d_in_p) CK(cudaMalloc((void **)d_in_p, S * row * sizeof(T)));
+  if (!*d_out_p) CK(cudaMalloc((void **)d_out_p, S * row * sizeof(T)));
+  const size_t w = (size_t)F * kFrame * sizeof(T);
+  CK(cudaMemcpy2DAsync(*d_in_p, row * sizeof(T), in, in_stride * sizeof(T), w, S, cudaMemcpyHostToDevice, e->stream));
+  int rc;
+  if (sizeof(T) == 4)
+    rc = process_device(e, (const float *)*d_in_p, nullptr, row, (float *)*d_out_p, nullptr, row, F, nullptr, e->stream);
+  else
+    rc = process_device(e, nullptr, (const short *)*d_in_p, row, nullptr, (short *)*d_out_p, row, F, nullptr, e->stream);
+  if (rc) return rc;
+  CK(cudaMemcpy2DAsync(out, out_stride * sizeof(T), *d_out_p, row * sizeof(T), w, S, cudaMemcpyDeviceToHost, e->stream));
+  if (gr) CK(cudaMemcpyAsync(gr, e->d_gr, (size_t)F * S * 68 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return PNB_OK;
+}
+
+extern "C" int pnb_process_host_f32(pnb_engine *e, const float *in, size_t in_stride, float *out, size_t out_stride,
+                                    int n_frames, float *gr) {
+  return process_host<float>(e, in, in_stride, out, out_stride, n_frames, gr, &e->d_hin, &e->d_hout);
+}
+extern "C" int pnb_process_host_i16(pnb_engine *e, const short *in, size_t in_stride, short *out, size_t out_stride,
+                                    int n_frames, float *gr) {
+  return process_host<short>(e, in, in_stride, out, out_stride, n_frames, gr, &e->d_hin16, &e->d_hout16);
+}
+
+extern "C" int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes) {
+  if (!e || !dst) return fail(PNB_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(e->device));
+  const size_t n = (size_t)e->last_frames * e->S;
+  const void *src = nullptr;
+  size_t bytes = 0;
+  switch (what) {
+    case PNB_TAP_FEATURES: src = e->d_feat; bytes = n * kFeat * 4; break;
+    case PNB_TAP_PITCH: src = e->d_tap_pitch; bytes = n * 16; break;
+    case PNB_TAP_PITCHF: src = e->d_tap_pitchf; bytes = n * 8; break;
+    case PNB_TAP_X: src = e->d_X; bytes = n * kBins * 8; break;
+    case PNB_TAP_P: src = e->d_P; bytes = n * kBins * 8; break;
+    case PNB_TAP_EX: src = e->d_Ex; bytes = n * kBands * 4; break;
+    case PNB_TAP_GR: src = e->d_gr; bytes = n * 68 * 4; break;
+    default: return fail(PNB_ERR_ARG, "unknown tap %d", what);
+  }
+  if (!src) return fail(PNB_ERR_ARG, "tap %d needs PNB_KEEP_TAPS at pnb_create", what);
+  if (dst_bytes < bytes) return fail(PNB_ERR_ARG, "tap %d needs %zu bytes, got %zu", what, bytes, dst_bytes);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return PNB_OK;
+}
+
+extern "C" long long pnb_launch_count(const pnb_engine *e) { return e ? e->launches : 0; }
+extern "C" int pnb_launches_per_call(const pnb_engine *e, int n_frames) {
+  if (!e) return 0;
+  int per_step = (e->flags & PNB_NN_TENSOR) ? tc_launches_per_step(e) : 25;
+  return 4 + per_step * n_frames;
+}
+extern "C" int pnb_n_streams(const pnb_engine *e) { return e ? e->S : 0; }
+extern "C" int pnb_max_frames(const pnb_engine *e) { return e ? e->Fmax : 0; }

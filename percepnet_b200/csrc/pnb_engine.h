@@ -1,0 +1,63 @@
+// pnb_engine.h -- the engine object behind the opaque pnb_engine handle.
+#pragma once
+#include <stddef.h>
+#include "pnb_kernels.h"
+#include "../../include/pnb_nnet_layout.h"
+
+struct pnb_tc_state;  // tensor-core path (pnb_nn_tc.cu)
+
+struct pnb_engine {
+  int S = 0, Fmax = 0, device = 0, sm_count = 0;
+  unsigned flags = 0;
+  cudaStream_t stream = nullptr;  // used by the host-buffer entry points
+  pnb::Tables *d_tab = nullptr;
+
+  // weights in the reference's layout
+  struct { float *W = nullptr, *b = nullptr; } fc, conv1, conv2, fc_gb, fc_rb;
+  struct { float *W = nullptr, *U = nullptr, *b = nullptr; int M = 0, H = 0; } gru[5];  // gru1..3, gru_gb, gru_rb
+  int act_fc = 0, act_conv1 = 0, act_conv2 = 0, act_gb = 0, act_rb = 0;
+
+  // per-stream signal state
+  float *d_pcm = nullptr;  // [S][5280 + Fmax*480]: history then the call's hops
+  size_t pcm_stride = 0;
+  float *d_synth = nullptr;
+  int *d_last_period = nullptr;
+  float *d_last_gain = nullptr;
+
+  // per-call intermediates [F][S][...]
+  float *d_feat = nullptr;
+  float2 *d_X = nullptr, *d_P = nullptr;
+  float *d_Ex = nullptr;
+  unsigned char *d_sil = nullptr;
+  float *d_gr = nullptr;
+  int *d_tap_pitch = nullptr;
+  float *d_tap_pitchf = nullptr;
+
+  // network state (fp32 path): conv rings, GRU states (ping-pong), scratch sums
+  float *ring_fc = nullptr;  // [5][S][128] outputs of fc for hops c-4..c
+  float *ring_c1 = nullptr;  // [3][S][512] outputs of conv1 for hops c-2..c
+  float *c2 = nullptr;       // [S][512]
+  float *h[5][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  int par[5] = {0, 0, 0, 0, 0};
+  float *zr = nullptr, *nx = nullptr, *nh = nullptr;
+  long hop = 0;  // hops processed since reset
+
+  // staging for the host-buffer entry points
+  float *d_hin = nullptr, *d_hout = nullptr;
+  short *d_hin16 = nullptr, *d_hout16 = nullptr;
+
+  pnb_tc_state *tc = nullptr;
+  int last_frames = 0;
+  long long launches = 0;
+
+  const float *tansig() const {
+    return reinterpret_cast<const float *>(reinterpret_cast<const char *>(d_tab) + offsetof(pnb::Tables, tansig));
+  }
+};
+
+// tensor-core path hooks (pnb_nn_tc.cu); return PNB_OK / negative error, tc_step returns launches
+int tc_prepare(pnb_engine *e, const pnb_model *model);
+void tc_release(pnb_engine *e);
+int tc_reset(pnb_engine *e);
+int tc_step(pnb_engine *e, int t, cudaStream_t st);
+int tc_launches_per_step(const pnb_engine *e);

@@ -1,0 +1,83 @@
+// pnb_kernels.h -- kernel argument blocks and launcher prototypes shared by the .cu files.
+#pragma once
+#include "pnb_common.cuh"
+
+namespace pnb {
+
+// ---- DSP (pnb_dsp.cu) -------------------------------------------------------------------
+struct AnalysisArgs {
+  const float *pcm;        // [S][pcm_stride]: 5280 samples of history, then the call's hops
+  size_t pcm_stride;
+  int n_streams, n_frames;
+  const Tables *tab;
+  float *feat;             // [F][S][70]
+  float2 *X, *P;           // [F][S][400]
+  float *Ex;               // [F][S][34] or null
+  unsigned char *silence;  // [F][S]
+  int *last_period;        // [S] carried state
+  float *last_gain;        // [S]
+  int *tap_pitch;          // [F][S][4] or null
+  float *tap_pitchf;       // [F][S][2] or null
+};
+
+struct SynthesisArgs {
+  const float2 *X, *P;     // [F][S][400]
+  const float *gr;         // [F][S][68]
+  const float *Ex;         // [F][S][34] (post-filter only)
+  const unsigned char *silence;
+  int n_streams, n_frames;
+  const Tables *tab;
+  float *synth_mem;        // [S][480] carried state
+  float *out;              // float output rows or null
+  short *out16;            // int16 output rows or null
+  size_t out_stride;
+  int postfilter;
+};
+
+cudaError_t dsp_configure();
+int launch_analysis(const AnalysisArgs &a, cudaStream_t st);
+int launch_synthesis(const SynthesisArgs &a, cudaStream_t st);
+int launch_stage_in(float *pcm, size_t pcm_stride, const float *in, const short *in16, size_t in_stride,
+                    int n_streams, int n_samples, cudaStream_t st);
+int launch_slide_history(float *pcm, size_t pcm_stride, int n_streams, int n_samples, cudaStream_t st);
+
+// ---- network, fp32 FMA path (pnb_nn_f32.cu) ---------------------------------------------
+// One contraction  C[M x N] = epilogue( sum_seg A_seg[M x K_seg] * B_seg[K_seg x N] ).
+// A segments are activation matrices (row = stream), B segments are slices of the reference's
+// input-major weight arrays (row = input j, column = output i: W[j*ldb + i]).
+struct GemmSeg {
+  const float *A;
+  int lda;
+  const float *B;
+  int ldb;
+  int K;  // multiple of 16
+};
+struct GemmArgs {
+  GemmSeg seg[5];
+  int n_seg;
+  int M, N;
+  float *C;
+  int ldc;
+  const float *bias;  // null -> raw sums
+  int act;            // PNB_ACT_* applied when bias != null
+  const float *tansig;
+};
+int launch_gemm_f32(const GemmArgs &g, cudaStream_t st);
+
+// fc: features [M x 70] -> [M x 128], relu (nnet.cpp:105 on the `fc` layer)
+int launch_fc_f32(const float *feat, const float *W, const float *bias, float *out, int M, int K, int N,
+                  cudaStream_t st);
+
+// GRU gate math (nnet.cpp:120-180, reset_after) on pre-computed sums:
+//   zr [M x 2H] = W_zr x + U_zr h,  nx [M x H] = W_n x,  nh [M x H] = U_n h
+struct GruGateArgs {
+  const float *zr, *nx, *nh;
+  const float *bias;   // [6H]
+  const float *h_old;  // [M x H]
+  float *h_new;        // [M x H]
+  int M, H;
+  const float *tansig;
+};
+int launch_gru_gates(const GruGateArgs &g, cudaStream_t st);
+
+}  // namespace pnb

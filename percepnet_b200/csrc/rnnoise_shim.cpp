@@ -1,0 +1,74 @@
+// rnnoise_shim.cpp -- the reference's own single-stream API on top of the batched engine.
+//
+// Exports, with C++ linkage exactly like /root/reference/src/rnnoise.h:52-60 (the reference sources are
+// all .cpp and the header has no extern "C"), the symbols an unmodified
+// /root/reference/src/main.cpp imports:
+//   int rnnoise_get_size();                                   src/denoise.cpp:348
+//   int rnnoise_init(DenoiseState*, RNNModel*);               src/denoise.cpp:259
+//   DenoiseState* rnnoise_create(RNNModel*);                  src/denoise.cpp:252
+//   void rnnoise_destroy(DenoiseState*);                      src/denoise.cpp:326
+//   float rnnoise_process_frame(DenoiseState*, float*, const float*, FILE*);   src/denoise.cpp:508
+// A stream handle is a batch of one; it exists for drop-in correctness (percepNet_run), throughput
+// comes from the pnb_* batch API.  model == NULL selects `percepnet_model_orig`, the symbol the
+// generated src/nnet_data.cpp defines (dump_percepnet.py:149); it is referenced weakly so that hosts
+// which always pass a model do not need to link one.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/percepnet_b200.h"
+
+struct RNNModel;      // layout == pnb_model (include/pnb_nnet_layout.h)
+struct DenoiseState { // opaque to callers (rnnoise.h:49)
+  pnb_engine *engine;
+  float gr[68];
+};
+
+extern const RNNModel percepnet_model_orig __attribute__((weak));
+
+int rnnoise_get_size() { return (int)sizeof(DenoiseState); }
+
+int rnnoise_init(DenoiseState *st, RNNModel *model) {
+  memset(st, 0, sizeof *st);
+  const RNNModel *m = model ? model : &percepnet_model_orig;
+  if (!m) {
+    fprintf(stderr, "rnnoise_init: no model given and percepnet_model_orig is not linked\n");
+    return -1;
+  }
+  int rc = pnb_create(&st->engine, 1, 1, reinterpret_cast<const pnb_model *>(m), PNB_NN_FP32, 0);
+  if (rc != PNB_OK) {
+    fprintf(stderr, "rnnoise_init: %s\n", pnb_last_error());
+    return rc;
+  }
+  return 0;
+}
+
+DenoiseState *rnnoise_create(RNNModel *model) {
+  DenoiseState *st = (DenoiseState *)malloc(rnnoise_get_size());
+  if (!st) return NULL;
+  if (rnnoise_init(st, model) != 0) {  // no CPU fallback: fail loudly
+    free(st);
+    fprintf(stderr, "rnnoise_create: cannot create the CUDA engine\n");
+    abort();
+  }
+  return st;
+}
+
+void rnnoise_destroy(DenoiseState *st) {
+  if (!st) return;
+  pnb_destroy(st->engine);
+  free(st);
+}
+
+float rnnoise_process_frame(DenoiseState *st, float *out, const float *in, FILE *f_feature) {
+  int rc = pnb_process_host_f32(st->engine, in, PNB_FRAME, out, PNB_FRAME, 1, st->gr);
+  if (rc != PNB_OK) {
+    fprintf(stderr, "rnnoise_process_frame: %s\n", pnb_last_error());
+    abort();
+  }
+  if (f_feature) {  // src/denoise.cpp:533-534
+    fwrite(st->gr, sizeof(float), 34, f_feature);
+    fwrite(st->gr + 34, sizeof(float), 34, f_feature);
+  }
+  return 0;  // src/denoise.cpp:546
+}

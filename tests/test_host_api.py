@@ -1,0 +1,86 @@
+"""CPU-side checks of the boundary: the C-ABI library builds for sm_100a, loads, exports every symbol
+the headers declare, fails loudly without a GPU, and the rnnoise.h shim exports the reference's
+C++-mangled names.  No compute."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def built():
+    from percepnet_b200 import build
+    build.build()
+    return build
+
+
+def test_library_exports_every_declared_symbol(built):
+    from percepnet_b200 import api
+    hdr = open(os.path.join(ROOT, "include", "percepnet_b200.h")).read()
+    declared = set(re.findall(r"\b(pnb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"pnb_model", "pnb_engine"}
+    assert declared == set(api.EXPORTS)
+    L = api.load_library()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.pnb_version()
+
+
+def test_layout_structs_match_header():
+    """ctypes mirrors == include/pnb_nnet_layout.h == reference nnet.h:44-89 field order."""
+    from percepnet_b200 import weights as W
+    assert [f[0] for f in W.DenseLayerC._fields_] == ["bias", "input_weights", "nb_inputs", "nb_neurons", "activation"]
+    assert [f[0] for f in W.GRULayerC._fields_] == ["bias", "input_weights", "recurrent_weights", "nb_inputs",
+                                                    "nb_neurons", "activation", "reset_after"]
+    assert [f[0] for f in W.Conv1DLayerC._fields_] == ["bias", "input_weights", "nb_inputs", "kernel_size",
+                                                       "nb_neurons", "activation"]
+    assert [f[0] for f in W.ModelC._fields_] == ["fc", "conv1", "conv2", "gru1", "gru2", "gru3", "gru_gb", "gru_rb",
+                                                 "fc_gb", "fc_rb"]
+    assert C.sizeof(W.ModelC) == 80 and C.sizeof(W.GRULayerC) == 40 and C.sizeof(W.DenseLayerC) == 32
+
+
+def test_create_fails_loudly_without_gpu(built, model0):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from percepnet_b200 import api
+    with pytest.raises(api.PnbError) as ei:
+        api.Engine(4, 4, model0)
+    assert "no CPU path" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_rejects_wrong_architecture(built, model0):
+    from percepnet_b200 import api
+    L = api.load_library()
+    m = model0.as_c_model()
+    bad = type(m)()
+    C.memmove(C.byref(bad), C.byref(m), C.sizeof(m))
+    fc = type(m.fc.contents)()
+    C.memmove(C.byref(fc), m.fc, C.sizeof(fc))
+    fc.nb_neurons = 64
+    bad.fc = C.pointer(fc)
+    h = C.c_void_p()
+    assert L.pnb_create(C.byref(h), 1, 1, C.byref(bad), 0, 0) == -1
+    assert b"PercepNet" in L.pnb_last_error()
+
+
+def test_rnnoise_shim_exports_reference_symbols(built):
+    """The names an unmodified src/main.cpp imports (PROBE nm)."""
+    out = subprocess.run(["nm", "-D", "--defined-only", built.SHIM], capture_output=True, text=True, check=True).stdout
+    for sym in ("_Z14rnnoise_createP8RNNModel", "_Z21rnnoise_process_frameP12DenoiseStatePfPKfP8_IO_FILE",
+                "_Z15rnnoise_destroyP12DenoiseState", "_Z16rnnoise_get_sizev", "_Z12rnnoise_initP12DenoiseStateP8RNNModel"):
+        assert sym in out, sym
+
+
+def test_synthetic_weights_are_reproducible(model0):
+    from percepnet_b200.weights import N_PARAMS, synth_model
+    assert model0.n_params() == N_PARAMS
+    assert synth_model(0).digest() == model0.digest()
+    assert synth_model(1).digest() != model0.digest()
+    w = model0.arrays["gru1_weights"]
+    assert w.shape == (512, 1536) and abs(float(w.std()) - (1 / np.sqrt(512)) / np.sqrt(3)) < 1e-3

@@ -1,0 +1,158 @@
+"""Pins the C restatement (oracle/pn_oracle.c) to the compiled, unmodified reference (oracle/_ref),
+stage by stage and end to end, BIT FOR BIT.  Runs where oracle/_ref was built (the build container;
+the library also travels to the GPU box).  CPU only."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from util import same_bits, edge_signals
+from conftest import REFERENCE_TREE
+
+
+@pytest.fixture(scope="module")
+def rng():
+    return np.random.RandomState(1234)
+
+
+def test_erb_borders(oracle, reference):
+    b = oracle.erb_borders()
+    assert np.array_equal(b, reference.erb_borders())
+    assert b.tolist() == [0, 2, 4, 6, 8, 10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 31, 36, 41, 48, 56, 65, 75, 86, 99,
+                          115, 132, 152, 175, 201, 230, 265, 304, 349, 400]
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE_TREE), reason="needs /root/reference")
+def test_tansig_table_matches_header(oracle):
+    txt = open(os.path.join(REFERENCE_TREE, "src/tansig_table.h")).read()
+    vals = np.array([np.float32(v) for v in re.findall(r"([0-9]\.[0-9]+)f", txt)], np.float32)
+    assert vals.size == 201
+    # tansig(0.04*i) at the table nodes returns the table value itself (x - 0.04f*i == 0 there)
+    got = oracle.tansig(np.float32(0.04) * np.arange(201, dtype=np.float32))
+    nodes_exact = np.float32(0.04) * np.arange(201, dtype=np.float32) - np.float32(0.04) * np.arange(201, dtype=np.float32)
+    assert np.all(nodes_exact == 0)
+    assert same_bits(got, vals)
+
+
+def test_fft960(oracle, reference, rng):
+    for amp in (1.0, 1e-3, 3e4):
+        z = (rng.randn(1920) * amp).astype(np.float32)
+        assert same_bits(oracle.fft960(z), reference.fft960(z))
+    d = np.zeros(1920, np.float32); d[2 * 7] = 1
+    assert same_bits(oracle.fft960(d), reference.fft960(d))
+
+
+def test_band_ops(oracle, reference, rng):
+    X = (rng.randn(962) * 3).astype(np.float32)
+    P = rng.randn(962).astype(np.float32)
+    assert same_bits(oracle.band_energy(X), reference.band_energy(X))
+    assert same_bits(oracle.band_corr(X, P), reference.band_corr(X, P))
+    g = rng.rand(34).astype(np.float32)
+    gi = oracle.interp_band_gain(g)
+    assert same_bits(gi, reference.interp_band_gain(g))
+    assert np.all(gi[400:] == 0)
+    assert same_bits(oracle.pitch_filter(X, P, g), reference.pitch_filter(X, P, g))
+
+
+def _pitch_bufs(rng):
+    t = np.arange(1728) / 48000.0
+    yield (3000 * np.sin(2 * np.pi * 140 * t) + 200 * rng.randn(1728)).astype(np.float32)
+    yield (0.2 * np.sin(2 * np.pi * 300 * t) + 0.01 * rng.randn(1728)).astype(np.float32)
+    yield np.zeros(1728, np.float32)
+    yield (rng.randn(1728) * 1e-4).astype(np.float32)
+    yield (8000 * np.sign(np.sin(2 * np.pi * 62.5 * t))).astype(np.float32)
+    for _ in range(6):
+        f0 = rng.uniform(60, 800)
+        yield (1000 * np.sin(2 * np.pi * f0 * t) + 500 * np.sin(4 * np.pi * f0 * t + 1) + 100 * rng.randn(1728)).astype(np.float32)
+
+
+def test_pitch_chain(oracle, reference, rng):
+    prev = (0, 0.0)
+    for buf in _pitch_bufs(rng):
+        lp_o, lp_r = oracle.pitch_downsample(buf), reference.pitch_downsample(buf)
+        assert same_bits(lp_o, lp_r)
+        ac_o, lpc_o = oracle.autocorr_lpc(lp_r)
+        ac_r, lpc_r = reference.autocorr_lpc(lp_r)
+        assert same_bits(ac_o, ac_r) and same_bits(lpc_o, lpc_r)
+        p_o, c_o, coarse, _ = oracle.pitch_search(lp_r)
+        p_r, c_r = reference.pitch_search(lp_r)
+        assert p_o == p_r and same_bits([c_o], [c_r])
+        x4, y4 = lp_r[384::2][:240].copy(), lp_r[::2][:387].copy()
+        assert same_bits(coarse, reference.pitch_xcorr(x4, y4, 147))
+        assert same_bits(oracle.pitch_xcorr(x4, y4, 147), coarse)
+        for pp, pg in (prev, (0, 0.0), (p_r // 2 * 2, 0.8), (120, 0.5)):
+            T_o, g_o = oracle.remove_doubling(lp_r, 768 - p_r, pp, pg)
+            T_r, g_r = reference.remove_doubling(lp_r, 768 - p_r, pp, pg)
+            assert T_o == T_r and same_bits([g_o], [g_r])
+        prev = (T_r, g_r)
+
+
+def test_network_layers(oracle, reference, model0, model_hot, rng):
+    for model in (model0, model_hot):
+        reference.set_model(model)
+        m = model.as_c_model()
+        x = (rng.rand(70) * 4).astype(np.float32)
+        assert same_bits(oracle.dense_layer(m.fc.contents, x, 128), reference.dense_layer(m.fc.contents, x, 128))
+        mem_o, mem_r = np.zeros(640, np.float32), np.zeros(640, np.float32)
+        for _ in range(6):
+            x = rng.rand(128).astype(np.float32)
+            a = oracle.conv1d_layer(m.conv1.contents, mem_o, x, 512)
+            b = reference.conv1d_layer(m.conv1.contents, mem_r, x, 512)
+            assert same_bits(a, b) and same_bits(mem_o, mem_r)
+        for layer, M, H in ((m.gru1.contents, 512, 512), (m.gru_rb.contents, 1024, 128)):
+            h_o, h_r = np.zeros(H, np.float32), np.zeros(H, np.float32)
+            for _ in range(4):
+                x = (rng.randn(M)).astype(np.float32)
+                oracle.gru_layer(layer, h_o, x)
+                reference.gru_layer(layer, h_r, x)
+                assert same_bits(h_o, h_r)
+        so, sr = np.zeros(3712, np.float32), np.zeros(3712, np.float32)
+        for _ in range(5):
+            f = (rng.rand(70) * 2).astype(np.float32)
+            go, ro = oracle.compute_rnn(model, so, f)
+            gr_, rr = reference.compute_rnn(sr, f)
+            assert same_bits(go, gr_) and same_bits(ro, rr) and same_bits(so, sr)
+
+
+def test_activation_sweep(oracle):
+    x = np.linspace(-9, 9, 4001).astype(np.float32)
+    t = oracle.tansig(x)
+    assert np.max(np.abs(t - np.tanh(x.astype(np.float64)))) < 2e-4   # table approximation error bound
+    s = oracle.sigmoid(x)
+    assert np.max(np.abs(s - 1 / (1 + np.exp(-x.astype(np.float64))))) < 1e-4
+
+
+@pytest.mark.parametrize("scale", [1.0, 32768.0])
+def test_end_to_end_edge_signals(oracle, reference, model0, scale):
+    reference.set_model(model0)
+    for name, x in edge_signals(16, scale).items():
+        hr = reference.create()
+        yr, gr = reference.process_stream(hr, x, True)
+        reference.destroy(hr)
+        ho = oracle.create(model0)
+        yo, go, _ = oracle.process_stream(ho, x, True)
+        oracle.destroy(ho)
+        assert same_bits(yo, yr), name
+        assert same_bits(go, gr), name
+
+
+def test_end_to_end_hot_weights_and_cli(oracle, reference, model_hot):
+    from percepnet_b200.synth import synth_pcm, to_int16
+    reference.set_model(model_hot)
+    x16 = to_int16(synth_pcm(1, 20, seed=99)[0])
+    o_r, g_r = reference.run_pcm16(x16)
+    o_o, g_o = oracle.run_pcm16(model_hot, x16)
+    assert np.array_equal(o_r, o_o) and same_bits(g_r, g_o)
+    x = x16.astype(np.float32)       # int16-scale floats: the comb-filter branch executes
+    hr = reference.create(); yr, gr = reference.process_stream(hr, x, True); reference.destroy(hr)
+    ho = oracle.create(model_hot); yo, go, taps = oracle.process_stream(ho, x, True, taps=True); oracle.destroy(ho)
+    assert same_bits(yo, yr) and same_bits(go, gr)
+    assert sum(1 for t in taps if not t.silence) >= 10
+
+
+def test_multi_stream_driver(oracle, reference, model0):
+    from percepnet_b200.synth import synth_pcm
+    reference.set_model(model0)
+    x = synth_pcm(3, 6, seed=5)
+    assert same_bits(oracle.process_streams(model0, x, 2), reference.process_streams(x, 2))
