@@ -101,6 +101,17 @@ enum {
 };
 int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes);
 
+/* Per-kernel-class device timing.  While enabled, every launch of a pnb_process_* call is bracketed by
+ * CUDA events on the launching stream; pnb_profile_read waits for them and returns the accumulated
+ * milliseconds and launch counts per class since the last read (arrays of PNB_NUM_KERNEL_CLASSES). */
+enum {
+  PNB_K_STAGE_IN = 0, PNB_K_ANALYSIS = 1, PNB_K_FC = 2, PNB_K_GEMM_F32 = 3, PNB_K_GRU_GATES = 4,
+  PNB_K_SYNTHESIS = 5, PNB_K_SLIDE = 6, PNB_K_TC_GEMM = 7, PNB_K_TC_AUX = 8, PNB_NUM_KERNEL_CLASSES = 9
+};
+int pnb_profile_enable(pnb_engine *e, int on);
+int pnb_profile_read(pnb_engine *e, double *ms, long long *counts);
+const char *pnb_kernel_class_name(int cls);
+
 /* Number of kernels this library has launched on behalf of e since creation. */
 long long pnb_launch_count(const pnb_engine *e);
 /* Kernel launches one pnb_process_* call with n_frames hops issues. */

@@ -53,6 +53,10 @@ def load_library() -> C.CDLL:
     L.pnb_launches_per_call.argtypes = [vp, i]
     L.pnb_n_streams.argtypes = [vp]
     L.pnb_max_frames.argtypes = [vp]
+    L.pnb_profile_enable.argtypes = [vp, i]
+    L.pnb_profile_read.argtypes = [vp, vp, vp]
+    L.pnb_kernel_class_name.argtypes = [i]
+    L.pnb_kernel_class_name.restype = C.c_char_p
     L.pnb_last_error.restype = C.c_char_p
     L.pnb_version.restype = C.c_char_p
     _lib = L
@@ -61,7 +65,7 @@ def load_library() -> C.CDLL:
 
 EXPORTS = ("pnb_create", "pnb_destroy", "pnb_reset", "pnb_process_host_f32", "pnb_process_host_i16",
            "pnb_process_device_f32", "pnb_process_device_i16", "pnb_read_tap", "pnb_launch_count",
-           "pnb_launches_per_call", "pnb_n_streams", "pnb_max_frames", "pnb_last_error", "pnb_version")
+           "pnb_launches_per_call", "pnb_profile_enable", "pnb_profile_read", "pnb_kernel_class_name", "pnb_n_streams", "pnb_max_frames", "pnb_last_error", "pnb_version")
 
 
 class Engine:
@@ -133,6 +137,17 @@ class Engine:
         a = np.empty((n_frames, self.n_streams, width), dt)
         self._ck(self.L.pnb_read_tap(self.h, code, a.ctypes.data, a.nbytes), f"pnb_read_tap({name})")
         return a
+
+    def profile(self, on: bool):
+        self._ck(self.L.pnb_profile_enable(self.h, 1 if on else 0), "pnb_profile_enable")
+
+    def profile_read(self) -> dict:
+        """{kernel class name: (total ms, launches)} since the last read; waits for the device."""
+        n = 9
+        ms = (C.c_double * n)()
+        cnt = (C.c_longlong * n)()
+        self._ck(self.L.pnb_profile_read(self.h, ms, cnt), "pnb_profile_read")
+        return {self.L.pnb_kernel_class_name(k).decode(): (ms[k], int(cnt[k])) for k in range(n) if cnt[k]}
 
     @property
     def launches(self) -> int:

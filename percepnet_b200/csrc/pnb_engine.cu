@@ -258,6 +258,8 @@ extern "C" void pnb_destroy(pnb_engine *e) {
   if (e->d_tab) cudaFree(e->d_tab);
   if (e->d_hin16) cudaFree(e->d_hin16);
   if (e->d_hout16) cudaFree(e->d_hout16);
+  for (auto &r : e->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -285,6 +287,56 @@ extern "C" int pnb_reset(pnb_engine *e) {
 }
 
 // ------------------------------------------------------------------------------------------
+// per-kernel-class timing
+// ------------------------------------------------------------------------------------------
+static cudaEvent_t prof_event(pnb_engine *e) {
+  if (!e->prof_pool.empty()) { cudaEvent_t ev = e->prof_pool.back(); e->prof_pool.pop_back(); return ev; }
+  cudaEvent_t ev;
+  cudaEventCreate(&ev);
+  return ev;
+}
+ProfScope::ProfScope(pnb_engine *eng, int cls, cudaStream_t s) : e(eng), idx(-1), st(s) {
+  if (!e->profiling) return;
+  pnb_engine::ProfRec r;
+  r.cls = cls; r.a = prof_event(e); r.b = prof_event(e);
+  cudaEventRecord(r.a, st);
+  e->prof_pending.push_back(r);
+  idx = (int)e->prof_pending.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(e->prof_pending[idx].b, st);
+}
+extern "C" int pnb_profile_enable(pnb_engine *e, int on) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  e->profiling = on != 0;
+  return PNB_OK;
+}
+extern "C" int pnb_profile_read(pnb_engine *e, double *ms, long long *counts) {
+  if (!e || !ms || !counts) return fail(PNB_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  for (auto &r : e->prof_pending) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, r.a, r.b));
+    e->prof_ms[r.cls] += t;
+    e->prof_n[r.cls] += 1;
+    e->prof_pool.push_back(r.a);
+    e->prof_pool.push_back(r.b);
+  }
+  e->prof_pending.clear();
+  for (int i = 0; i < PNB_NUM_KERNEL_CLASSES; i++) {
+    ms[i] = e->prof_ms[i]; counts[i] = e->prof_n[i];
+    e->prof_ms[i] = 0; e->prof_n[i] = 0;
+  }
+  return PNB_OK;
+}
+extern "C" const char *pnb_kernel_class_name(int cls) {
+  static const char *names[PNB_NUM_KERNEL_CLASSES] = {"stage_in_kernel", "analysis_kernel", "fc_f32_kernel",
+      "gemm_f32_kernel", "gru_gates_kernel", "synthesis_kernel", "slide_history_kernel", "tc_gemm_kernel", "tc_aux_kernel"};
+  return (cls >= 0 && cls < PNB_NUM_KERNEL_CLASSES) ? names[cls] : "?";
+}
+
+// ------------------------------------------------------------------------------------------
 // one network step in fp32 (rnn.cpp:42-81), hop index `c` counted since reset
 // ------------------------------------------------------------------------------------------
 static GemmSeg seg(const float *A, int lda, const float *B, int ldb, int K) {
@@ -307,19 +359,19 @@ static int gru_step_f32(pnb_engine *e, int li, const GemmSeg *xs, int nx_seg, cu
   for (int i = 0; i < nx_seg; i++) g.seg[i] = xs[i];
   g.seg[nx_seg] = seg(h_old, H, e->gru[li].U, ld, H);
   g.n_seg = nx_seg + 1; g.N = 2 * H; g.C = e->zr; g.ldc = 2 * H;
-  n += launch_gemm_f32(g, st);
+  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
   // candidate: input part
   for (int i = 0; i < nx_seg; i++) { g.seg[i] = xs[i]; g.seg[i].B = xs[i].B + 2 * H; }
   g.n_seg = nx_seg; g.N = H; g.C = e->nx; g.ldc = H;
-  n += launch_gemm_f32(g, st);
+  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
   // candidate: recurrent part
   g.seg[0] = seg(h_old, H, e->gru[li].U + 2 * H, ld, H);
   g.n_seg = 1; g.N = H; g.C = e->nh; g.ldc = H;
-  n += launch_gemm_f32(g, st);
+  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
   GruGateArgs gg;
   gg.zr = e->zr; gg.nx = e->nx; gg.nh = e->nh; gg.bias = e->gru[li].b; gg.h_old = h_old; gg.h_new = h_new;
   gg.M = S; gg.H = H; gg.tansig = tbl;
-  n += launch_gru_gates(gg, st);
+  { ProfScope ps(e, PNB_K_GRU_GATES, st); n += launch_gru_gates(gg, st); }
   e->par[li] ^= 1;
   return n;
 }
@@ -330,7 +382,7 @@ static int nn_step_f32(pnb_engine *e, int t, cudaStream_t st) {
   const float *tbl = e->tansig();
   int n = 0;
   float *fc_out = e->ring_fc + (size_t)(c % 5) * S * 128;
-  n += launch_fc_f32(e->d_feat + (size_t)t * S * kFeat, e->fc.W, e->fc.b, fc_out, S, 70, 128, st);
+  { ProfScope ps(e, PNB_K_FC, st); n += launch_fc_f32(e->d_feat + (size_t)t * S * kFeat, e->fc.W, e->fc.b, fc_out, S, 70, 128, st); }
   GemmArgs g;
   memset(&g, 0, sizeof g);
   g.M = S; g.tansig = tbl;
@@ -339,11 +391,11 @@ static int nn_step_f32(pnb_engine *e, int t, cudaStream_t st) {
     g.seg[q] = seg(e->ring_fc + (size_t)(((c - 4 + q) % 5 + 5) % 5) * S * 128, 128, e->conv1.W + (size_t)q * 128 * 512, 512, 128);
   float *c1_out = e->ring_c1 + (size_t)(c % 3) * S * 512;
   g.n_seg = 5; g.N = 512; g.C = c1_out; g.ldc = 512; g.bias = e->conv1.b; g.act = e->act_conv1;
-  n += launch_gemm_f32(g, st);
+  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
   for (int q = 0; q < 3; q++)
     g.seg[q] = seg(e->ring_c1 + (size_t)(((c - 2 + q) % 3 + 3) % 3) * S * 512, 512, e->conv2.W + (size_t)q * 512 * 512, 512, 512);
   g.n_seg = 3; g.N = 512; g.C = e->c2; g.ldc = 512; g.bias = e->conv2.b; g.act = e->act_conv2;
-  n += launch_gemm_f32(g, st);
+  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
   // stacked GRUs: each consumes the freshly updated state of the one below
   GemmSeg xs[2];
   xs[0] = seg(e->c2, 512, e->gru[0].W, 1536, 512);
@@ -361,10 +413,10 @@ static int nn_step_f32(pnb_engine *e, int t, cudaStream_t st) {
   const float *cat[5] = {e->c2, e->h[0][e->par[0]], e->h[1][e->par[1]], e->h[2][e->par[2]], e->h[3][e->par[3]]};
   for (int q = 0; q < 5; q++) g.seg[q] = seg(cat[q], 512, e->fc_gb.W + (size_t)q * 512 * 34, 34, 512);
   g.n_seg = 5; g.N = 34; g.C = gr; g.ldc = 68; g.bias = e->fc_gb.b; g.act = e->act_gb;
-  n += launch_gemm_f32(g, st);
+  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
   g.seg[0] = seg(e->h[4][e->par[4]], 128, e->fc_rb.W, 34, 128);
   g.n_seg = 1; g.N = 34; g.C = gr + 34; g.ldc = 68; g.bias = e->fc_rb.b; g.act = e->act_rb;
-  n += launch_gemm_f32(g, st);
+  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
   return n;
 }
 
@@ -379,13 +431,13 @@ static int process_device(pnb_engine *e, const float *d_in, const short *d_in16,
   CK(cudaSetDevice(e->device));
   const int S = e->S;
   long long n = 0;
-  n += launch_stage_in(e->d_pcm, e->pcm_stride, d_in, d_in16, in_stride, S, F * kFrame, st);
+  { ProfScope ps(e, PNB_K_STAGE_IN, st); n += launch_stage_in(e->d_pcm, e->pcm_stride, d_in, d_in16, in_stride, S, F * kFrame, st); }
   AnalysisArgs a;
   a.pcm = e->d_pcm; a.pcm_stride = e->pcm_stride; a.n_streams = S; a.n_frames = F; a.tab = e->d_tab;
   a.feat = e->d_feat; a.X = e->d_X; a.P = e->d_P; a.Ex = e->d_Ex; a.silence = e->d_sil;
   a.last_period = e->d_last_period; a.last_gain = e->d_last_gain;
   a.tap_pitch = e->d_tap_pitch; a.tap_pitchf = e->d_tap_pitchf;
-  n += launch_analysis(a, st);
+  { ProfScope ps(e, PNB_K_ANALYSIS, st); n += launch_analysis(a, st); }
   for (int t = 0; t < F; t++) {
     if (e->flags & PNB_NN_TENSOR) {
       int k = tc_step(e, t, st);
@@ -399,8 +451,8 @@ static int process_device(pnb_engine *e, const float *d_in, const short *d_in16,
   s.X = e->d_X; s.P = e->d_P; s.gr = e->d_gr; s.Ex = e->d_Ex; s.silence = e->d_sil; s.n_streams = S; s.n_frames = F;
   s.tab = e->d_tab; s.synth_mem = e->d_synth; s.out = d_out; s.out16 = d_out16; s.out_stride = out_stride;
   s.postfilter = (e->flags & PNB_POSTFILTER) ? 1 : 0;
-  n += launch_synthesis(s, st);
-  n += launch_slide_history(e->d_pcm, e->pcm_stride, S, F * kFrame, st);
+  { ProfScope ps(e, PNB_K_SYNTHESIS, st); n += launch_synthesis(s, st); }
+  { ProfScope ps(e, PNB_K_SLIDE, st); n += launch_slide_history(e->d_pcm, e->pcm_stride, S, F * kFrame, st); }
   if (d_gr) CK(cudaMemcpyAsync(d_gr, e->d_gr, (size_t)F * S * 68 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   CK(cudaGetLastError());
   e->hop += F;

@@ -1,7 +1,9 @@
 // pnb_engine.h -- the engine object behind the opaque pnb_engine handle.
 #pragma once
 #include <stddef.h>
+#include <vector>
 #include "pnb_kernels.h"
+#include "../../include/percepnet_b200.h"
 #include "../../include/pnb_nnet_layout.h"
 
 struct pnb_tc_state;  // tensor-core path (pnb_nn_tc.cu)
@@ -50,6 +52,14 @@ struct pnb_engine {
   int last_frames = 0;
   long long launches = 0;
 
+  // optional per-kernel-class timing (pnb_profile_enable): CUDA events around every launch
+  bool profiling = false;
+  struct ProfRec { int cls; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[PNB_NUM_KERNEL_CLASSES] = {0};
+  long long prof_n[PNB_NUM_KERNEL_CLASSES] = {0};
+
   const float *tansig() const {
     return reinterpret_cast<const float *>(reinterpret_cast<const char *>(d_tab) + offsetof(pnb::Tables, tansig));
   }
@@ -61,3 +71,11 @@ void tc_release(pnb_engine *e);
 int tc_reset(pnb_engine *e);
 int tc_step(pnb_engine *e, int t, cudaStream_t st);
 int tc_launches_per_step(const pnb_engine *e);
+
+// RAII marker used by the launch schedule: records an event pair around a launch when profiling
+struct ProfScope {
+  pnb_engine *e; int idx;
+  ProfScope(pnb_engine *eng, int cls, cudaStream_t st);
+  ~ProfScope();
+  cudaStream_t st;
+};

@@ -13,7 +13,10 @@ namespace pnb {
 __device__ __forceinline__ float tansig_approx(float x, const float *__restrict__ tbl) {  // vec.h:53-71
   float sign = 1.f;
   if (x < 0.f) { x = -x; sign = -1.f; }
-  int i = (int)floorf(.5f + 25.f * x);
+  float fi = floorf(.5f + 25.f * x);
+  // the reference converts with x86 cvttss2si, which yields INT_MIN when out of range or NaN (then the
+  // clamp below lands on 0, not 200): keep that for |x| >= 8.6e7 so both sides leave the table the same way
+  int i = (fi < 2147483648.f) ? (int)fi : (int)0x80000000;
   i = i < 200 ? i : 200;
   i = i > 0 ? i : 0;
   x -= .04f * i;
