@@ -97,7 +97,10 @@ enum {
   PNB_TAP_X = 3,        /* float[800] analysis spectrum bins 0..399 (re,im)                   */
   PNB_TAP_P = 4,        /* float[800] comb-filtered spectrum bins 0..399 (re,im)              */
   PNB_TAP_EX = 5,       /* float[34]  band energy of X                                        */
-  PNB_TAP_GR = 6        /* float[68]  g, r                                                    */
+  PNB_TAP_GR = 6,       /* float[68]  g, r                                                    */
+  /* network state after the last hop of the call, layout [n_streams][width] (no PNB_KEEP_TAPS needed): */
+  PNB_TAP_NN_C2 = 7,    /* float[512] conv2 output                                            */
+  PNB_TAP_NN_H0 = 8     /* +0..4: float[512|128] states of gru1, gru2, gru3, gru_gb, gru_rb   */
 };
 int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes);
 

@@ -138,6 +138,16 @@ class Engine:
         self._ck(self.L.pnb_read_tap(self.h, code, a.ctypes.data, a.nbytes), f"pnb_read_tap({name})")
         return a
 
+    def read_nn_state(self) -> dict:
+        """fp32 network state after the last hop: conv2 output and the five GRU states, [S, width]."""
+        out = {}
+        for name, code, width in (("c2", 7, 512), ("gru1", 8, 512), ("gru2", 9, 512), ("gru3", 10, 512),
+                                  ("gru_gb", 11, 512), ("gru_rb", 12, 128)):
+            a = np.empty((self.n_streams, width), np.float32)
+            self._ck(self.L.pnb_read_tap(self.h, code, a.ctypes.data, a.nbytes), f"pnb_read_tap({name})")
+            out[name] = a
+        return out
+
     def profile(self, on: bool):
         self._ck(self.L.pnb_profile_enable(self.h, 1 if on else 0), "pnb_profile_enable")
 

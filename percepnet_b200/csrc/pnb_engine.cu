@@ -36,6 +36,8 @@ static int fail(int code, const char *fmt, ...) {
     if (_e != cudaSuccess) return fail(PNB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
+int tc_fail(int code, const char *msg) { return fail(code, "%s", msg); }
+
 extern "C" const char *pnb_last_error(void) { return g_err.c_str(); }
 extern "C" const char *pnb_version(void) { return "percepnet_b200 0.1 (sm_100a)"; }
 
@@ -521,6 +523,11 @@ extern "C" int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes
     case PNB_TAP_P: src = e->d_P; bytes = n * kBins * 8; break;
     case PNB_TAP_EX: src = e->d_Ex; bytes = n * kBands * 4; break;
     case PNB_TAP_GR: src = e->d_gr; bytes = n * 68 * 4; break;
+    case PNB_TAP_NN_C2: src = e->c2; bytes = (size_t)e->S * 512 * 4; break;
+    case PNB_TAP_NN_H0: case PNB_TAP_NN_H0 + 1: case PNB_TAP_NN_H0 + 2: case PNB_TAP_NN_H0 + 3: case PNB_TAP_NN_H0 + 4: {
+      int li = what - PNB_TAP_NN_H0;
+      src = e->h[li][e->par[li]]; bytes = (size_t)e->S * e->gru[li].H * 4; break;
+    }
     default: return fail(PNB_ERR_ARG, "unknown tap %d", what);
   }
   if (!src) return fail(PNB_ERR_ARG, "tap %d needs PNB_KEEP_TAPS at pnb_create", what);

@@ -1,0 +1,89 @@
+"""The tcgen05 network path (PNB_NN_TENSOR: split-fp16 / split-bf16 operands on the tensor cores, fp32
+accumulate in TMEM) against the oracle and against the fp32-FMA path.  Same bars as test_gpu_parity."""
+import numpy as np
+import pytest
+
+from test_gpu_parity import GR_RTOL, PCM_LSB, _inputs, _lsb_diff, _oracle_run, api  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def _report(tag, a, b):
+    d = np.abs(a - b)
+    print(f"{tag}: max abs {d.max():.3e}  max rel {(d / np.maximum(np.abs(b), 1e-6)).max():.3e}")
+    return d
+
+
+def test_layer_states_match_fp32_path(api, model0):
+    """Layer by layer (conv2 output and the five GRU states after 3 hops) against the fp32 path: localises
+    any descriptor / layout mistake to a layer."""
+    # unit scale: pre-activations are O(1), so differences measure the split-operand arithmetic itself (at int16
+    # scale the conv pre-activations are ~1e5 and fp32 accumulation ORDER alone moves tanh inputs by ~1e-2)
+    x = _inputs(1.0, 6, n_synth=6)
+    S = x.shape[0]
+    ref = api.Engine(S, 6, model0, api.NN_FP32)
+    ref.process(x)
+    want = ref.read_nn_state()
+    ref.close()
+    eng = api.Engine(S, 6, model0, api.NN_TENSOR)
+    eng.process(x)
+    got = eng.read_nn_state()
+    eng.close()
+    worst = 0.0
+    for k in ("c2", "gru1", "gru2", "gru3", "gru_gb", "gru_rb"):
+        d = _report(k, got[k], want[k])
+        worst = max(worst, float(d.max()))
+    assert worst < 5e-6
+
+
+@pytest.mark.parametrize("scale", [1.0, 256.0], ids=["unit", "x256"])
+def test_tensor_path_parity(api, oracle, model0, scale):
+    """unit: the CLI's scale (silence branch).  x256: loud enough that the comb-filter branch runs
+    (sum Ex >= 0.1) while the network stays inside the domain where the reference's tansig_approx is
+    defined (at full int16 scale feature 69, the raw pitch xcorr, is ~1e10 and the reference's float->int
+    conversion overflows: its conv2 "tanh" then returns its argument, ~1e9, which no 16-bit operand holds;
+    that regime is covered bit-faithfully by the fp32 path in test_gpu_parity)."""
+    F = 16
+    x = _inputs(scale, F)
+    if scale != 1.0:
+        x = (x * np.float32(4.0)).astype(np.float32)      # _inputs applies 0.25 to the edge signals at scale != 1
+    S = x.shape[0]
+    ref_out, ref_gr, _ = _oracle_run(oracle, model0, x)
+    _, _, taps = _oracle_run(oracle, model0, x[:2]) if scale != 1.0 else (None, None, None)
+    if taps is not None:
+        assert sum(1 for t in taps[0] if not t.silence) >= 8
+    eng = api.Engine(S, 8, model0, api.NN_TENSOR)
+    out, gr = eng.process_stream_chunks(x, want_gr=True)
+    eng.close()
+    rel = np.abs(gr - ref_gr) / np.maximum(np.abs(ref_gr), 1e-6)
+    print(f"tensor path g/r max rel err {rel.max():.3e}; PCM max LSB diff {_lsb_diff(out, ref_out, scale == 1.0)}")
+    # At x256 the conv pre-activations are ~1e5: the reference's own sequential fp32 sums carry ~1e-1 of
+    # rounding noise there, so ANY other summation order moves g/r by a few 1e-4 (the fp32-FMA path does too);
+    # the 1e-4 bar is asserted at the CLI scale, where the network is well conditioned.
+    assert rel.max() < (GR_RTOL if scale == 1.0 else 2e-3)
+    k = 32768.0 / scale                     # LSBs of the int16 grid this amplitude scale corresponds to
+    assert np.abs(np.trunc(out.astype(np.float64) * k) - np.trunc(ref_out.astype(np.float64) * k)).max() <= PCM_LSB
+
+
+def test_tensor_path_hot_weights(api, oracle, model_hot):
+    x = _inputs(1.0, 10, n_synth=3)[:5]
+    ref_out, ref_gr, _ = _oracle_run(oracle, model_hot, x)
+    eng = api.Engine(x.shape[0], 10, model_hot, api.NN_TENSOR)
+    out, gr = eng.process(x, want_gr=True)
+    eng.close()
+    assert np.abs(gr - ref_gr).max() < 1e-4
+    assert _lsb_diff(out, ref_out, True) <= PCM_LSB
+
+
+def test_tensor_path_batch_independence(api, model0):
+    base = (_inputs(1.0, 5, n_synth=8)[:8] * np.float32(256.0)).astype(np.float32)
+    S = 1024 + 40                       # not a multiple of the 128-row tile
+    x = np.tile(base, (S // 8, 1))
+    eng = api.Engine(S, 5, model0, api.NN_TENSOR)
+    out, gr = eng.process(x, want_gr=True)
+    eng.close()
+    assert np.array_equal(out.reshape(S // 8, 8, -1), np.broadcast_to(out[:8], (S // 8, 8, out.shape[1])))
+    small = api.Engine(8, 5, model0, api.NN_TENSOR)
+    o_s, g_s = small.process(base, want_gr=True)
+    small.close()
+    assert np.array_equal(o_s, out[:8]) and np.array_equal(g_s, gr[:, :8])
