@@ -125,12 +125,14 @@ __device__ void fft960_warp(float2 *f, const float2 *tw, int lane) {
 }
 
 // window a real 960-sample block (denoise.cpp:282-289) and place it, scaled by 1/960, in FFT order
-__device__ __forceinline__ void load_real_windowed(float2 *f, const float *src, const float *hw, int lane) {
+__device__ __forceinline__ void load_real_windowed(float2 *f, const float *src, const float *hw, const short *slot,
+                                                   int lane) {
   const float scale = 1.f / kWin;
+#pragma unroll 6
   for (int i = lane; i < kWin; i += 32) {
     float w = hw[i < kFrame ? i : kWin - 1 - i];
     float v = src[i] * w;
-    f[fft_slot(i)] = make_float2(scale * v, 0.f);
+    f[slot[i]] = make_float2(scale * v, 0.f);
   }
 }
 
@@ -158,8 +160,9 @@ __device__ void band_pool_warp(const float *v, float *out, const float *frac, co
 
 // pitch.cpp:46-104 (float build): best two lags by xcorr^2/Syy with the reference's update rule.
 // y has element stride `ys` in shared memory.  Runs on one lane.
-__device__ void best_two(const float *xcorr, const float *y, int ys, int len, int max_pitch, float syy,
-                         int &b0, int &b1) {
+// dsyy[i] = y[i+len]^2 - y[i]^2 has been precomputed by the whole warp (same expression as the reference's
+// running update), so the serial part is one add and one max per lag.
+__device__ void best_two(const float *xcorr, const float *dsyy, int max_pitch, float syy, int &b0, int &b1) {
   float num0 = -1.f, num1 = -1.f, den0 = 0.f, den1 = 0.f;
   b0 = 0;
   b1 = 1;
@@ -177,8 +180,7 @@ __device__ void best_two(const float *xcorr, const float *y, int ys, int len, in
         }
       }
     }
-    float yn = y[(i + len) * ys], yo = y[i * ys];
-    syy = syy + (yn * yn - yo * yo);
+    syy = syy + dsyy[i];
     syy = 1.f > syy ? 1.f : syy;
   }
 }
@@ -187,17 +189,23 @@ __device__ __forceinline__ float pitch_gain(float xy, float xx, float yy) {
   return xy / sqrtf(1.f + xx * yy);  // pitch.cpp:417-420 (float sqrt overload)
 }
 
-struct WarpSmem {
-  float2 fft[kWin];    // FFT work line
+struct PitchSmem {
   float lp[kLp];       // decimated, whitened pitch buffer
-  float xc[400];       // xcorr (147 / 294) -- doubles as the per-bin scratch of band pooling
-  float yy[392];       // yy_lookup of remove_doubling (385 used)
-  float Ex[kBands], Ep[kBands], Exp[kBands], Ey[kBands];
+  float yy[392];       // yy_lookup of remove_doubling (385 used); before that the energy deltas of the lag scans
   float cand_xy[32];   // per-candidate cross products of remove_doubling
+};
+struct WarpSmem {
+  union {              // the pitch stage runs strictly between the two transforms of a hop
+    float2 fft[kWin];  // FFT work line
+    PitchSmem p;
+  };
+  float xc[400];       // xcorr (147 / 294) -- doubles as the per-bin scratch of band pooling
+  float Ex[kBands], Ep[kBands], Exp[kBands], Ey[kBands];
 };
 
 struct BlockSmem {
   float2 tw[kWin];
+  short slot[kWin];    // digit-reversed position of every input sample
   float hw[kFrame];
   float frac[kBins];
   float omf[kBins];
@@ -205,7 +213,7 @@ struct BlockSmem {
   float comb_w[8];
 };
 
-constexpr int kAnaWarps = 4;
+constexpr int kAnaWarps = 8;
 
 __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
   WarpSmem *Wall = reinterpret_cast<WarpSmem *>(smem_raw + ((sizeof(BlockSmem) + 15) / 16) * 16);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const Tables *T = A.tab;
-  for (int i = threadIdx.x; i < kWin; i += blockDim.x) B.tw[i] = T->tw[i];
+  for (int i = threadIdx.x; i < kWin; i += blockDim.x) { B.tw[i] = T->tw[i]; B.slot[i] = (short)fft_slot(i); }
   for (int i = threadIdx.x; i < kFrame; i += blockDim.x) B.hw[i] = T->half_window[i];
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) { B.frac[i] = T->frac[i]; B.omf[i] = T->omf[i]; }
   if (threadIdx.x < kBands + 2) B.border[threadIdx.x] = T->border[threadIdx.x];
@@ -231,31 +239,33 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
     const float *line = row + (size_t)t * kFrame;  // line[j] == reference comb_buf[j] at this hop
     const size_t fs = (size_t)t * A.n_streams + s;
 
-    // ---- analysis spectrum X of the hop delayed by five (denoise.cpp:402, :333-346) ----
-    load_real_windowed(W.fft, line + kOffAnalysis, B.hw, lane);
+    // ---- one transform per hop.  The look-ahead window of hop c (denoise.cpp:498-506: the newest 960
+    // samples) is the very block whose spectrum is the analysis spectrum X five hops later (:402, :333-346:
+    // line[2400..3360) at hop c+5 == line[4800..5760) at hop c), so each windowed block is transformed once,
+    // kept in a per-stream ring of spectra / band energies, and read back as X and Ex when it comes due.
+    const long c = A.hop0 + t;
+    const int slot_new = (int)(c % A.ring), slot_x = (int)(((c - 5) % A.ring + A.ring) % A.ring);
+    load_real_windowed(W.fft, line + kOffLook, B.hw, B.slot, lane);
     fft960_warp(W.fft, B.tw, lane);
     {
-      float2 *Xg = A.X + fs * kBins;
+      float2 *Zg = A.zring + ((size_t)slot_new * A.n_streams + s) * kBins;
       for (int k = lane; k < kBins; k += 32) {
         float2 x = W.fft[k];
-        Xg[k] = x;
+        Zg[k] = x;
         float e = x.x * x.x;
         e += x.y * x.y;
         W.xc[k] = e;
       }
-      band_pool_warp(W.xc, W.Ex, B.frac, B.omf, B.border, lane);
+      band_pool_warp(W.xc, W.Ey, B.frac, B.omf, B.border, lane);
+      float *Eg = A.ering + ((size_t)slot_new * A.n_streams + s) * kBands;
+      const float *Eo = A.ering + ((size_t)slot_x * A.n_streams + s) * kBands;
+      for (int b = lane; b < kBands; b += 32) {
+        Eg[b] = W.Ey[b];
+        W.Ex[b] = Eo[b];  // written five hops ago (by this warp, or by the previous call)
+      }
     }
-
-    // ---- look-ahead band energies from the newest 960 samples (denoise.cpp:498-506) ----
-    load_real_windowed(W.fft, line + kOffLook, B.hw, lane);
-    fft960_warp(W.fft, B.tw, lane);
-    for (int k = lane; k < kBins; k += 32) {
-      float2 x = W.fft[k];
-      float e = x.x * x.x;
-      e += x.y * x.y;
-      W.xc[k] = e;
-    }
-    band_pool_warp(W.xc, W.Ey, B.frac, B.omf, B.border, lane);
+    const float2 *Xg = A.zring + ((size_t)slot_x * A.n_streams + s) * kBins;
+    __syncwarp();
 
     // ---- pitch_downsample (pitch.cpp:148-216) ----
     {
@@ -264,17 +274,17 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         float v;
         if (i == 0) v = .5f * (.5f * src[1] + src[0]);
         else v = .5f * (.5f * (src[2 * i - 1] + src[2 * i + 1]) + src[2 * i]);
-        W.lp[i] = v;
+        W.p.lp[i] = v;
       }
       __syncwarp();
       // autocorrelation, 5 lags: bulk over 860 samples then the 4-sample tail (celt_lpc.cpp:250-256)
       float ac = 0.f;
       if (lane < 5) {
-        const float *a = W.lp, *b = W.lp + lane;
+        const float *a = W.p.lp, *b = W.p.lp + lane;
 #pragma unroll 4
         for (int j = 0; j < 860; j++) ac = ac + a[j] * b[j];
         float d = 0.f;
-        for (int i = lane + 860; i < kLp; i++) d = d + W.lp[i] * W.lp[i - lane];
+        for (int i = lane + 860; i < kLp; i++) d = d + W.p.lp[i] * W.p.lp[i - lane];
         ac += d;
       }
       float ac0 = __shfl_sync(0xffffffffu, ac, 0), ac1 = __shfl_sync(0xffffffffu, ac, 1),
@@ -320,9 +330,9 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
       // still see unfiltered samples
       for (int base = kLp - 32; base >= 0; base -= 32) {
         int i = base + lane;
-        float x0 = W.lp[i];
-        float m0 = i >= 1 ? W.lp[i - 1] : 0.f, m1 = i >= 2 ? W.lp[i - 2] : 0.f, m2 = i >= 3 ? W.lp[i - 3] : 0.f,
-              m3 = i >= 4 ? W.lp[i - 4] : 0.f, m4 = i >= 5 ? W.lp[i - 5] : 0.f;
+        float x0 = W.p.lp[i];
+        float m0 = i >= 1 ? W.p.lp[i - 1] : 0.f, m1 = i >= 2 ? W.p.lp[i - 2] : 0.f, m2 = i >= 3 ? W.p.lp[i - 3] : 0.f,
+              m3 = i >= 4 ? W.p.lp[i - 4] : 0.f, m4 = i >= 5 ? W.p.lp[i - 5] : 0.f;
         float sum = x0;
         sum = sum + fir0 * m0;
         sum = sum + fir1 * m1;
@@ -330,7 +340,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         sum = sum + fir3 * m3;
         sum = sum + fir4 * m4;
         __syncwarp();
-        W.lp[i] = sum;
+        W.p.lp[i] = sum;
         __syncwarp();
       }
     }
@@ -339,32 +349,55 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
     int pitch_lag, T;
     float pitch_corr, gain;
     {
-      // coarse: 4x-decimated signals are stride-2 views of lp; lag L = lane + 32 q
-      float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      const bool syy_lane = (lane == 31);  // q = 4 is unused there (lag 159 > 146): it accumulates Syy
-      if (syy_lane) acc[4] = 1.f;
-      const float *x4 = W.lp + 384;
-#pragma unroll 2
-      for (int j = 0; j < 240; j++) {
-        float xj = x4[2 * j];
-#pragma unroll
-        for (int q = 0; q < 4; q++) acc[q] = acc[q] + xj * W.lp[2 * (j + lane + 32 * q)];
-        if (lane < 19) acc[4] = acc[4] + xj * W.lp[2 * (j + lane + 128)];
-        else if (syy_lane) { float y = W.lp[2 * j]; acc[4] = acc[4] + y * y; }
+      int b0, b1;
+      // coarse: the 4x-decimated signals are stride-2 views of lp.  Lane l < 30 owns the five adjacent lags
+      // 5l .. 5l+4 and slides a five-sample window of y along, so each step costs one new y load; every lag
+      // still accumulates in ascending j exactly like the reference (pitch.cpp:218-281).  Lane 30 accumulates the
+      // energy Syy = 1 + sum y4[j]^2 of find_best_pitch (pitch.cpp:54,69-70) through the same code shape.
+      {
+        const float *xb = (lane == 30) ? W.p.lp : W.p.lp + 384;
+        const int L = (lane < 30) ? 5 * lane : 0;
+        const float *yb = W.p.lp + 2 * L;
+        float acc0 = (lane == 30) ? 1.f : 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, acc4 = 0.f;
+        float w0 = yb[0], w1 = yb[2], w2 = yb[4], w3 = yb[6], w4 = yb[8];
+        for (int j = 0; j < 240; j += 5) {
+          float xj;
+#define PNB_STEP(A0, A1, A2, A3, A4, JJ)                                                   \
+          xj = xb[2 * (j + JJ)];                                                           \
+          acc0 = acc0 + xj * A0; acc1 = acc1 + xj * A1; acc2 = acc2 + xj * A2;            \
+          acc3 = acc3 + xj * A3; acc4 = acc4 + xj * A4;                                    \
+          A0 = yb[2 * (j + JJ + 5)];
+          PNB_STEP(w0, w1, w2, w3, w4, 0)
+          PNB_STEP(w1, w2, w3, w4, w0, 1)
+          PNB_STEP(w2, w3, w4, w0, w1, 2)
+          PNB_STEP(w3, w4, w0, w1, w2, 3)
+          PNB_STEP(w4, w0, w1, w2, w3, 4)
+#undef PNB_STEP
+        }
+        if (lane < 30) {
+          W.xc[L] = acc0; W.xc[L + 1] = acc1;
+          if (L + 2 < 147) { W.xc[L + 2] = acc2; W.xc[L + 3] = acc3; W.xc[L + 4] = acc4; }
+        }
+        // energy deltas of the coarse scan: y4[i+240]^2 - y4[i]^2 (pitch.cpp:101)
+        for (int i = lane; i < 147; i += 32) {
+          float yn = W.p.lp[2 * (i + 240)], yo = W.p.lp[2 * i];
+          W.p.yy[i] = yn * yn - yo * yo;
+        }
+        float syy_c = __shfl_sync(0xffffffffu, acc0, 30);
+        __syncwarp();
+        b0 = 0; b1 = 0;
+        if (lane == 0) best_two(W.xc, W.p.yy, 147, syy_c, b0, b1);
+        b0 = __shfl_sync(0xffffffffu, b0, 0);
+        b1 = __shfl_sync(0xffffffffu, b1, 0);
+        __syncwarp();
       }
-#pragma unroll
-      for (int q = 0; q < 4; q++) W.xc[lane + 32 * q] = acc[q];
-      if (lane < 19) W.xc[lane + 128] = acc[4];
-      float syy_c = __shfl_sync(0xffffffffu, acc[4], 31);
-      __syncwarp();
-      int b0 = 0, b1 = 0;
-      if (lane == 0) best_two(W.xc, W.lp, 2, 240, 147, syy_c, b0, b1);
-      b0 = __shfl_sync(0xffffffffu, b0, 0);
-      b1 = __shfl_sync(0xffffffffu, b1, 0);
-      __syncwarp();
       // fine: at most ten lags around 2*b0 and 2*b1 (pitch.cpp:344-361); lane 10 accumulates Syy of the
       // second find_best_pitch, lane 11 the xx of remove_doubling (pitch.cpp:448)
-      for (int i = lane; i < 294; i += 32) W.xc[i] = 0.f;
+      for (int i = lane; i < 294; i += 32) {
+        W.xc[i] = 0.f;
+        float yn = W.p.lp[i + 480], yo = W.p.lp[i];  // energy deltas of the fine scan
+        W.p.yy[i] = yn * yn - yo * yo;
+      }
       __syncwarp();
       int fl = -1;
       if (lane < 5) fl = 2 * b0 - 2 + lane;
@@ -374,10 +407,10 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
       {
         const float *a, *b;
         int n = 480;
-        if (lane < 10) { a = W.lp + 384; b = W.lp + (fine_ok ? fl : 0); if (!fine_ok) n = 0; }
-        else if (lane == 10) { a = W.lp; b = W.lp; }
-        else if (lane == 11) { a = W.lp + 384; b = W.lp + 384; }
-        else { a = W.lp; b = W.lp; n = 0; }
+        if (lane < 10) { a = W.p.lp + 384; b = W.p.lp + (fine_ok ? fl : 0); if (!fine_ok) n = 0; }
+        else if (lane == 10) { a = W.p.lp; b = W.p.lp; }
+        else if (lane == 11) { a = W.p.lp + 384; b = W.p.lp + 384; }
+        else { a = W.p.lp; b = W.p.lp; n = 0; }
 #pragma unroll 4
         for (int j = 0; j < n; j++) s = s + a[j] * b[j];
       }
@@ -389,7 +422,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
       float corr = 0.f;
       if (lane == 0) {
         int c0, c1;
-        best_two(W.xc, W.lp, 1, 480, 294, syy_f, c0, c1);
+        best_two(W.xc, W.p.yy, 294, syy_f, c0, c1);
         if (c0 > 0 && c0 < 293) {
           float a = W.xc[c0 - 1], b = W.xc[c0], c = W.xc[c0 + 1];
           if ((c - a) > .7f * (b - a)) off = 1;
@@ -403,7 +436,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
 
       // ---- remove_doubling (pitch.cpp:423-527) with maxperiod 384, minperiod 30, N 480 ----
       const int second_check[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};
-      const float *x = W.lp + 384;
+      const float *x = W.p.lp + 384;
       int T0 = (kMaxPeriod - pitch_lag) / 2;
       if (T0 >= 384) T0 = 383;
       const int prev_period = last_period / 2;
@@ -422,11 +455,11 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         }
         if (lane == 1) {
           float yy = xx;
-          W.yy[0] = xx;
+          W.p.yy[0] = xx;
           for (int i = 1; i <= 384; i++) {
             float a = x[-i], b = x[480 - i];
             yy = yy + a * a - b * b;
-            W.yy[i] = 0.f > yy ? 0.f : yy;
+            W.p.yy[i] = 0.f > yy ? 0.f : yy;
           }
         } else {
           float d = 0.f;
@@ -435,15 +468,15 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
 #pragma unroll 4
             for (int j = 0; j < 480; j++) d = d + x[j] * b[j];
           }
-          W.cand_xy[lane] = d;
+          W.p.cand_xy[lane] = d;
         }
       }
       __syncwarp();
       int Tsel = T0;
       float g = 0.f, best_xy = 0.f, best_yy = 0.f;
       if (lane == 0) {
-        float xy = W.cand_xy[0];
-        float yy = W.yy[T0];
+        float xy = W.p.cand_xy[0];
+        float yy = W.p.yy[T0];
         best_xy = xy;
         best_yy = yy;
         float g0 = pitch_gain(xy, xx, yy);
@@ -454,9 +487,9 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
           int T1b;
           if (k == 2) T1b = (T1 + T0 > 384) ? T0 : T0 + T1;
           else T1b = (2 * second_check[k] * T0 + k) / (2 * k);
-          float xy1 = W.cand_xy[2 + 2 * (k - 2)], xy2 = W.cand_xy[3 + 2 * (k - 2)];
+          float xy1 = W.p.cand_xy[2 + 2 * (k - 2)], xy2 = W.p.cand_xy[3 + 2 * (k - 2)];
           xy = .5f * (xy1 + xy2);
-          yy = .5f * (W.yy[T1] + W.yy[T1b]);
+          yy = .5f * (W.p.yy[T1] + W.p.yy[T1b]);
           float g1 = pitch_gain(xy, xx, yy);
           float cont;
           int dT = T1 - prev_period;
@@ -506,6 +539,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
     }
 
     // ---- comb-filtered block, its spectrum P and the band statistics (denoise.cpp:416-427) ----
+    __syncwarp();  // the pitch scratch is dead from here on; its storage becomes the FFT line again
     {
       const float scale = 1.f / kWin;
       for (int i = lane; i < kWin; i += 32) {
@@ -514,11 +548,10 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         for (int k = -3; k <= 3; k++) p = p + line[kOffAnalysis - T * k + i] * B.comb_w[k + 3];
         float w = B.hw[i < kFrame ? i : kWin - 1 - i];
         float v = p * w;
-        W.fft[fft_slot(i)] = make_float2(scale * v, 0.f);
+        W.fft[B.slot[i]] = make_float2(scale * v, 0.f);
       }
       fft960_warp(W.fft, B.tw, lane);
       float2 *Pg = A.P + fs * kBins;
-      const float2 *Xg = A.X + fs * kBins;
       for (int k = lane; k < kBins; k += 32) {
         float2 p = W.fft[k];
         Pg[k] = p;
@@ -528,7 +561,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
       }
       band_pool_warp(W.xc, W.Ep, B.frac, B.omf, B.border, lane);
       for (int k = lane; k < kBins; k += 32) {
-        float2 p = W.fft[k], x = Xg[k];  // Xg was written by this warp above (same lanes, same k)
+        float2 p = W.fft[k], x = Xg[k];
         float e = x.x * p.x;
         e += x.y * p.y;
         W.xc[k] = e;
@@ -580,6 +613,7 @@ struct SynWarpSmem {
 };
 struct SynBlockSmem {
   float2 tw[kWin];
+  short slot[kWin];
   float hw[kFrame];
   float frac[kBins];
   float omf[kBins];
@@ -593,7 +627,7 @@ __global__ void __launch_bounds__(kSynWarps * 32) synthesis_kernel(SynthesisArgs
   SynWarpSmem *Wall = reinterpret_cast<SynWarpSmem *>(smem_raw + ((sizeof(SynBlockSmem) + 15) / 16) * 16);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const Tables *T = A.tab;
-  for (int i = threadIdx.x; i < kWin; i += blockDim.x) B.tw[i] = T->tw[i];
+  for (int i = threadIdx.x; i < kWin; i += blockDim.x) { B.tw[i] = T->tw[i]; B.slot[i] = (short)fft_slot(i); }
   for (int i = threadIdx.x; i < kFrame; i += blockDim.x) B.hw[i] = T->half_window[i];
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
     B.frac[i] = T->frac[i];
@@ -636,7 +670,9 @@ __global__ void __launch_bounds__(kSynWarps * 32) synthesis_kernel(SynthesisArgs
       __syncwarp();
     }
     const bool silence = A.silence[fs] != 0;
-    const float2 *Xg = A.X + fs * kBins, *Pg = A.P + fs * kBins;
+    const long c = A.hop0 + t;
+    const int slot_x = (int)(((c - 5) % A.ring + A.ring) % A.ring);
+    const float2 *Xg = A.zring + ((size_t)slot_x * A.n_streams + s) * kBins, *Pg = A.P + fs * kBins;
     const float scale = 1.f / kWin;
     // bins 0..399 and their mirror images; everything from 400 to 560 is zero
     for (int i = lane; i < kWin; i += 32) {
@@ -660,7 +696,7 @@ __global__ void __launch_bounds__(kSynWarps * 32) synthesis_kernel(SynthesisArgs
         x.y *= gf;
         v = (i <= kFrame) ? x : make_float2(x.x, -x.y);  // Hermitian extension, :314-317
       }
-      W.fft[fft_slot(i)] = make_float2(scale * v.x, scale * v.y);
+      W.fft[B.slot[i]] = make_float2(scale * v.x, scale * v.y);
     }
     fft960_warp(W.fft, B.tw, lane);
     // time samples are read back reversed and rescaled (denoise.cpp:318-323), windowed, overlap-added

@@ -210,7 +210,9 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
   CKD(dalloc(&e->d_last_gain, S));
   // per-call buffers
   CKD(dalloc(&e->d_feat, F * S * kFeat));
-  CKD(dalloc(&e->d_X, F * S * kBins));
+  e->ring = (int)F + 5;
+  CKD(dalloc(&e->d_zring, (size_t)e->ring * S * kBins));
+  CKD(dalloc(&e->d_ering, (size_t)e->ring * S * kBands));
   CKD(dalloc(&e->d_P, F * S * kBins));
   CKD(dalloc(&e->d_Ex, F * S * kBands));
   CKD(dalloc(&e->d_sil, F * S));
@@ -252,7 +254,8 @@ extern "C" void pnb_destroy(pnb_engine *e) {
     if (e->gru[i].b) cudaFree(e->gru[i].b);
     for (int p = 0; p < 2; p++) if (e->h[i][p]) cudaFree(e->h[i][p]);
   }
-  if (e->d_X) cudaFree(e->d_X);
+  if (e->d_zring) cudaFree(e->d_zring);
+  if (e->d_ering) cudaFree(e->d_ering);
   if (e->d_P) cudaFree(e->d_P);
   if (e->d_sil) cudaFree(e->d_sil);
   if (e->d_last_period) cudaFree(e->d_last_period);
@@ -273,6 +276,8 @@ extern "C" int pnb_reset(pnb_engine *e) {
   const size_t S = e->S;
   CK(cudaMemset(e->d_pcm, 0, S * e->pcm_stride * sizeof(float)));
   CK(cudaMemset(e->d_synth, 0, S * kFrame * sizeof(float)));
+  CK(cudaMemset(e->d_zring, 0, (size_t)e->ring * S * kBins * sizeof(float2)));
+  CK(cudaMemset(e->d_ering, 0, (size_t)e->ring * S * kBands * sizeof(float)));
   CK(cudaMemset(e->d_last_period, 0, S * sizeof(int)));
   CK(cudaMemset(e->d_last_gain, 0, S * sizeof(float)));
   CK(cudaMemset(e->ring_fc, 0, 5 * S * 128 * sizeof(float)));
@@ -436,7 +441,8 @@ static int process_device(pnb_engine *e, const float *d_in, const short *d_in16,
   { ProfScope ps(e, PNB_K_STAGE_IN, st); n += launch_stage_in(e->d_pcm, e->pcm_stride, d_in, d_in16, in_stride, S, F * kFrame, st); }
   AnalysisArgs a;
   a.pcm = e->d_pcm; a.pcm_stride = e->pcm_stride; a.n_streams = S; a.n_frames = F; a.tab = e->d_tab;
-  a.feat = e->d_feat; a.X = e->d_X; a.P = e->d_P; a.Ex = e->d_Ex; a.silence = e->d_sil;
+  a.feat = e->d_feat; a.zring = e->d_zring; a.ering = e->d_ering; a.ring = e->ring; a.hop0 = e->hop;
+  a.P = e->d_P; a.Ex = e->d_Ex; a.silence = e->d_sil;
   a.last_period = e->d_last_period; a.last_gain = e->d_last_gain;
   a.tap_pitch = e->d_tap_pitch; a.tap_pitchf = e->d_tap_pitchf;
   { ProfScope ps(e, PNB_K_ANALYSIS, st); n += launch_analysis(a, st); }
@@ -450,7 +456,7 @@ static int process_device(pnb_engine *e, const float *d_in, const short *d_in16,
     }
   }
   SynthesisArgs s;
-  s.X = e->d_X; s.P = e->d_P; s.gr = e->d_gr; s.Ex = e->d_Ex; s.silence = e->d_sil; s.n_streams = S; s.n_frames = F;
+  s.zring = e->d_zring; s.ring = e->ring; s.hop0 = e->hop; s.P = e->d_P; s.gr = e->d_gr; s.Ex = e->d_Ex; s.silence = e->d_sil; s.n_streams = S; s.n_frames = F;
   s.tab = e->d_tab; s.synth_mem = e->d_synth; s.out = d_out; s.out16 = d_out16; s.out_stride = out_stride;
   s.postfilter = (e->flags & PNB_POSTFILTER) ? 1 : 0;
   { ProfScope ps(e, PNB_K_SYNTHESIS, st); n += launch_synthesis(s, st); }
@@ -519,7 +525,18 @@ extern "C" int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes
     case PNB_TAP_FEATURES: src = e->d_feat; bytes = n * kFeat * 4; break;
     case PNB_TAP_PITCH: src = e->d_tap_pitch; bytes = n * 16; break;
     case PNB_TAP_PITCHF: src = e->d_tap_pitchf; bytes = n * 8; break;
-    case PNB_TAP_X: src = e->d_X; bytes = n * kBins * 8; break;
+    case PNB_TAP_X: {  // gather from the ring: the analysis spectrum of hop c is the slot of hop c-5
+      bytes = n * kBins * 8;
+      if (dst_bytes < bytes) return fail(PNB_ERR_ARG, "tap %d needs %zu bytes, got %zu", what, bytes, dst_bytes);
+      CK(cudaDeviceSynchronize());
+      const size_t per = (size_t)e->S * kBins * 8;
+      for (int k = 0; k < e->last_frames; k++) {
+        long c = e->hop - e->last_frames + k;
+        int slot = (int)(((c - 5) % e->ring + e->ring) % e->ring);
+        CK(cudaMemcpy((char *)dst + k * per, (const char *)e->d_zring + slot * per, per, cudaMemcpyDeviceToHost));
+      }
+      return PNB_OK;
+    }
     case PNB_TAP_P: src = e->d_P; bytes = n * kBins * 8; break;
     case PNB_TAP_EX: src = e->d_Ex; bytes = n * kBands * 4; break;
     case PNB_TAP_GR: src = e->d_gr; bytes = n * 68 * 4; break;

@@ -28,7 +28,10 @@ struct pnb_engine {
 
   // per-call intermediates [F][S][...]
   float *d_feat = nullptr;
-  float2 *d_X = nullptr, *d_P = nullptr;
+  float2 *d_zring = nullptr;  // [ring][S][400] carried spectra (see pnb_dsp.cu), slot = hop % ring
+  float *d_ering = nullptr;   // [ring][S][34]
+  int ring = 0;
+  float2 *d_P = nullptr;
   float *d_Ex = nullptr;
   unsigned char *d_sil = nullptr;
   float *d_gr = nullptr;

@@ -11,7 +11,11 @@ struct AnalysisArgs {
   int n_streams, n_frames;
   const Tables *tab;
   float *feat;             // [F][S][70]
-  float2 *X, *P;           // [F][S][400]
+  float2 *zring;           // [ring][S][400] spectra of the windowed blocks, slot = hop % ring (carried state)
+  float *ering;            // [ring][S][34] their band energies
+  int ring;                // slots (>= n_frames + 5)
+  long hop0;               // absolute index of the call's first hop
+  float2 *P;               // [F][S][400]
   float *Ex;               // [F][S][34] or null
   unsigned char *silence;  // [F][S]
   int *last_period;        // [S] carried state
@@ -21,7 +25,10 @@ struct AnalysisArgs {
 };
 
 struct SynthesisArgs {
-  const float2 *X, *P;     // [F][S][400]
+  const float2 *zring;     // analysis spectrum of hop c is the ring slot of hop c-5
+  int ring;
+  long hop0;
+  const float2 *P;         // [F][S][400]
   const float *gr;         // [F][S][68]
   const float *Ex;         // [F][S][34] (post-filter only)
   const unsigned char *silence;
