@@ -265,11 +265,8 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * S * F * K / (ms_max * 1e-3)
+    from percepnet_b200.sharding import aggregate_throughput
+    _, ms_max, value = aggregate_throughput(S * F * K, ms, device=device)   # sum of frames, max of device time
 
     # ---- kernel breakdown of one more (untimed) step, CUDA events around every launch -----
     eng.profile(True)

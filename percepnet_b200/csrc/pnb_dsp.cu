@@ -39,101 +39,141 @@ __device__ __forceinline__ int fft_slot(int i) {
   return 192 * n0 + 64 * n1 + 16 * n2 + 4 * n3 + i;
 }
 
-__device__ void fft960_warp(float2 *f, const float2 *tw, int lane) {
+// Work-line layout: element e lives at float2 index e + 2 (e >> 4), i.e. 16 bytes of padding after every 16
+// complex values, so that a lane's 128-byte block and the stride-16 / stride-192 walks of the later passes
+// are free of shared-memory bank conflicts.
+constexpr int kFftLine = kWin + 2 * (kWin / 16);  // 1080 float2
+__device__ __forceinline__ int fpos(int e) { return e + 2 * (e >> 4); }
+
+struct FftTw {            // per-block tables in shared memory
+  float2 tw[kWin];        // exp(-2 pi i k / 960)                       (kiss_fft.cpp:415-419)
+  float2 tw5[4][192];     // tw[m u], m = 1..4: the radix-5 twiddles, contiguous in u
+};
+
+// Three register-blocked passes over the five kiss_fft stages (kiss_fft.cpp:518-564: radix 4,4,4,3,5 with
+// m = 1,4,16,64,192 on the digit-reversed, 1/960-scaled input).  Every butterfly performs exactly the
+// reference's operations in the reference's order; only the order BETWEEN independent butterflies differs.
+//   pass A: lane loads the 16 inputs of a 16-element output block straight from `load(i)` (no scatter
+//           through shared memory), does radix-4 m=1 and radix-4 m=4 in registers, stores 128 contiguous bytes
+//   pass B: radix-4 m=16 then radix-3 m=64 on the 12 elements {192 n0 + 64 r + 16 q + j}
+//   pass C: radix-5 m=192
+template <bool kAllOutputs, class Load>
+__device__ __forceinline__ void fft960_warp(float2 *f, const FftTw &T, int lane, Load load) {
   __syncwarp();
-  // radix-4, m = 1: 240 butterflies on adjacent quads (kiss_fft.cpp:112-131)
-  for (int b = lane; b < 240; b += 32) {
-    float2 *q = f + 4 * b;
-    float2 a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3];
-    float2 d02 = csub(a0, a2);
-    a0 = cadd(a0, a2);
-    float2 s13 = cadd(a1, a3);
-    a2 = csub(a0, s13);
-    a0 = cadd(a0, s13);
-    float2 d13 = csub(a1, a3);
-    q[0] = a0;
-    q[2] = a2;
-    q[1] = make_float2(d02.x + d13.y, d02.y - d13.x);
-    q[3] = make_float2(d02.x - d13.y, d02.y + d13.x);
-  }
-  __syncwarp();
-  // radix-4 with twiddles, m = 4 (60 groups, twiddle stride 60) then m = 16 (15 groups, stride 15)
-#pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
-    const int m = pass ? 16 : 4, tws = pass ? 15 : 60, sh = pass ? 4 : 2;
-    for (int q = lane; q < 240; q += 32) {
-      int g = q >> sh, j = q & (m - 1);
-      float2 *p = f + g * 4 * m + j;
-      float2 a = cmul(p[m], tw[j * tws]);
-      float2 b = cmul(p[2 * m], tw[2 * j * tws]);
-      float2 c = cmul(p[3 * m], tw[3 * j * tws]);
-      float2 f0 = p[0];
-      float2 d0b = csub(f0, b);
-      f0 = cadd(f0, b);
-      float2 sac = cadd(a, c);
-      float2 dac = csub(a, c);
-      p[2 * m] = csub(f0, sac);
-      p[0] = cadd(f0, sac);
-      p[m] = make_float2(d0b.x + dac.y, d0b.y - dac.x);
-      p[3 * m] = make_float2(d0b.x - dac.y, d0b.y + dac.x);
+  {  // ---------------- pass A ----------------
+    const float2 t1a = T.tw[60], t1b = T.tw[120], t1c = T.tw[180];    // j = 1: tw[60 j], tw[120 j], tw[180 j]
+    const float2 t2a = T.tw[120], t2b = T.tw[240], t2c = T.tw[360];   // j = 2
+    const float2 t3a = T.tw[180], t3b = T.tw[360], t3c = T.tw[540];   // j = 3
+    const float2 t0 = T.tw[0];
+    for (int b = lane; b < 60; b += 32) {
+      const int n0 = b / 12, n1 = (b >> 2) % 3, n2 = b & 3;
+      const int ibase = n0 + 5 * n1 + 15 * n2;
+      float2 v[16];
+#pragma unroll
+      for (int n3 = 0; n3 < 4; n3++)
+#pragma unroll
+        for (int n4 = 0; n4 < 4; n4++) v[4 * n3 + n4] = load(ibase + 60 * n3 + 240 * n4);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {  // radix-4, m = 1 (kiss_fft.cpp:112-131)
+        float2 a0 = v[4 * q], a1 = v[4 * q + 1], a2 = v[4 * q + 2], a3 = v[4 * q + 3];
+        float2 d02 = csub(a0, a2);
+        a0 = cadd(a0, a2);
+        float2 s13 = cadd(a1, a3);
+        a2 = csub(a0, s13);
+        a0 = cadd(a0, s13);
+        float2 d13 = csub(a1, a3);
+        v[4 * q] = a0;
+        v[4 * q + 2] = a2;
+        v[4 * q + 1] = make_float2(d02.x + d13.y, d02.y - d13.x);
+        v[4 * q + 3] = make_float2(d02.x - d13.y, d02.y + d13.x);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {  // radix-4, m = 4, twiddle stride 60 (kiss_fft.cpp:132-166)
+        const float2 wa = j == 0 ? t0 : j == 1 ? t1a : j == 2 ? t2a : t3a;
+        const float2 wb = j == 0 ? t0 : j == 1 ? t1b : j == 2 ? t2b : t3b;
+        const float2 wc = j == 0 ? t0 : j == 1 ? t1c : j == 2 ? t2c : t3c;
+        float2 a = cmul(v[j + 4], wa), bb = cmul(v[j + 8], wb), c = cmul(v[j + 12], wc);
+        float2 f0 = v[j];
+        float2 d0b = csub(f0, bb);
+        f0 = cadd(f0, bb);
+        float2 sac = cadd(a, c), dac = csub(a, c);
+        v[j + 8] = csub(f0, sac);
+        v[j] = cadd(f0, sac);
+        v[j + 4] = make_float2(d0b.x + dac.y, d0b.y - dac.x);
+        v[j + 12] = make_float2(d0b.x - dac.y, d0b.y + dac.x);
+      }
+      float4 *dst = reinterpret_cast<float4 *>(f + 18 * b);
+#pragma unroll
+      for (int k = 0; k < 8; k++) dst[k] = make_float4(v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
     }
-    __syncwarp();
   }
-  // radix-3, m = 64, 5 groups, twiddle stride 5 (kiss_fft.cpp:173-228); epi3 = tw[320]
-  {
-    const float w3i = tw[320].y;
-    for (int q = lane; q < 320; q += 32) {
-      int g = q >> 6, j = q & 63;
-      float2 *p = f + g * 192 + j;
-      float2 a = cmul(p[64], tw[j * 5]);
-      float2 b = cmul(p[128], tw[j * 10]);
-      float2 s = cadd(a, b);
-      float2 d = csub(a, b);
-      float2 f0 = p[0];
-      float2 f1 = make_float2(f0.x - s.x * .5f, f0.y - s.y * .5f);
-      d.x *= w3i;
-      d.y *= w3i;
-      p[0] = cadd(f0, s);
-      p[128] = make_float2(f1.x + d.y, f1.y - d.x);
-      p[64] = make_float2(f1.x - d.y, f1.y + d.x);
+  __syncwarp();
+  {  // ---------------- pass B ----------------
+    const float w3i = T.tw[320].y;  // epi3, kiss_fft.cpp:194
+    for (int g = lane; g < 80; g += 32) {
+      const int n0 = g >> 4, jj = g & 15;
+      const int e0 = 192 * n0 + jj;
+      float2 v[3][4];
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[r][q] = f[fpos(e0 + 64 * r + 16 * q)];
+      const float2 wa = T.tw[15 * jj], wb = T.tw[30 * jj], wc = T.tw[45 * jj];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {  // radix-4, m = 16, twiddle stride 15
+        float2 a = cmul(v[r][1], wa), bb = cmul(v[r][2], wb), c = cmul(v[r][3], wc);
+        float2 f0 = v[r][0];
+        float2 d0b = csub(f0, bb);
+        f0 = cadd(f0, bb);
+        float2 sac = cadd(a, c), dac = csub(a, c);
+        v[r][2] = csub(f0, sac);
+        v[r][0] = cadd(f0, sac);
+        v[r][1] = make_float2(d0b.x + dac.y, d0b.y - dac.x);
+        v[r][3] = make_float2(d0b.x - dac.y, d0b.y + dac.x);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {  // radix-3, m = 64, twiddle stride 5 (kiss_fft.cpp:173-228)
+        const int j64 = jj + 16 * q;
+        float2 a = cmul(v[1][q], T.tw[5 * j64]);
+        float2 bb = cmul(v[2][q], T.tw[10 * j64]);
+        float2 s = cadd(a, bb), d = csub(a, bb);
+        float2 f0 = v[0][q];
+        float2 f1 = make_float2(f0.x - s.x * .5f, f0.y - s.y * .5f);
+        d.x *= w3i;
+        d.y *= w3i;
+        v[0][q] = cadd(f0, s);
+        v[2][q] = make_float2(f1.x + d.y, f1.y - d.x);
+        v[1][q] = make_float2(f1.x - d.y, f1.y + d.x);
+      }
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) f[fpos(e0 + 64 * r + 16 * q)] = v[r][q];
     }
   }
   __syncwarp();
-  // radix-5, m = 192, twiddle stride 1 (kiss_fft.cpp:232-305); ya = tw[192], yb = tw[384]
-  {
-    const float2 ya = tw[192], yb = tw[384];
+  {  // ---------------- pass C: radix-5, m = 192 (kiss_fft.cpp:232-305); ya = tw[192], yb = tw[384] ----------------
+    const float2 ya = T.tw[192], yb = T.tw[384];
     for (int u = lane; u < 192; u += 32) {
-      float2 z0 = f[u];
-      float2 z1 = cmul(f[u + 192], tw[u]);
-      float2 z2 = cmul(f[u + 384], tw[2 * u]);
-      float2 z3 = cmul(f[u + 576], tw[3 * u]);
-      float2 z4 = cmul(f[u + 768], tw[4 * u]);
+      float2 z0 = f[fpos(u)];
+      float2 z1 = cmul(f[fpos(u + 192)], T.tw5[0][u]);
+      float2 z2 = cmul(f[fpos(u + 384)], T.tw5[1][u]);
+      float2 z3 = cmul(f[fpos(u + 576)], T.tw5[2][u]);
+      float2 z4 = cmul(f[fpos(u + 768)], T.tw5[3][u]);
       float2 s14 = cadd(z1, z4), d14 = csub(z1, z4);
       float2 s23 = cadd(z2, z3), d23 = csub(z2, z3);
-      f[u] = make_float2(z0.x + (s14.x + s23.x), z0.y + (s14.y + s23.y));
+      f[fpos(u)] = make_float2(z0.x + (s14.x + s23.x), z0.y + (s14.y + s23.y));
       float2 p = make_float2(z0.x + (s14.x * ya.x + s23.x * yb.x), z0.y + (s14.y * ya.x + s23.y * yb.x));
       float2 q = make_float2(d14.y * ya.y + d23.y * yb.y, -(d14.x * ya.y + d23.x * yb.y));
-      f[u + 192] = csub(p, q);
-      f[u + 768] = cadd(p, q);
+      f[fpos(u + 192)] = csub(p, q);
+      if (kAllOutputs) f[fpos(u + 768)] = cadd(p, q);
       p = make_float2(z0.x + (s14.x * yb.x + s23.x * ya.x), z0.y + (s14.y * yb.x + s23.y * ya.x));
       q = make_float2(d23.y * ya.y - d14.y * yb.y, d14.x * yb.y - d23.x * ya.y);
-      f[u + 384] = cadd(p, q);
-      f[u + 576] = csub(p, q);
+      if (kAllOutputs || u < 16) f[fpos(u + 384)] = cadd(p, q);
+      if (kAllOutputs) f[fpos(u + 576)] = csub(p, q);
     }
   }
   __syncwarp();
-}
-
-// window a real 960-sample block (denoise.cpp:282-289) and place it, scaled by 1/960, in FFT order
-__device__ __forceinline__ void load_real_windowed(float2 *f, const float *src, const float *hw, const short *slot,
-                                                   int lane) {
-  const float scale = 1.f / kWin;
-#pragma unroll 6
-  for (int i = lane; i < kWin; i += 32) {
-    float w = hw[i < kFrame ? i : kWin - 1 - i];
-    float v = src[i] * w;
-    f[slot[i]] = make_float2(scale * v, 0.f);
-  }
 }
 
 // ERB band pooling (denoise.cpp:89-123 / 125-160): v[bin] is |X|^2 or Re(X conj P) for bins 0..399.
@@ -196,7 +236,7 @@ struct PitchSmem {
 };
 struct WarpSmem {
   union {              // the pitch stage runs strictly between the two transforms of a hop
-    float2 fft[kWin];  // FFT work line
+    float2 fft[kFftLine];  // FFT work line (padded, see fpos)
     PitchSmem p;
   };
   float xc[400];       // xcorr (147 / 294) -- doubles as the per-bin scratch of band pooling
@@ -204,8 +244,7 @@ struct WarpSmem {
 };
 
 struct BlockSmem {
-  float2 tw[kWin];
-  short slot[kWin];    // digit-reversed position of every input sample
+  FftTw ft;
   float hw[kFrame];
   float frac[kBins];
   float omf[kBins];
@@ -221,7 +260,8 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
   WarpSmem *Wall = reinterpret_cast<WarpSmem *>(smem_raw + ((sizeof(BlockSmem) + 15) / 16) * 16);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const Tables *T = A.tab;
-  for (int i = threadIdx.x; i < kWin; i += blockDim.x) { B.tw[i] = T->tw[i]; B.slot[i] = (short)fft_slot(i); }
+  for (int i = threadIdx.x; i < kWin; i += blockDim.x) B.ft.tw[i] = T->tw[i];
+  for (int i = threadIdx.x; i < 4 * 192; i += blockDim.x) B.ft.tw5[i / 192][i % 192] = T->tw[(i / 192 + 1) * (i % 192)];
   for (int i = threadIdx.x; i < kFrame; i += blockDim.x) B.hw[i] = T->half_window[i];
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) { B.frac[i] = T->frac[i]; B.omf[i] = T->omf[i]; }
   if (threadIdx.x < kBands + 2) B.border[threadIdx.x] = T->border[threadIdx.x];
@@ -245,12 +285,20 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
     // kept in a per-stream ring of spectra / band energies, and read back as X and Ex when it comes due.
     const long c = A.hop0 + t;
     const int slot_new = (int)(c % A.ring), slot_x = (int)(((c - 5) % A.ring + A.ring) % A.ring);
-    load_real_windowed(W.fft, line + kOffLook, B.hw, B.slot, lane);
-    fft960_warp(W.fft, B.tw, lane);
+    {
+      const float *src = line + kOffLook;
+      const float *hw = B.hw;
+      // window (denoise.cpp:282-289), real -> complex, 1/960 (kiss_fft.cpp:582-583)
+      fft960_warp<false>(W.fft, B.ft, lane, [&](int i) {
+        float w = hw[i < kFrame ? i : kWin - 1 - i];
+        float v = src[i] * w;
+        return make_float2((1.f / kWin) * v, 0.f);
+      });
+    }
     {
       float2 *Zg = A.zring + ((size_t)slot_new * A.n_streams + s) * kBins;
       for (int k = lane; k < kBins; k += 32) {
-        float2 x = W.fft[k];
+        float2 x = W.fft[fpos(k)];
         Zg[k] = x;
         float e = x.x * x.x;
         e += x.y * x.y;
@@ -541,19 +589,20 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
     // ---- comb-filtered block, its spectrum P and the band statistics (denoise.cpp:416-427) ----
     __syncwarp();  // the pitch scratch is dead from here on; its storage becomes the FFT line again
     {
-      const float scale = 1.f / kWin;
-      for (int i = lane; i < kWin; i += 32) {
+      const float *hw = B.hw;
+      const float *cw = B.comb_w;
+      const float *ctr = line + kOffAnalysis;
+      fft960_warp<false>(W.fft, B.ft, lane, [&](int i) {
         float p = 0.f;
 #pragma unroll
-        for (int k = -3; k <= 3; k++) p = p + line[kOffAnalysis - T * k + i] * B.comb_w[k + 3];
-        float w = B.hw[i < kFrame ? i : kWin - 1 - i];
+        for (int k = -3; k <= 3; k++) p = p + ctr[i - T * k] * cw[k + 3];
+        float w = hw[i < kFrame ? i : kWin - 1 - i];
         float v = p * w;
-        W.fft[B.slot[i]] = make_float2(scale * v, 0.f);
-      }
-      fft960_warp(W.fft, B.tw, lane);
+        return make_float2((1.f / kWin) * v, 0.f);
+      });
       float2 *Pg = A.P + fs * kBins;
       for (int k = lane; k < kBins; k += 32) {
-        float2 p = W.fft[k];
+        float2 p = W.fft[fpos(k)];
         Pg[k] = p;
         float e = p.x * p.x;
         e += p.y * p.y;
@@ -561,7 +610,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
       }
       band_pool_warp(W.xc, W.Ep, B.frac, B.omf, B.border, lane);
       for (int k = lane; k < kBins; k += 32) {
-        float2 p = W.fft[k], x = Xg[k];
+        float2 p = W.fft[fpos(k)], x = Xg[k];
         float e = x.x * p.x;
         e += x.y * p.y;
         W.xc[k] = e;
@@ -608,12 +657,11 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
 // synthesis: per-bin gains from band values, optional comb mix, inverse transform, overlap-add
 // ------------------------------------------------------------------------------------------
 struct SynWarpSmem {
-  float2 fft[kWin];
+  float2 fft[kFftLine];
   float g[kBands], r[kBands], ir[kBands], gw[kBands];
 };
 struct SynBlockSmem {
-  float2 tw[kWin];
-  short slot[kWin];
+  FftTw ft;
   float hw[kFrame];
   float frac[kBins];
   float omf[kBins];
@@ -627,7 +675,8 @@ __global__ void __launch_bounds__(kSynWarps * 32) synthesis_kernel(SynthesisArgs
   SynWarpSmem *Wall = reinterpret_cast<SynWarpSmem *>(smem_raw + ((sizeof(SynBlockSmem) + 15) / 16) * 16);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const Tables *T = A.tab;
-  for (int i = threadIdx.x; i < kWin; i += blockDim.x) { B.tw[i] = T->tw[i]; B.slot[i] = (short)fft_slot(i); }
+  for (int i = threadIdx.x; i < kWin; i += blockDim.x) B.ft.tw[i] = T->tw[i];
+  for (int i = threadIdx.x; i < 4 * 192; i += blockDim.x) B.ft.tw5[i / 192][i % 192] = T->tw[(i / 192 + 1) * (i % 192)];
   for (int i = threadIdx.x; i < kFrame; i += blockDim.x) B.hw[i] = T->half_window[i];
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
     B.frac[i] = T->frac[i];
@@ -675,43 +724,47 @@ __global__ void __launch_bounds__(kSynWarps * 32) synthesis_kernel(SynthesisArgs
     const float2 *Xg = A.zring + ((size_t)slot_x * A.n_streams + s) * kBins, *Pg = A.P + fs * kBins;
     const float scale = 1.f / kWin;
     // bins 0..399 and their mirror images; everything from 400 to 560 is zero
-    for (int i = lane; i < kWin; i += 32) {
-      int k = i <= kFrame ? i : kWin - i;
-      float2 v = make_float2(0.f, 0.f);
-      if (k < kBins) {
-        float2 x = Xg[k];
-        int b = B.band_of[k];
-        float fr = B.frac[k], om = B.omf[k];
-        if (!silence) {  // pitch_filter, denoise.cpp:436-485
-          float rf = om * W.ir[b] + fr * W.ir[b + 1];
-          x.x = rf * x.x;
-          x.y = rf * x.y;
-          rf = om * W.r[b] + fr * W.r[b + 1];
-          float2 p = Pg[k];
-          x.x += rf * p.x;
-          x.y += rf * p.y;
+    {
+      const float *frac = B.frac, *omf = B.omf;
+      const short *band_of = B.band_of;
+      const float *gg = W.g, *rr = W.r, *ir = W.ir;
+      fft960_warp<true>(W.fft, B.ft, lane, [&](int i) {
+        int k = i <= kFrame ? i : kWin - i;
+        float2 v = make_float2(0.f, 0.f);
+        if (k < kBins) {
+          float2 x = Xg[k];
+          int b = band_of[k];
+          float fr = frac[k], om = omf[k];
+          if (!silence) {  // pitch_filter, denoise.cpp:436-485
+            float rf = om * ir[b] + fr * ir[b + 1];
+            x.x = rf * x.x;
+            x.y = rf * x.y;
+            rf = om * rr[b] + fr * rr[b + 1];
+            float2 p = Pg[k];
+            x.x += rf * p.x;
+            x.y += rf * p.y;
+          }
+          float gf = om * gg[b] + fr * gg[b + 1];  // interp_band_gain + gain apply, :539-544
+          x.x *= gf;
+          x.y *= gf;
+          v = (i <= kFrame) ? x : make_float2(x.x, -x.y);  // Hermitian extension, :314-317
         }
-        float gf = om * W.g[b] + fr * W.g[b + 1];  // interp_band_gain + gain apply, :539-544
-        x.x *= gf;
-        x.y *= gf;
-        v = (i <= kFrame) ? x : make_float2(x.x, -x.y);  // Hermitian extension, :314-317
-      }
-      W.fft[B.slot[i]] = make_float2(scale * v.x, scale * v.y);
+        return make_float2((1.f / kWin) * v.x, (1.f / kWin) * v.y);
+      });
     }
-    fft960_warp(W.fft, B.tw, lane);
     // time samples are read back reversed and rescaled (denoise.cpp:318-323), windowed, overlap-added
     float *outp = A.out ? A.out + (size_t)s * A.out_stride + (size_t)t * kFrame : nullptr;
     short *outs = A.out16 ? A.out16 + (size_t)s * A.out_stride + (size_t)t * kFrame : nullptr;
 #pragma unroll
     for (int i = 0; i < 15; i++) {
       int n = lane + 32 * i;
-      float a = (float)kWin * W.fft[(kWin - n) % kWin].x;
+      float a = (float)kWin * W.fft[fpos((kWin - n) % kWin)].x;
       a = a * B.hw[n];
       float o = a + mem[i];
       if (outp) outp[n] = o;
       if (outs) outs[n] = (short)(int)(o * 32768.f);  // main.cpp:36: truncation toward zero
       int n2 = n + kFrame;
-      float c = (float)kWin * W.fft[kWin - n2].x;
+      float c = (float)kWin * W.fft[fpos(kWin - n2)].x;
       mem[i] = c * B.hw[kWin - 1 - n2];
     }
     __syncwarp();
