@@ -16,8 +16,10 @@
 // state in fp32 and already split for the next contraction.
 //
 // The GRU tile holds, for 64 hidden units, four accumulators per unit (z, r, W_n x, U_n h: nnet.cpp:136-173
-// needs the last two apart), 256 TMEM columns; weight rows are packed gate-interleaved per tile so that
-// one TMA box brings the z|r|n rows of the tile.
+// needs the last two apart), 256 TMEM columns [nx | z | r | nh]; weight rows are packed gate-interleaved per tile
+// (input part [n|z|r], recurrent part [z|r|n]) so that one TMA box brings a tile's rows and one N = 192 MMA
+// covers it -- the kernel is bound by shared-memory operand reads (A is re-read by every MMA), so fewer, wider
+// MMAs matter more than anything else here.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -261,14 +263,15 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      const uint32_t id_main = idesc_f16(GRU ? 2 * HT : BN, args.fmt), id_n = idesc_f16(HT, args.fmt);
+      const uint32_t id_main = idesc_f16(GRU ? 3 * HT : BN, args.fmt), id_zr = idesc_f16(2 * HT, args.fmt),
+                     id_n = idesc_f16(HT, args.fmt);
       int it = 0, j = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, j++) {
         const int buf = j & 1;
         const uint32_t acc = tmem_base + buf * kAccCols;
         mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);  // epilogue has drained this buffer (2 tiles ago)
         tc_fence_after();
-        bool started_main = false, started_nx = false, started_nh = false;
+        bool started_main = false, started_nh = false;
         for (int s = 0; s < args.n_seg; s++) {
           const TcSeg sg = args.seg[s];
           for (int kb = 0; kb < sg.k_blocks; kb++, it++) {
@@ -283,17 +286,22 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
               for (int p = 0; p < PR::n; p++) {
                 const uint64_t ad = smem_desc_sw64(sa + PR::a(p) * SL::kABytes) + (uint64_t)(ks * 2);
                 const uint32_t bt = sb + PR::b(p) * SL::kBBytes;
-                umma_f16(acc, ad, smem_desc_sw64(bt) + (uint64_t)(ks * 2), id_main, started_main ? 1u : 0u);
-                started_main = true;
-                if (GRU) {
-                  const uint64_t bd = smem_desc_sw64(bt + 2 * HT * BK * 2) + (uint64_t)(ks * 2);
-                  if (sg.recurrent) {
-                    umma_f16(acc + 3 * HT, ad, bd, id_n, started_nh ? 1u : 0u);
-                    started_nh = true;
-                  } else {
-                    umma_f16(acc + 2 * HT, ad, bd, id_n, started_nx ? 1u : 0u);
-                    started_nx = true;
-                  }
+                const uint64_t bd = smem_desc_sw64(bt) + (uint64_t)(ks * 2);
+                if (!GRU) {
+                  umma_f16(acc, ad, bd, id_main, started_main ? 1u : 0u);
+                  started_main = true;
+                } else if (!sg.recurrent) {
+                  // input part: weight rows [n | z | r] -> columns [nx | z | r] = acc + 0 .. 191, one N = 192 MMA
+                  umma_f16(acc, ad, bd, id_main, started_main ? 1u : 0u);
+                  started_main = true;
+                } else if (started_nh) {
+                  // recurrent part: weight rows [z | r | n] -> columns [z | r | nh] = acc + 64 .. 255
+                  umma_f16(acc + HT, ad, bd, id_main, 1u);
+                } else {
+                  // first recurrent MMA: z, r already hold the input part (accumulate), nh starts from zero
+                  umma_f16(acc + HT, ad, bd, id_zr, started_main ? 1u : 0u);
+                  umma_f16(acc + 3 * HT, ad, smem_desc_sw64(bt + 2 * HT * BK * 2) + (uint64_t)(ks * 2), id_n, 0u);
+                  started_nh = true;
                 }
               }
             }
@@ -321,9 +329,9 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
         const float *b = args.bias;
         for (int c = 0; c < HT; c += 16) {
           float zs[16], rs[16], nx[16], nh[16];
-          tmem_ld16(tlane + c, zs);
-          tmem_ld16(tlane + HT + c, rs);
-          tmem_ld16(tlane + 2 * HT + c, nx);
+          tmem_ld16(tlane + HT + c, zs);      // accumulator columns: [nx | z | r | nh]
+          tmem_ld16(tlane + 2 * HT + c, rs);
+          tmem_ld16(tlane + c, nx);
           tmem_ld16(tlane + 3 * HT + c, nh);
           const int j0 = n_tile * HT + c;
           if (row_ok) {
@@ -519,13 +527,17 @@ extern int tc_fail(int code, const char *msg);  // sets pnb_last_error (pnb_engi
   } while (0)
 
 // GRU weights: reference layout W[j*3H + g*H + i] -> K-major rows ordered [tile][gate][64 units], scaled, split
-static void pack_gru(const float *W, int K, int H, float scale, std::vector<__half> &out) {
+// `order` lists the reference gate index (0 z, 1 r, 2 n) of each 64-row group of a tile: input weights are packed
+// [n | z | r], recurrent weights [z | r | n], so that either part is ONE N = 192 MMA onto the accumulator columns
+// [nx | z | r | nh] (at column 0 and at column 64 respectively).
+static void pack_gru(const float *W, int K, int H, float scale, const int order[3], std::vector<__half> &out) {
   const int tiles = H / HT, rows = tiles * GRU_BN;
   out.assign((size_t)2 * rows * K, __float2half(0.f));
   for (int tl = 0; tl < tiles; tl++)
-    for (int g = 0; g < 3; g++)
+    for (int gq = 0; gq < 3; gq++)
       for (int ii = 0; ii < HT; ii++) {
-        const int row = tl * GRU_BN + g * HT + ii, i = tl * HT + ii;
+        const int g = order[gq];
+        const int row = tl * GRU_BN + gq * HT + ii, i = tl * HT + ii;
         for (int j = 0; j < K; j++) {
           float w = W[(size_t)j * 3 * H + g * H + i] * scale;
           __half hi = __float2half_rn(w);
@@ -607,9 +619,10 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
     float sc = pow2_scale_for(g5[i]->input_weights, (size_t)K * 3 * H, g5[i]->recurrent_weights, (size_t)H * 3 * H, &ex);
     t->scale_gru[i] = ldexpf(1.f, -(10 + ex));
     std::vector<__half> p;
-    pack_gru(g5[i]->input_weights, K, H, sc, p);
+    const int order_w[3] = {2, 0, 1}, order_u[3] = {0, 1, 2};
+    pack_gru(g5[i]->input_weights, K, H, sc, order_w, p);
     TCK(dev_upload(&t->w_gru[i], p));
-    pack_gru(g5[i]->recurrent_weights, H, H, sc, p);
+    pack_gru(g5[i]->recurrent_weights, H, H, sc, order_u, p);
     TCK(dev_upload(&t->u_gru[i], p));
   }
   {
