@@ -42,6 +42,7 @@ constexpr int BK = 32;    // k per pipeline stage: 64-byte rows, SWIZZLE_64B
 constexpr int HT = 64;    // hidden units per GRU tile
 constexpr int GRU_BN = 3 * HT;  // weight rows per GRU tile (z|r|n)
 constexpr int DENSE_BN = 128;   // output columns per dense tile
+constexpr int kConvTerms = 2;         // bf16 terms per operand on the conv layers (2: 16-bit operands, 3 products)
 constexpr float kActScale = 1024.f;  // fp16 activations are stored x 2^10 (keeps the low term normal)
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -180,6 +181,11 @@ template <> struct Products<3, 3> {
   static constexpr int n = 6;
   __device__ static constexpr int a(int i) { return i == 0 ? 0 : i == 1 ? 0 : i == 2 ? 1 : i == 3 ? 0 : i == 4 ? 1 : 2; }
   __device__ static constexpr int b(int i) { return i == 0 ? 0 : i == 1 ? 1 : i == 2 ? 0 : i == 3 ? 2 : i == 4 ? 1 : 0; }
+};
+template <> struct Products<3, 2> {  // a = a0 + a1 + a2 (24 bits), b = b0 + b1 (16 bits): all products >= 2^-16
+  static constexpr int n = 5;
+  __device__ static constexpr int a(int i) { return i == 0 ? 0 : i == 1 ? 0 : i == 2 ? 1 : i == 3 ? 1 : 2; }
+  __device__ static constexpr int b(int i) { return i == 0 ? 0 : i == 1 ? 1 : i == 2 ? 0 : i == 3 ? 1 : 0; }
 };
 
 __device__ __forceinline__ void split_h2(float v, __half &hi, __half &lo) {
@@ -408,10 +414,12 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
               const size_t plane = (size_t)args.M * N;
               uint4 *p0 = reinterpret_cast<uint4 *>(args.out_b + (size_t)row * N + j0);
               uint4 *p1 = reinterpret_cast<uint4 *>(args.out_b + plane + (size_t)row * N + j0);
-              uint4 *p2 = reinterpret_cast<uint4 *>(args.out_b + 2 * plane + (size_t)row * N + j0);
               p0[0] = reinterpret_cast<uint4 *>(t0)[0]; p0[1] = reinterpret_cast<uint4 *>(t0)[1];
               p1[0] = reinterpret_cast<uint4 *>(t1)[0]; p1[1] = reinterpret_cast<uint4 *>(t1)[1];
-              p2[0] = reinterpret_cast<uint4 *>(t2)[0]; p2[1] = reinterpret_cast<uint4 *>(t2)[1];
+              if (kConvTerms == 3) {
+                uint4 *p2 = reinterpret_cast<uint4 *>(args.out_b + 2 * plane + (size_t)row * N + j0);
+                p2[0] = reinterpret_cast<uint4 *>(t2)[0]; p2[1] = reinterpret_cast<uint4 *>(t2)[1];
+              }
             }
           }
         }
@@ -429,7 +437,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
   }
 }
 
-constexpr int GRU_STAGES = 5, DENSE_STAGES = 4, SMALL_BN = 48, SMALL_STAGES = 8;
+constexpr int GRU_STAGES = 5, DENSE_STAGES = 6, SMALL_BN = 48, SMALL_STAGES = 8;
 template <int NA, int NB, int BN, int STAGES>
 constexpr size_t tc_smem_bytes() {
   return (size_t)STAGES * StageLayout<NA, NB, BN>::kBytes + (2 * STAGES + 4) * 8 + 16 + 208 * 4 + 1024;
@@ -461,7 +469,8 @@ __global__ void __launch_bounds__(128) fc_split_kernel(const float *__restrict__
     __nv_bfloat16 t0, t1, t2;
     split_b3(v, t0, t1, t2);
     size_t o = (size_t)(r0 + rr) * 128 + n;
-    out[o] = t0; out[plane + o] = t1; out[2 * plane + o] = t2;
+    out[o] = t0; out[plane + o] = t1;
+    if (kConvTerms == 3) out[2 * plane + o] = t2;
   }
 }
 
@@ -549,7 +558,7 @@ static void pack_gru(const float *W, int K, int H, float scale, const int order[
 }
 // dense/conv weights: W[k*N + n] -> [n][k], three bf16 terms
 static void pack_dense_b3(const float *W, int K, int N, std::vector<__nv_bfloat16> &out) {
-  out.assign((size_t)3 * N * K, __float2bfloat16(0.f));
+  out.assign((size_t)kConvTerms * N * K, __float2bfloat16(0.f));
   for (int n = 0; n < N; n++)
     for (int k = 0; k < K; k++) {
       float w = W[(size_t)k * N + n];
@@ -560,7 +569,7 @@ static void pack_dense_b3(const float *W, int K, int N, std::vector<__nv_bfloat1
       __nv_bfloat16 t2 = __float2bfloat16_rn(r);
       out[(size_t)n * K + k] = t0;
       out[((size_t)N + n) * K + k] = t1;
-      out[((size_t)2 * N + n) * K + k] = t2;
+      if (kConvTerms == 3) out[((size_t)2 * N + n) * K + k] = t2;
     }
 }
 
@@ -600,8 +609,8 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
   pnb_tc_state *t = new pnb_tc_state();
   e->tc = t;
   const size_t S = e->S;
-  TCK(dev_zeros(&t->ring_fc, 5 * 3 * S * 128));
-  TCK(dev_zeros(&t->ring_c1, 3 * 3 * S * 512));
+  TCK(dev_zeros(&t->ring_fc, 5 * kConvTerms * S * 128));
+  TCK(dev_zeros(&t->ring_c1, 3 * kConvTerms * S * 512));
   TCK(dev_zeros(&t->c2_h, 2 * S * 512));
   for (int i = 0; i < 5; i++)
     for (int p = 0; p < 2; p++) TCK(dev_zeros(&t->h_h[i][p], 2 * S * e->gru[i].H));
@@ -640,13 +649,13 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
   int bad = 0;
   bad |= make_map(&t->m_wgb, t->w_gb, false, 2 * SMALL_BN, 2560, SMALL_BN);
   bad |= make_map(&t->m_wrb, t->w_rb, false, 2 * SMALL_BN, 128, SMALL_BN);
-  for (int q = 0; q < 5; q++) bad |= make_map(&t->m_ring_fc[q], t->ring_fc + (size_t)q * 3 * S * 128, true, 3 * S, 128, TM);
-  for (int q = 0; q < 3; q++) bad |= make_map(&t->m_ring_c1[q], t->ring_c1 + (size_t)q * 3 * S * 512, true, 3 * S, 512, TM);
+  for (int q = 0; q < 5; q++) bad |= make_map(&t->m_ring_fc[q], t->ring_fc + (size_t)q * kConvTerms * S * 128, true, kConvTerms * S, 128, TM);
+  for (int q = 0; q < 3; q++) bad |= make_map(&t->m_ring_c1[q], t->ring_c1 + (size_t)q * kConvTerms * S * 512, true, kConvTerms * S, 512, TM);
   bad |= make_map(&t->m_c2, t->c2_h, false, 2 * S, 512, TM);
   for (int i = 0; i < 5; i++)
     for (int p = 0; p < 2; p++) bad |= make_map(&t->m_h[i][p], t->h_h[i][p], false, 2 * S, e->gru[i].H, TM);
-  bad |= make_map(&t->m_wconv1, t->w_conv1, true, 3 * 512, 640, DENSE_BN);
-  bad |= make_map(&t->m_wconv2, t->w_conv2, true, 3 * 512, 1536, DENSE_BN);
+  bad |= make_map(&t->m_wconv1, t->w_conv1, true, kConvTerms * 512, 640, DENSE_BN);
+  bad |= make_map(&t->m_wconv2, t->w_conv2, true, kConvTerms * 512, 1536, DENSE_BN);
   for (int i = 0; i < 5; i++) {
     const int rows = (e->gru[i].H / HT) * GRU_BN;
     bad |= make_map(&t->m_w[i], t->w_gru[i], false, 2 * rows, e->gru[i].M, GRU_BN);
@@ -655,8 +664,8 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
   if (bad) return tc_fail(PNB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   TCK(cudaFuncSetAttribute(tc_gemm_kernel<2, 2, GRU_BN, GRU_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)tc_smem_bytes<2, 2, GRU_BN, GRU_STAGES>()));
-  TCK(cudaFuncSetAttribute(tc_gemm_kernel<3, 3, DENSE_BN, DENSE_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)tc_smem_bytes<3, 3, DENSE_BN, DENSE_STAGES>()));
+  TCK(cudaFuncSetAttribute(tc_gemm_kernel<kConvTerms, kConvTerms, DENSE_BN, DENSE_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)tc_smem_bytes<kConvTerms, kConvTerms, DENSE_BN, DENSE_STAGES>()));
   TCK(cudaFuncSetAttribute(tc_gemm_kernel<2, 2, SMALL_BN, SMALL_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)tc_smem_bytes<2, 2, SMALL_BN, SMALL_STAGES>()));
   return PNB_OK;
@@ -680,8 +689,8 @@ int tc_reset(pnb_engine *e) {
   pnb_tc_state *t = e->tc;
   if (!t) return PNB_OK;
   const size_t S = e->S;
-  TCK(cudaMemset(t->ring_fc, 0, 5 * 3 * S * 128 * 2));
-  TCK(cudaMemset(t->ring_c1, 0, 3 * 3 * S * 512 * 2));
+  TCK(cudaMemset(t->ring_fc, 0, 5 * kConvTerms * S * 128 * 2));
+  TCK(cudaMemset(t->ring_c1, 0, 3 * kConvTerms * S * 512 * 2));
   TCK(cudaMemset(t->c2_h, 0, 2 * S * 512 * 2));
   for (int i = 0; i < 5; i++)
     for (int p = 0; p < 2; p++) TCK(cudaMemset(t->h_h[i][p], 0, 2 * S * e->gru[i].H * 2));
@@ -715,7 +724,7 @@ int tc_step(pnb_engine *e, int tstep, cudaStream_t st) {
   {
     ProfScope ps(e, PNB_K_TC_AUX, st);
     fc_split_kernel<<<(S + 3) / 4, 128, 0, st>>>(e->d_feat + (size_t)tstep * S * kFeat, e->fc.W, e->fc.b,
-                                                 t->ring_fc + (size_t)(c % 5) * 3 * S * 128, S);
+                                                 t->ring_fc + (size_t)(c % 5) * kConvTerms * S * 128, S);
     n++;
   }
   TcArgs a;
@@ -728,10 +737,10 @@ int tc_step(pnb_engine *e, int tstep, cudaStream_t st) {
   a.maps[5] = t->m_wconv1;
   a.n_seg = 5; a.M = S; a.a_term_rows = S; a.b_term_rows = 512; a.fmt = 1; a.out_scale = 1.f; a.tansig = tbl;
   a.bias = e->conv1.b; a.act = e->act_conv1; a.N = 512;
-  a.out_b = t->ring_c1 + (size_t)(c % 3) * 3 * S * 512;
+  a.out_b = t->ring_c1 + (size_t)(c % 3) * kConvTerms * S * 512;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    tc_launch<3, 3, DENSE_BN, DENSE_STAGES, false>(e, a, 512 / DENSE_BN, st);
+    tc_launch<kConvTerms, kConvTerms, DENSE_BN, DENSE_STAGES, false>(e, a, 512 / DENSE_BN, st);
     n++;
   }
   // conv2: three taps -> tanh -> fp32 (fc_gb input) and fp16 split (gru1 / gru_rb input)
@@ -745,7 +754,7 @@ int tc_step(pnb_engine *e, int tstep, cudaStream_t st) {
   a.bias = e->conv2.b; a.act = e->act_conv2; a.N = 512; a.out_f32 = e->c2; a.ldc = 512; a.out_h = t->c2_h;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    tc_launch<3, 3, DENSE_BN, DENSE_STAGES, false>(e, a, 512 / DENSE_BN, st);
+    tc_launch<kConvTerms, kConvTerms, DENSE_BN, DENSE_STAGES, false>(e, a, 512 / DENSE_BN, st);
     n++;
   }
   // GRUs (rnn.cpp:58-71): each consumes the freshly written state of the layer below
