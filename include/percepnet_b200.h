@@ -81,6 +81,14 @@ int pnb_process_host_f32(pnb_engine *e, const float *in, size_t in_stride, float
 int pnb_process_host_i16(pnb_engine *e, const short *in, size_t in_stride, short *out, size_t out_stride,
                          int n_frames, float *gr);
 
+/* Pipelined host entry for sustained throughput: enqueues host->device copy, processing and device->host copy
+ * on internal streams and returns; the copies of neighbouring calls overlap the kernels.  At most two calls are
+ * in flight (a third blocks until the oldest completed).  Buffers must stay valid -- and should be pinned --
+ * until pnb_wait() returns.  Calls are processed in submission order (the streams' state advances in order). */
+int pnb_submit_host_f32(pnb_engine *e, const float *in, size_t in_stride, float *out, size_t out_stride, int n_frames);
+int pnb_submit_host_i16(pnb_engine *e, const short *in, size_t in_stride, short *out, size_t out_stride, int n_frames);
+int pnb_wait(pnb_engine *e);
+
 /* Device buffers on the engine's device; asynchronous on cuda_stream (a cudaStream_t, NULL = default
  * stream).  d_gr (NULL ok) as above, in device memory. */
 int pnb_process_device_f32(pnb_engine *e, const float *d_in, size_t in_stride, float *d_out, size_t out_stride,

@@ -47,6 +47,9 @@ def load_library() -> C.CDLL:
     L.pnb_process_host_i16.argtypes = [vp, vp, sz, vp, sz, i, vp]
     L.pnb_process_device_f32.argtypes = [vp, vp, sz, vp, sz, i, vp, vp]
     L.pnb_process_device_i16.argtypes = [vp, vp, sz, vp, sz, i, vp, vp]
+    L.pnb_submit_host_f32.argtypes = [vp, vp, sz, vp, sz, i]
+    L.pnb_submit_host_i16.argtypes = [vp, vp, sz, vp, sz, i]
+    L.pnb_wait.argtypes = [vp]
     L.pnb_read_tap.argtypes = [vp, i, vp, sz]
     L.pnb_launch_count.argtypes = [vp]
     L.pnb_launch_count.restype = C.c_longlong
@@ -64,7 +67,8 @@ def load_library() -> C.CDLL:
 
 
 EXPORTS = ("pnb_create", "pnb_destroy", "pnb_reset", "pnb_process_host_f32", "pnb_process_host_i16",
-           "pnb_process_device_f32", "pnb_process_device_i16", "pnb_read_tap", "pnb_launch_count",
+           "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_wait",
+           "pnb_read_tap", "pnb_launch_count",
            "pnb_launches_per_call", "pnb_profile_enable", "pnb_profile_read", "pnb_kernel_class_name", "pnb_n_streams", "pnb_max_frames", "pnb_last_error", "pnb_version")
 
 
@@ -131,6 +135,18 @@ class Engine:
         f = self.L.pnb_process_device_i16 if int16 else self.L.pnb_process_device_f32
         self._ck(f(self.h, d_in, in_stride, d_out, out_stride, n_frames, d_gr or None, stream or None),
                  "pnb_process_device")
+
+    def submit(self, x: np.ndarray, out: np.ndarray):
+        """Pipelined host call (pnb_submit_host_*): returns at once; x/out ([S, F*480] float32 or int16, ideally
+        pinned) must stay alive until wait()."""
+        assert x.shape == out.shape and x.dtype == out.dtype and x.shape[0] == self.n_streams
+        F = x.shape[1] // FRAME
+        f = self.L.pnb_submit_host_f32 if x.dtype == np.float32 else self.L.pnb_submit_host_i16
+        self._ck(f(self.h, x.ctypes.data, x.strides[0] // x.itemsize, out.ctypes.data, out.strides[0] // out.itemsize, F),
+                 "pnb_submit_host")
+
+    def wait(self):
+        self._ck(self.L.pnb_wait(self.h), "pnb_wait")
 
     def read_tap(self, name: str, n_frames: int) -> np.ndarray:
         code, dt, width = TAPS[name]

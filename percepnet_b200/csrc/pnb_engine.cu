@@ -263,6 +263,15 @@ extern "C" void pnb_destroy(pnb_engine *e) {
   if (e->d_tab) cudaFree(e->d_tab);
   if (e->d_hin16) cudaFree(e->d_hin16);
   if (e->d_hout16) cudaFree(e->d_hout16);
+  for (int k = 0; k < 2; k++) {
+    if (e->pipe_in[k]) cudaFree(e->pipe_in[k]);
+    if (e->pipe_out[k]) cudaFree(e->pipe_out[k]);
+    if (e->ev_in[k]) cudaEventDestroy(e->ev_in[k]);
+    if (e->ev_cmp[k]) cudaEventDestroy(e->ev_cmp[k]);
+    if (e->ev_out[k]) cudaEventDestroy(e->ev_out[k]);
+  }
+  if (e->s_in) cudaStreamDestroy(e->s_in);
+  if (e->s_out) cudaStreamDestroy(e->s_out);
   for (auto &r : e->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -513,6 +522,74 @@ extern "C" int pnb_process_host_f32(pnb_engine *e, const float *in, size_t in_st
 extern "C" int pnb_process_host_i16(pnb_engine *e, const short *in, size_t in_stride, short *out, size_t out_stride,
                                     int n_frames, float *gr) {
   return process_host<short>(e, in, in_stride, out, out_stride, n_frames, gr, &e->d_hin16, &e->d_hout16);
+}
+
+// ------------------------------------------------------------------------------------------
+// pipelined host entry: H2D of call i+1 and D2H of call i-1 overlap the kernels of call i
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static int submit_host(pnb_engine *e, const T *in, size_t in_stride, T *out, size_t out_stride, int F) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  if (!in || !out) return fail(PNB_ERR_ARG, "input/output pointer is NULL");
+  if (F < 1 || F > e->Fmax) return fail(PNB_ERR_ARG, "n_frames %d outside [1, %d]", F, e->Fmax);
+  if (in_stride < (size_t)F * kFrame || out_stride < (size_t)F * kFrame)
+    return fail(PNB_ERR_ARG, "row stride smaller than n_frames*480");
+  CK(cudaSetDevice(e->device));
+  const size_t S = e->S, row = (size_t)e->Fmax * kFrame;
+  if (!e->s_in) {
+    CK(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      CK(cudaEventCreateWithFlags(&e->ev_in[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&e->ev_cmp[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&e->ev_out[k], cudaEventDisableTiming));
+    }
+  }
+  if (e->pipe_elem != sizeof(T)) {
+    CK(cudaDeviceSynchronize());
+    for (int k = 0; k < 2; k++) {
+      if (e->pipe_in[k]) cudaFree(e->pipe_in[k]);
+      if (e->pipe_out[k]) cudaFree(e->pipe_out[k]);
+      CK(cudaMalloc(&e->pipe_in[k], S * row * sizeof(T)));
+      CK(cudaMalloc(&e->pipe_out[k], S * row * sizeof(T)));
+    }
+    e->pipe_elem = sizeof(T);
+    e->submitted = 0;
+  }
+  const int k = (int)(e->submitted & 1);
+  if (e->submitted >= 2) CK(cudaEventSynchronize(e->ev_out[k]));  // the slot's previous round trip is complete
+  const size_t w = (size_t)F * kFrame * sizeof(T);
+  CK(cudaMemcpy2DAsync(e->pipe_in[k], row * sizeof(T), in, in_stride * sizeof(T), w, S, cudaMemcpyHostToDevice, e->s_in));
+  CK(cudaEventRecord(e->ev_in[k], e->s_in));
+  CK(cudaStreamWaitEvent(e->stream, e->ev_in[k], 0));
+  int rc;
+  if (sizeof(T) == 4)
+    rc = process_device(e, (const float *)e->pipe_in[k], nullptr, row, (float *)e->pipe_out[k], nullptr, row, F, nullptr, e->stream);
+  else
+    rc = process_device(e, nullptr, (const short *)e->pipe_in[k], row, nullptr, (short *)e->pipe_out[k], row, F, nullptr, e->stream);
+  if (rc) return rc;
+  CK(cudaEventRecord(e->ev_cmp[k], e->stream));
+  CK(cudaStreamWaitEvent(e->s_out, e->ev_cmp[k], 0));
+  CK(cudaMemcpy2DAsync(out, out_stride * sizeof(T), e->pipe_out[k], row * sizeof(T), w, S, cudaMemcpyDeviceToHost, e->s_out));
+  CK(cudaEventRecord(e->ev_out[k], e->s_out));
+  e->submitted++;
+  return PNB_OK;
+}
+extern "C" int pnb_submit_host_f32(pnb_engine *e, const float *in, size_t in_stride, float *out, size_t out_stride,
+                                   int n_frames) {
+  return submit_host<float>(e, in, in_stride, out, out_stride, n_frames);
+}
+extern "C" int pnb_submit_host_i16(pnb_engine *e, const short *in, size_t in_stride, short *out, size_t out_stride,
+                                   int n_frames) {
+  return submit_host<short>(e, in, in_stride, out, out_stride, n_frames);
+}
+extern "C" int pnb_wait(pnb_engine *e) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  CK(cudaSetDevice(e->device));
+  if (e->s_in) CK(cudaStreamSynchronize(e->s_in));
+  CK(cudaStreamSynchronize(e->stream));
+  if (e->s_out) CK(cudaStreamSynchronize(e->s_out));
+  return PNB_OK;
 }
 
 extern "C" int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes) {

@@ -51,6 +51,13 @@ struct pnb_engine {
   float *d_hin = nullptr, *d_hout = nullptr;
   short *d_hin16 = nullptr, *d_hout16 = nullptr;
 
+  // pipelined host entry (pnb_submit_host_*): two slots of device staging, three streams
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  void *pipe_in[2] = {nullptr, nullptr}, *pipe_out[2] = {nullptr, nullptr};
+  size_t pipe_elem = 0;  // element size the staging was allocated for
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  long long submitted = 0;
+
   pnb_tc_state *tc = nullptr;
   int last_frames = 0;
   long long launches = 0;

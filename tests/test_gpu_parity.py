@@ -208,6 +208,26 @@ def test_device_pointer_entry_and_stream(api, model0):
     assert np.array_equal(d_out.cpu().numpy(), ref)
 
 
+def test_pipelined_submit_matches_blocking(api, model0):
+    """pnb_submit_host_* / pnb_wait (copies overlapped with kernels) gives the blocking call's bits, in both
+    wire formats, across more calls than pipeline slots."""
+    from percepnet_b200.synth import to_int16
+    x = _inputs(1.0, 20, n_synth=4)[:6]
+    S = x.shape[0]
+    for cast in (lambda a: a, to_int16):
+        xi = cast(x)
+        eng = api.Engine(S, 4, model0)
+        want, _ = eng.process_stream_chunks(xi)
+        eng.reset()
+        outs = [np.empty((S, 4 * 480), xi.dtype) for _ in range(5)]
+        ins = [np.ascontiguousarray(xi[:, k * 1920:(k + 1) * 1920]) for k in range(5)]
+        for k in range(5):
+            eng.submit(ins[k], outs[k])
+        eng.wait()
+        eng.close()
+        assert np.array_equal(np.concatenate(outs, axis=1), want)
+
+
 def test_argument_errors(api, model0):
     eng = api.Engine(2, 4, model0)
     with pytest.raises(api.PnbError):
