@@ -70,24 +70,59 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: the two CTAs of a cluster act as one M = 256 tensor-core unit ----
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> the leader's copy
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into this CTA's shared memory whose bytes are accounted on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(x), "r"(y),
+      "l"(0x1000000000000000ull)  // EVICT_NORMAL
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {  // arrive on the leader CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
 }
+// D[256 x N] (+)= A[256 x 16] B[N x 16]^T : rows 0..127 from the leader's A tile / TMEM, 128..255 from the peer's;
+// each CTA's shared memory supplies N/2 rows of B
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// completion of all MMAs issued so far arrives on `bar` in BOTH CTAs
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
 }
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
@@ -110,7 +145,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, A/B format (0 fp16, 1 bf16), both K-major
 __host__ __device__ constexpr uint32_t idesc_f16(int n, int fmt) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);  // M = 256: the CTA pair
 }
 
 // ------------------------------------------------------------------------------------------ activations
@@ -166,8 +201,9 @@ struct TcArgs {
 template <int NA, int NB, int BN>
 struct StageLayout {
   static constexpr int kABytes = TM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / 2) * BK * 2;  // each CTA of the pair holds half of the weight rows
   static constexpr int kBytes = NA * kABytes + NB * kBBytes;
+  static constexpr int kPairBytes = kBytes;          // bytes one CTA brings per stage
 };
 
 // products of split terms that are kept: (a term, b term), largest first
@@ -208,6 +244,11 @@ __host__ __device__ constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 
 
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-7 = epilogue.  Two accumulator buffers in TMEM: the epilogue of tile i overlaps the MMAs of tile i+1.
+// CTAs run as pairs (cluster of 2, tcgen05 cta_group::2): the pair works on one weight tile for two adjacent
+// 128-stream row tiles as a single M = 256 MMA.  Each CTA loads its own A rows and HALF of the weight rows, the
+// leader issues the MMAs and the tensor cores of both SMs read B from both shared memories -- per SM that halves
+// the B operand traffic (global->shared and shared->tensor core), which is what bounds this kernel.
+// The accumulators are zeroed by the epilogue warps (tcgen05.st) so that every MMA accumulates.
 template <int NA, int NB, int BN, int STAGES, bool GRU>
 __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__ TcArgs args) {
   using SL = StageLayout<NA, NB, BN>;
@@ -227,11 +268,13 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
   float *tbl = reinterpret_cast<float *>(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = args.tiles_m * args.tiles_n;
+  const int crank = (int)cluster_ctarank();  // 0 = leader
+  const int n_pairs_cta = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
+  const int total_pairs = ((args.tiles_m + 1) >> 1) * args.tiles_n;  // work unit: one B tile x two row tiles
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }  // both CTAs' epilogues
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
@@ -240,46 +283,56 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 4) {  // zero both accumulator buffers: every MMA accumulates
+    const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c = 0; c < kTmemCols; c += 16) tmem_st16_zero(tl + c);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers and TMEM are ready before the leader issues anything
+  tc_fence_after();
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (both CTAs): own A rows, own half of the B rows; bytes counted on the leader's barrier =====
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % args.tiles_n, m0 = (tile / args.tiles_n) * TM;
+      for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta) {
+        const int n_tile = pair % args.tiles_n, m0 = (2 * (pair / args.tiles_n) + crank) * TM;
         for (int s = 0; s < args.n_seg; s++) {
           const TcSeg sg = args.seg[s];
           const CUtensorMap *ma = &args.maps[sg.a_map], *mb = &args.maps[sg.b_map];
           for (int kb = 0; kb < sg.k_blocks; kb++, it++) {
             const int st = it % STAGES;
             mbar_wait(&empty_bar[st], ((it / STAGES) & 1) ^ 1);  // fresh barrier: passes immediately
-            mbar_expect_tx(&full_bar[st], SL::kBytes);
+            if (crank == 0) mbar_expect_tx(&full_bar[st], 2 * SL::kPairBytes);
             uint8_t *sp = stage_base + st * SL::kBytes;
 #pragma unroll
             for (int ta = 0; ta < NA; ta++)
-              tma_load_2d(sp + ta * SL::kABytes, ma, &full_bar[st], sg.a_k0 + kb * BK, ta * args.a_term_rows + m0);
+              tma_load_2d_pair(sp + ta * SL::kABytes, ma, &full_bar[st], sg.a_k0 + kb * BK, ta * args.a_term_rows + m0);
 #pragma unroll
             for (int tb = 0; tb < NB; tb++)
-              tma_load_2d(sp + NA * SL::kABytes + tb * SL::kBBytes, mb, &full_bar[st], sg.b_k0 + kb * BK,
-                          tb * args.b_term_rows + n_tile * BN);
+              tma_load_2d_pair(sp + NA * SL::kABytes + tb * SL::kBBytes, mb, &full_bar[st], sg.b_k0 + kb * BK,
+                               tb * args.b_term_rows + n_tile * BN + crank * (BN / 2));
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      const uint32_t id_main = idesc_f16(GRU ? 3 * HT : BN, args.fmt), id_zr = idesc_f16(2 * HT, args.fmt),
-                     id_n = idesc_f16(HT, args.fmt);
+    // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
+    if (lane == 0 && crank == 0) {
+      const uint32_t id_main = idesc_f16(GRU ? 3 * HT : BN, args.fmt);
       int it = 0, j = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, j++) {
+      for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta, j++) {
         const int buf = j & 1;
         const uint32_t acc = tmem_base + buf * kAccCols;
-        mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);  // epilogue has drained this buffer (2 tiles ago)
+        mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);  // both epilogues drained (and re-zeroed) this buffer
         tc_fence_after();
-        bool started_main = false, started_nh = false;
         for (int s = 0; s < args.n_seg; s++) {
           const TcSeg sg = args.seg[s];
+          // GRU accumulator columns [nx | z | r | nh]: input part (rows [n|z|r]) at column 0, recurrent part
+          // (rows [z|r|n]) at column 64; each is one N = 192 MMA
+          const uint32_t dcol = (GRU && sg.recurrent) ? acc + HT : acc;
           for (int kb = 0; kb < sg.k_blocks; kb++, it++) {
             const int st = it % STAGES;
             mbar_wait(&full_bar[st], (it / STAGES) & 1);
@@ -291,30 +344,14 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
 #pragma unroll
               for (int p = 0; p < PR::n; p++) {
                 const uint64_t ad = smem_desc_sw64(sa + PR::a(p) * SL::kABytes) + (uint64_t)(ks * 2);
-                const uint32_t bt = sb + PR::b(p) * SL::kBBytes;
-                const uint64_t bd = smem_desc_sw64(bt) + (uint64_t)(ks * 2);
-                if (!GRU) {
-                  umma_f16(acc, ad, bd, id_main, started_main ? 1u : 0u);
-                  started_main = true;
-                } else if (!sg.recurrent) {
-                  // input part: weight rows [n | z | r] -> columns [nx | z | r] = acc + 0 .. 191, one N = 192 MMA
-                  umma_f16(acc, ad, bd, id_main, started_main ? 1u : 0u);
-                  started_main = true;
-                } else if (started_nh) {
-                  // recurrent part: weight rows [z | r | n] -> columns [z | r | nh] = acc + 64 .. 255
-                  umma_f16(acc + HT, ad, bd, id_main, 1u);
-                } else {
-                  // first recurrent MMA: z, r already hold the input part (accumulate), nh starts from zero
-                  umma_f16(acc + HT, ad, bd, id_zr, started_main ? 1u : 0u);
-                  umma_f16(acc + 3 * HT, ad, smem_desc_sw64(bt + 2 * HT * BK * 2) + (uint64_t)(ks * 2), id_n, 0u);
-                  started_nh = true;
-                }
+                const uint64_t bd = smem_desc_sw64(sb + PR::b(p) * SL::kBBytes) + (uint64_t)(ks * 2);
+                umma_f16(dcol, ad, bd, id_main, 1u);
               }
             }
-            umma_commit(&empty_bar[st]);  // frees the stage when the MMAs above have read it
+            umma_commit(&empty_bar[st]);  // frees the stage in both CTAs once these MMAs have read it
           }
         }
-        umma_commit(&acc_full[buf]);
+        umma_commit(&acc_full[buf]);  // both epilogues
       }
     }
   } else if (warp >= 4) {
@@ -322,8 +359,8 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
     const int wq = warp & 3;
     const float sc = args.out_scale;
     int j = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, j++) {
-      const int n_tile = tile % args.tiles_n, m0 = (tile / args.tiles_n) * TM;
+    for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta, j++) {
+      const int n_tile = pair % args.tiles_n, m0 = (2 * (pair / args.tiles_n) + crank) * TM;
       const int buf = j & 1;
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
@@ -424,20 +461,23 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
           }
         }
       }
-      // hand the accumulator buffer back to the MMA warp
+      // zero the buffer for its next tile and hand it back to the leader's MMA thread
+      for (int c = 0; c < kAccCols; c += 16) tmem_st16_zero(tlane + c);
+      tmem_st_wait();
       tc_fence_before();
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
+      mbar_arrive_leader(&acc_empty[buf]);
     }
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the pair still has work in flight
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-constexpr int GRU_STAGES = 5, DENSE_STAGES = 6, SMALL_BN = 48, SMALL_STAGES = 8;
+constexpr int GRU_STAGES = 7, DENSE_STAGES = 8, SMALL_BN = 48, SMALL_STAGES = 8;
 template <int NA, int NB, int BN, int STAGES>
 constexpr size_t tc_smem_bytes() {
   return (size_t)STAGES * StageLayout<NA, NB, BN>::kBytes + (2 * STAGES + 4) * 8 + 16 + 208 * 4 + 1024;
@@ -647,19 +687,19 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
     TCK(dev_upload(&t->w_rb, p));
   }
   int bad = 0;
-  bad |= make_map(&t->m_wgb, t->w_gb, false, 2 * SMALL_BN, 2560, SMALL_BN);
-  bad |= make_map(&t->m_wrb, t->w_rb, false, 2 * SMALL_BN, 128, SMALL_BN);
+  bad |= make_map(&t->m_wgb, t->w_gb, false, 2 * SMALL_BN, 2560, SMALL_BN / 2);
+  bad |= make_map(&t->m_wrb, t->w_rb, false, 2 * SMALL_BN, 128, SMALL_BN / 2);
   for (int q = 0; q < 5; q++) bad |= make_map(&t->m_ring_fc[q], t->ring_fc + (size_t)q * kConvTerms * S * 128, true, kConvTerms * S, 128, TM);
   for (int q = 0; q < 3; q++) bad |= make_map(&t->m_ring_c1[q], t->ring_c1 + (size_t)q * kConvTerms * S * 512, true, kConvTerms * S, 512, TM);
   bad |= make_map(&t->m_c2, t->c2_h, false, 2 * S, 512, TM);
   for (int i = 0; i < 5; i++)
     for (int p = 0; p < 2; p++) bad |= make_map(&t->m_h[i][p], t->h_h[i][p], false, 2 * S, e->gru[i].H, TM);
-  bad |= make_map(&t->m_wconv1, t->w_conv1, true, kConvTerms * 512, 640, DENSE_BN);
-  bad |= make_map(&t->m_wconv2, t->w_conv2, true, kConvTerms * 512, 1536, DENSE_BN);
+  bad |= make_map(&t->m_wconv1, t->w_conv1, true, kConvTerms * 512, 640, DENSE_BN / 2);
+  bad |= make_map(&t->m_wconv2, t->w_conv2, true, kConvTerms * 512, 1536, DENSE_BN / 2);
   for (int i = 0; i < 5; i++) {
     const int rows = (e->gru[i].H / HT) * GRU_BN;
-    bad |= make_map(&t->m_w[i], t->w_gru[i], false, 2 * rows, e->gru[i].M, GRU_BN);
-    bad |= make_map(&t->m_u[i], t->u_gru[i], false, 2 * rows, e->gru[i].H, GRU_BN);
+    bad |= make_map(&t->m_w[i], t->w_gru[i], false, 2 * rows, e->gru[i].M, GRU_BN / 2);
+    bad |= make_map(&t->m_u[i], t->u_gru[i], false, 2 * rows, e->gru[i].H, GRU_BN / 2);
   }
   if (bad) return tc_fail(PNB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   TCK(cudaFuncSetAttribute(tc_gemm_kernel<2, 2, GRU_BN, GRU_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -703,9 +743,20 @@ template <int NA, int NB, int BN, int STAGES, bool GRU>
 static void tc_launch(pnb_engine *e, TcArgs &a, int tiles_n, cudaStream_t st) {
   a.tiles_m = (e->S + TM - 1) / TM;
   a.tiles_n = tiles_n;
-  int total = a.tiles_m * a.tiles_n;
-  int grid = total < e->sm_count ? total : e->sm_count;
-  tc_gemm_kernel<NA, NB, BN, STAGES, GRU><<<grid, 256, tc_smem_bytes<NA, NB, BN, STAGES>(), st>>>(a);
+  int pairs = ((a.tiles_m + 1) / 2) * a.tiles_n;
+  int clusters = pairs < e->sm_count / 2 ? pairs : e->sm_count / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = tc_smem_bytes<NA, NB, BN, STAGES>();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, tc_gemm_kernel<NA, NB, BN, STAGES, GRU>, a);
 }
 
 static TcSeg mkseg(int a_map, int b_map, int K, int a_k0, int b_k0, int rec) {
