@@ -225,6 +225,21 @@ __device__ void best_two(const float *xcorr, const float *dsyy, int max_pitch, f
   }
 }
 
+// Sequential dot product s + sum_j a[j] b[j] (ascending j, multiply then add -- the reference's order) with the
+// `a` operand fetched four at a time: `a` is the operand that is common to (almost) all lanes, so its 128-bit load
+// is a single shared-memory wavefront per four steps.  a must be 16-byte aligned, n a multiple of 4.
+__device__ __forceinline__ float seq_dot4(const float *a, const float *b, int n, float s) {
+#pragma unroll 2
+  for (int j = 0; j < n; j += 4) {
+    const float4 av = *reinterpret_cast<const float4 *>(a + j);
+    s = s + av.x * b[j];
+    s = s + av.y * b[j + 1];
+    s = s + av.z * b[j + 2];
+    s = s + av.w * b[j + 3];
+  }
+  return s;
+}
+
 __device__ __forceinline__ float pitch_gain(float xy, float xx, float yy) {
   return xy / sqrtf(1.f + xx * yy);  // pitch.cpp:417-420 (float sqrt overload)
 }
@@ -328,9 +343,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
       // autocorrelation, 5 lags: bulk over 860 samples then the 4-sample tail (celt_lpc.cpp:250-256)
       float ac = 0.f;
       if (lane < 5) {
-        const float *a = W.p.lp, *b = W.p.lp + lane;
-#pragma unroll 4
-        for (int j = 0; j < 860; j++) ac = ac + a[j] * b[j];
+        ac = seq_dot4(W.p.lp, W.p.lp + lane, 860, 0.f);
         float d = 0.f;
         for (int i = lane + 860; i < kLp; i++) d = d + W.p.lp[i] * W.p.lp[i - lane];
         ac += d;
@@ -459,8 +472,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         else if (lane == 10) { a = W.p.lp; b = W.p.lp; }
         else if (lane == 11) { a = W.p.lp + 384; b = W.p.lp + 384; }
         else { a = W.p.lp; b = W.p.lp; n = 0; }
-#pragma unroll 4
-        for (int j = 0; j < n; j++) s = s + a[j] * b[j];
+        if (n) s = seq_dot4(a, b, 480, s);
       }
       if (fine_ok) W.xc[fl] = (-1.f > s) ? -1.f : s;
       float syy_f = __shfl_sync(0xffffffffu, s, 10);
@@ -502,20 +514,23 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
           }
         }
         if (lane == 1) {
+          // yy_lookup recurrence (pitch.cpp:449-455), strictly sequential; operands fetched four at a time.
+          // Table entry i is stored at W.p.yy[i + 3] so that groups of four are 16-byte aligned.
           float yy = xx;
-          W.p.yy[0] = xx;
-          for (int i = 1; i <= 384; i++) {
-            float a = x[-i], b = x[480 - i];
-            yy = yy + a * a - b * b;
-            W.p.yy[i] = 0.f > yy ? 0.f : yy;
+          W.p.yy[3] = xx;
+          for (int i = 1; i <= 384; i += 4) {
+            const float4 a = *reinterpret_cast<const float4 *>(x - i - 3);        // x[-i-3 .. -i]
+            const float4 b = *reinterpret_cast<const float4 *>(x + 480 - i - 3);  // x[480-i-3 .. 480-i]
+            float4 o;
+            yy = yy + a.w * a.w - b.w * b.w; o.x = 0.f > yy ? 0.f : yy;
+            yy = yy + a.z * a.z - b.z * b.z; o.y = 0.f > yy ? 0.f : yy;
+            yy = yy + a.y * a.y - b.y * b.y; o.z = 0.f > yy ? 0.f : yy;
+            yy = yy + a.x * a.x - b.x * b.x; o.w = 0.f > yy ? 0.f : yy;
+            *reinterpret_cast<float4 *>(&W.p.yy[i + 3]) = o;
           }
         } else {
           float d = 0.f;
-          if (lag >= 0) {
-            const float *b = x - lag;
-#pragma unroll 4
-            for (int j = 0; j < 480; j++) d = d + x[j] * b[j];
-          }
+          if (lag >= 0) d = seq_dot4(x, x - lag, 480, 0.f);
           W.p.cand_xy[lane] = d;
         }
       }
@@ -524,7 +539,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
       float g = 0.f, best_xy = 0.f, best_yy = 0.f;
       if (lane == 0) {
         float xy = W.p.cand_xy[0];
-        float yy = W.p.yy[T0];
+        float yy = W.p.yy[T0 + 3];
         best_xy = xy;
         best_yy = yy;
         float g0 = pitch_gain(xy, xx, yy);
@@ -537,7 +552,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
           else T1b = (2 * second_check[k] * T0 + k) / (2 * k);
           float xy1 = W.p.cand_xy[2 + 2 * (k - 2)], xy2 = W.p.cand_xy[3 + 2 * (k - 2)];
           xy = .5f * (xy1 + xy2);
-          yy = .5f * (W.p.yy[T1] + W.p.yy[T1b]);
+          yy = .5f * (W.p.yy[T1 + 3] + W.p.yy[T1b + 3]);
           float g1 = pitch_gain(xy, xx, yy);
           float cont;
           int dT = T1 - prev_period;
@@ -558,11 +573,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
       // final +-1 refinement: three dot products around the selected period (pitch.cpp:512-513)
       {
         float d = 0.f;
-        if (lane < 3) {
-          const float *b = x - (Tsel + lane - 1);
-#pragma unroll 4
-          for (int j = 0; j < 480; j++) d = d + x[j] * b[j];
-        }
+        if (lane < 3) d = seq_dot4(x, x - (Tsel + lane - 1), 480, 0.f);
         float x0 = __shfl_sync(0xffffffffu, d, 0), x1 = __shfl_sync(0xffffffffu, d, 1),
               x2 = __shfl_sync(0xffffffffu, d, 2);
         int Tout = 0;
