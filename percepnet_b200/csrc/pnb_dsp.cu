@@ -179,18 +179,19 @@ __device__ __forceinline__ void fft960_warp(float2 *f, const FftTw &T, int lane,
 // ERB band pooling (denoise.cpp:89-123 / 125-160): v[bin] is |X|^2 or Re(X conj P) for bins 0..399.
 // Accumulator b receives, in the reference's order, first the frac-weighted bins of band b-1 and then
 // the (1-frac)-weighted bins of band b; ends are doubled.
-__device__ void band_pool_warp(const float *v, float *out, const float *frac, const float *omf,
-                               const short *border, int lane) {
+__device__ void band_pool_warp(const float *vf, const float *vo, float *out, const short *border, int lane) {
+  // vf[k] = frac[k] * v[k] and vo[k] = (1 - frac[k]) * v[k] were formed by the caller (the very products the
+  // reference adds, denoise.cpp:102-103), so the serial part is one load and one add per bin
   __syncwarp();
   for (int b = lane; b < kBands; b += 32) {
     float acc = 0.f;
     if (b > 0) {
       int lo = border[b - 1], hi = border[b];
-      for (int k = lo; k < hi; k++) acc = acc + frac[k] * v[k];
+      for (int k = lo; k < hi; k++) acc = acc + vf[k];
     }
     if (b < kBands - 1) {
       int lo = border[b], hi = border[b + 1];
-      for (int k = lo; k < hi; k++) acc = acc + omf[k] * v[k];
+      for (int k = lo; k < hi; k++) acc = acc + vo[k];
     }
     if (b == 0 || b == kBands - 1) acc *= 2;
     out[b] = acc;
@@ -240,6 +241,48 @@ __device__ __forceinline__ float seq_dot4(const float *a, const float *b, int n,
   return s;
 }
 
+// The fine search leaves xcorr at zero except within +-2 of 2*b0 and 2*b1 (pitch.cpp:344-361); zero entries can
+// never become candidates (pitch.cpp:73), so between the two windows only the running energy is advanced.
+__device__ void best_two_sparse(const float *xcorr, const float *dsyy, int max_pitch, float syy, int w0, int w1,
+                                int &b0, int &b1) {
+  float num0 = -1.f, num1 = -1.f, den0 = 0.f, den1 = 0.f;
+  b0 = 0;
+  b1 = 1;
+  int lo_a = w0 < w1 ? w0 : w1, lo_b = w0 < w1 ? w1 : w0;
+  int i = 0;
+#pragma unroll 1
+  for (int seg = 0; seg < 2; seg++) {
+    int lo = seg == 0 ? lo_a : lo_b;
+    lo = lo < i ? i : lo;
+    lo = lo > max_pitch ? max_pitch : lo;
+    int hi = (seg == 0 ? lo_a : lo_b) + 5;
+    hi = hi < lo ? lo : hi;
+    hi = hi > max_pitch ? max_pitch : hi;
+    for (; i < lo; i++) {  // no candidates here
+      syy = syy + dsyy[i];
+      syy = 1.f > syy ? 1.f : syy;
+    }
+    for (; i < hi; i++) {
+      float xc = xcorr[i];
+      if (xc > 0.f) {
+        float c = xc * 1e-12f;
+        float num = c * c;
+        if (num * den1 > num1 * syy) {
+          if (num * den0 > num0 * syy) {
+            num1 = num0; den1 = den0; b1 = b0;
+            num0 = num;  den0 = syy;  b0 = i;
+          } else {
+            num1 = num; den1 = syy; b1 = i;
+          }
+        }
+      }
+      syy = syy + dsyy[i];
+      syy = 1.f > syy ? 1.f : syy;
+    }
+  }
+  // the energy after the last window is never used again
+}
+
 __device__ __forceinline__ float pitch_gain(float xy, float xx, float yy) {
   return xy / sqrtf(1.f + xx * yy);  // pitch.cpp:417-420 (float sqrt overload)
 }
@@ -254,7 +297,8 @@ struct WarpSmem {
     float2 fft[kFftLine];  // FFT work line (padded, see fpos)
     PitchSmem p;
   };
-  float xc[400];       // xcorr (147 / 294) -- doubles as the per-bin scratch of band pooling
+  float xc[400];       // xcorr (147 / 294) -- doubles as the per-bin scratch of band pooling (frac-weighted);
+                       // the (1-frac)-weighted scratch lives in the tail of the FFT line (bins 0..399 end at slot 447)
   float Ex[kBands], Ep[kBands], Exp[kBands], Ey[kBands];
 };
 
@@ -286,6 +330,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
   const int s = blockIdx.x * kAnaWarps + wib;
   if (s >= A.n_streams) return;
   WarpSmem &W = Wall[wib];
+  float *xo = reinterpret_cast<float *>(&W.fft[448]);
   const float *row = A.pcm + (size_t)s * A.pcm_stride;
   int last_period = A.last_period[s];
   float last_gain = A.last_gain[s];
@@ -317,9 +362,10 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         Zg[k] = x;
         float e = x.x * x.x;
         e += x.y * x.y;
-        W.xc[k] = e;
+        W.xc[k] = B.frac[k] * e;
+        xo[k] = B.omf[k] * e;
       }
-      band_pool_warp(W.xc, W.Ey, B.frac, B.omf, B.border, lane);
+      band_pool_warp(W.xc, xo, W.Ey, B.border, lane);
       float *Eg = A.ering + ((size_t)slot_new * A.n_streams + s) * kBands;
       const float *Eo = A.ering + ((size_t)slot_x * A.n_streams + s) * kBands;
       for (int b = lane; b < kBands; b += 32) {
@@ -482,7 +528,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
       float corr = 0.f;
       if (lane == 0) {
         int c0, c1;
-        best_two(W.xc, W.p.yy, 294, syy_f, c0, c1);
+        best_two_sparse(W.xc, W.p.yy, 294, syy_f, 2 * b0 - 2, 2 * b1 - 2, c0, c1);
         if (c0 > 0 && c0 < 293) {
           float a = W.xc[c0 - 1], b = W.xc[c0], c = W.xc[c0 + 1];
           if ((c - a) > .7f * (b - a)) off = 1;
@@ -617,16 +663,18 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         Pg[k] = p;
         float e = p.x * p.x;
         e += p.y * p.y;
-        W.xc[k] = e;
+        W.xc[k] = B.frac[k] * e;
+        xo[k] = B.omf[k] * e;
       }
-      band_pool_warp(W.xc, W.Ep, B.frac, B.omf, B.border, lane);
+      band_pool_warp(W.xc, xo, W.Ep, B.border, lane);
       for (int k = lane; k < kBins; k += 32) {
         float2 p = W.fft[fpos(k)], x = Xg[k];
         float e = x.x * p.x;
         e += x.y * p.y;
-        W.xc[k] = e;
+        W.xc[k] = B.frac[k] * e;
+        xo[k] = B.omf[k] * e;
       }
-      band_pool_warp(W.xc, W.Exp, B.frac, B.omf, B.border, lane);
+      band_pool_warp(W.xc, xo, W.Exp, B.border, lane);
     }
 
     // ---- features (denoise.cpp:427-433, 487-496, 528-530) ----
