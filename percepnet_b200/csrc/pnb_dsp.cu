@@ -16,6 +16,7 @@
 // strict ascending multiply-then-add chain, so pitch decisions, spectra and features are bit-identical
 // to the reference (whose objects contain no FMA and no re-associated sums).
 // The two double-precision islands (denoise.cpp:427, celt_lpc.cpp:61) run in fp64 here as well.
+#include <stdlib.h>
 #include "pnb_kernels.h"
 
 namespace pnb {
@@ -57,15 +58,16 @@ struct FftTw {            // per-block tables in shared memory
 //           through shared memory), does radix-4 m=1 and radix-4 m=4 in registers, stores 128 contiguous bytes
 //   pass B: radix-4 m=16 then radix-3 m=64 on the 12 elements {192 n0 + 64 r + 16 q + j}
 //   pass C: radix-5 m=192
-template <bool kAllOutputs, class Load>
-__device__ __forceinline__ void fft960_warp(float2 *f, const FftTw &T, int lane, Load load) {
-  __syncwarp();
+// L lanes (32 or 16) cooperate on one transform; `mask` names them, `lane` is the index within the group.
+template <bool kAllOutputs, int L, class Load>
+__device__ __forceinline__ void fft960_warp(float2 *f, const FftTw &T, int lane, unsigned mask, Load load) {
+  __syncwarp(mask);
   {  // ---------------- pass A ----------------
     const float2 t1a = T.tw[60], t1b = T.tw[120], t1c = T.tw[180];    // j = 1: tw[60 j], tw[120 j], tw[180 j]
     const float2 t2a = T.tw[120], t2b = T.tw[240], t2c = T.tw[360];   // j = 2
     const float2 t3a = T.tw[180], t3b = T.tw[360], t3c = T.tw[540];   // j = 3
     const float2 t0 = T.tw[0];
-    for (int b = lane; b < 60; b += 32) {
+    for (int b = lane; b < 60; b += L) {
       const int n0 = b / 12, n1 = (b >> 2) % 3, n2 = b & 3;
       const int ibase = n0 + 5 * n1 + 15 * n2;
       float2 v[16];
@@ -107,10 +109,10 @@ __device__ __forceinline__ void fft960_warp(float2 *f, const FftTw &T, int lane,
       for (int k = 0; k < 8; k++) dst[k] = make_float4(v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
     }
   }
-  __syncwarp();
+  __syncwarp(mask);
   {  // ---------------- pass B ----------------
     const float w3i = T.tw[320].y;  // epi3, kiss_fft.cpp:194
-    for (int g = lane; g < 80; g += 32) {
+    for (int g = lane; g < 80; g += L) {
       const int n0 = g >> 4, jj = g & 15;
       const int e0 = 192 * n0 + jj;
       float2 v[3][4];
@@ -151,10 +153,10 @@ __device__ __forceinline__ void fft960_warp(float2 *f, const FftTw &T, int lane,
         for (int q = 0; q < 4; q++) f[fpos(e0 + 64 * r + 16 * q)] = v[r][q];
     }
   }
-  __syncwarp();
+  __syncwarp(mask);
   {  // ---------------- pass C: radix-5, m = 192 (kiss_fft.cpp:232-305); ya = tw[192], yb = tw[384] ----------------
     const float2 ya = T.tw[192], yb = T.tw[384];
-    for (int u = lane; u < 192; u += 32) {
+    for (int u = lane; u < 192; u += L) {
       float2 z0 = f[fpos(u)];
       float2 z1 = cmul(f[fpos(u + 192)], T.tw5[0][u]);
       float2 z2 = cmul(f[fpos(u + 384)], T.tw5[1][u]);
@@ -173,17 +175,19 @@ __device__ __forceinline__ void fft960_warp(float2 *f, const FftTw &T, int lane,
       if (kAllOutputs) f[fpos(u + 576)] = csub(p, q);
     }
   }
-  __syncwarp();
+  __syncwarp(mask);
 }
 
 // ERB band pooling (denoise.cpp:89-123 / 125-160): v[bin] is |X|^2 or Re(X conj P) for bins 0..399.
 // Accumulator b receives, in the reference's order, first the frac-weighted bins of band b-1 and then
 // the (1-frac)-weighted bins of band b; ends are doubled.
-__device__ void band_pool_warp(const float *vf, const float *vo, float *out, const short *border, int lane) {
+template <int L>
+__device__ void band_pool_warp(const float *vf, const float *vo, float *out, const short *border, int lane,
+                               unsigned mask) {
   // vf[k] = frac[k] * v[k] and vo[k] = (1 - frac[k]) * v[k] were formed by the caller (the very products the
   // reference adds, denoise.cpp:102-103), so the serial part is one load and one add per bin
-  __syncwarp();
-  for (int b = lane; b < kBands; b += 32) {
+  __syncwarp(mask);
+  for (int b = lane; b < kBands; b += L) {
     float acc = 0.f;
     if (b > 0) {
       int lo = border[b - 1], hi = border[b];
@@ -196,7 +200,7 @@ __device__ void band_pool_warp(const float *vf, const float *vo, float *out, con
     if (b == 0 || b == kBands - 1) acc *= 2;
     out[b] = acc;
   }
-  __syncwarp();
+  __syncwarp(mask);
 }
 
 // pitch.cpp:46-104 (float build): best two lags by xcorr^2/Syy with the reference's update rule.
@@ -311,13 +315,27 @@ struct BlockSmem {
   float comb_w[8];
 };
 
-constexpr int kAnaWarps = 8;
+// One stream is owned by a group of L lanes: L = 32 (a warp per stream) or L = 16 (two streams per warp).  The
+// serial stretches of the pitch analysis keep only a handful of lanes busy, so with L = 16 every such instruction
+// (and shared-memory wavefront) serves two streams.
+template <int L>
+struct AnaCfg {
+  static constexpr int kStreamsPerWarp = 32 / L;
+  static constexpr int kWarps = (L == 32) ? 8 : 4;             // 8 streams per block either way
+  static constexpr int kStreamsPerBlock = kWarps * kStreamsPerWarp;
+  static constexpr int kLagsPerLane = (L == 32) ? 5 : 10;       // coarse search: adjacent lags per lane
+  static constexpr int kLagLanes = (L == 32) ? 30 : 15;         // lanes that own lags; the next lane accumulates Syy
+};
 
-__global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A) {
+template <int L>
+__global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(AnalysisArgs A) {
+  using CF = AnaCfg<L>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BlockSmem &B = *reinterpret_cast<BlockSmem *>(smem_raw);
   WarpSmem *Wall = reinterpret_cast<WarpSmem *>(smem_raw + ((sizeof(BlockSmem) + 15) / 16) * 16);
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int wlane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = wlane % L, sub = wlane / L;  // lane within the stream's group, group within the warp
+  const unsigned mask = (L == 32) ? 0xffffffffu : (0xffffu << (16 * sub));
   const Tables *T = A.tab;
   for (int i = threadIdx.x; i < kWin; i += blockDim.x) B.ft.tw[i] = T->tw[i];
   for (int i = threadIdx.x; i < 4 * 192; i += blockDim.x) B.ft.tw5[i / 192][i % 192] = T->tw[(i / 192 + 1) * (i % 192)];
@@ -327,9 +345,10 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
   if (threadIdx.x < 8) B.comb_w[threadIdx.x] = T->comb_w[threadIdx.x];
   __syncthreads();
 
-  const int s = blockIdx.x * kAnaWarps + wib;
+  const int sl = wib * CF::kStreamsPerWarp + sub;  // stream slot within the block
+  const int s = blockIdx.x * CF::kStreamsPerBlock + sl;
   if (s >= A.n_streams) return;
-  WarpSmem &W = Wall[wib];
+  WarpSmem &W = Wall[sl];
   float *xo = reinterpret_cast<float *>(&W.fft[448]);
   const float *row = A.pcm + (size_t)s * A.pcm_stride;
   int last_period = A.last_period[s];
@@ -349,7 +368,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
       const float *src = line + kOffLook;
       const float *hw = B.hw;
       // window (denoise.cpp:282-289), real -> complex, 1/960 (kiss_fft.cpp:582-583)
-      fft960_warp<false>(W.fft, B.ft, lane, [&](int i) {
+      fft960_warp<false, L>(W.fft, B.ft, lane, mask, [&](int i) {
         float w = hw[i < kFrame ? i : kWin - 1 - i];
         float v = src[i] * w;
         return make_float2((1.f / kWin) * v, 0.f);
@@ -357,7 +376,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
     }
     {
       float2 *Zg = A.zring + ((size_t)slot_new * A.n_streams + s) * kBins;
-      for (int k = lane; k < kBins; k += 32) {
+      for (int k = lane; k < kBins; k += L) {
         float2 x = W.fft[fpos(k)];
         Zg[k] = x;
         float e = x.x * x.x;
@@ -365,27 +384,27 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         W.xc[k] = B.frac[k] * e;
         xo[k] = B.omf[k] * e;
       }
-      band_pool_warp(W.xc, xo, W.Ey, B.border, lane);
+      band_pool_warp<L>(W.xc, xo, W.Ey, B.border, lane, mask);
       float *Eg = A.ering + ((size_t)slot_new * A.n_streams + s) * kBands;
       const float *Eo = A.ering + ((size_t)slot_x * A.n_streams + s) * kBands;
-      for (int b = lane; b < kBands; b += 32) {
+      for (int b = lane; b < kBands; b += L) {
         Eg[b] = W.Ey[b];
-        W.Ex[b] = Eo[b];  // written five hops ago (by this warp, or by the previous call)
+        W.Ex[b] = Eo[b];  // written five hops ago (by this lane group, or by the previous call)
       }
     }
     const float2 *Xg = A.zring + ((size_t)slot_x * A.n_streams + s) * kBins;
-    __syncwarp();
+    __syncwarp(mask);
 
     // ---- pitch_downsample (pitch.cpp:148-216) ----
     {
       const float *src = line + kOffPitch;
-      for (int i = lane; i < kLp; i += 32) {
+      for (int i = lane; i < kLp; i += L) {
         float v;
         if (i == 0) v = .5f * (.5f * src[1] + src[0]);
         else v = .5f * (.5f * (src[2 * i - 1] + src[2 * i + 1]) + src[2 * i]);
         W.p.lp[i] = v;
       }
-      __syncwarp();
+      __syncwarp(mask);
       // autocorrelation, 5 lags: bulk over 860 samples then the 4-sample tail (celt_lpc.cpp:250-256)
       float ac = 0.f;
       if (lane < 5) {
@@ -394,9 +413,8 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         for (int i = lane + 860; i < kLp; i++) d = d + W.p.lp[i] * W.p.lp[i - lane];
         ac += d;
       }
-      float ac0 = __shfl_sync(0xffffffffu, ac, 0), ac1 = __shfl_sync(0xffffffffu, ac, 1),
-            ac2 = __shfl_sync(0xffffffffu, ac, 2), ac3 = __shfl_sync(0xffffffffu, ac, 3),
-            ac4 = __shfl_sync(0xffffffffu, ac, 4);
+      float ac0 = __shfl_sync(mask, ac, 0, L), ac1 = __shfl_sync(mask, ac, 1, L), ac2 = __shfl_sync(mask, ac, 2, L),
+            ac3 = __shfl_sync(mask, ac, 3, L), ac4 = __shfl_sync(mask, ac, 4, L);
       float fir0 = 0, fir1 = 0, fir2 = 0, fir3 = 0, fir4 = 0;
       if (lane == 0) {
         float a[5] = {ac0, ac1, ac2, ac3, ac4};
@@ -428,14 +446,14 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         fir3 = lpc[3] + .8f * lpc[2];
         fir4 = .8f * lpc[3];
       }
-      fir0 = __shfl_sync(0xffffffffu, fir0, 0);
-      fir1 = __shfl_sync(0xffffffffu, fir1, 0);
-      fir2 = __shfl_sync(0xffffffffu, fir2, 0);
-      fir3 = __shfl_sync(0xffffffffu, fir3, 0);
-      fir4 = __shfl_sync(0xffffffffu, fir4, 0);
+      fir0 = __shfl_sync(mask, fir0, 0, L);
+      fir1 = __shfl_sync(mask, fir1, 0, L);
+      fir2 = __shfl_sync(mask, fir2, 0, L);
+      fir3 = __shfl_sync(mask, fir3, 0, L);
+      fir4 = __shfl_sync(mask, fir4, 0, L);
       // 5-tap FIR in place with zero history (pitch.cpp:106-145,154), walked from the end so the taps
       // still see unfiltered samples
-      for (int base = kLp - 32; base >= 0; base -= 32) {
+      for (int base = kLp - L; base >= 0; base -= L) {
         int i = base + lane;
         float x0 = W.p.lp[i];
         float m0 = i >= 1 ? W.p.lp[i - 1] : 0.f, m1 = i >= 2 ? W.p.lp[i - 2] : 0.f, m2 = i >= 3 ? W.p.lp[i - 3] : 0.f,
@@ -446,9 +464,9 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         sum = sum + fir2 * m2;
         sum = sum + fir3 * m3;
         sum = sum + fir4 * m4;
-        __syncwarp();
+        __syncwarp(mask);
         W.p.lp[i] = sum;
-        __syncwarp();
+        __syncwarp(mask);
       }
     }
 
@@ -457,60 +475,60 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
     float pitch_corr, gain;
     {
       int b0, b1;
-      // coarse: the 4x-decimated signals are stride-2 views of lp.  Lane l < 30 owns the five adjacent lags
-      // 5l .. 5l+4 and slides a five-sample window of y along, so each step costs one new y load; every lag
-      // still accumulates in ascending j exactly like the reference (pitch.cpp:218-281).  Lane 30 accumulates the
-      // energy Syy = 1 + sum y4[j]^2 of find_best_pitch (pitch.cpp:54,69-70) through the same code shape.
+      // coarse: the 4x-decimated signals are stride-2 views of lp.  A lag lane owns kLagsPerLane adjacent lags and
+      // slides a window of y along, so each step costs one new y load; every lag still accumulates in ascending
+      // j exactly like the reference (pitch.cpp:218-281).  The lane after the lag lanes accumulates the energy
+      // Syy = 1 + sum y4[j]^2 of find_best_pitch (pitch.cpp:54,69-70) through the same code shape (lag 0 of y on y).
       {
-        const float *xb = (lane == 30) ? W.p.lp : W.p.lp + 384;
-        const int L = (lane < 30) ? 5 * lane : 0;
-        const float *yb = W.p.lp + 2 * L;
-        float acc0 = (lane == 30) ? 1.f : 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, acc4 = 0.f;
-        float w0 = yb[0], w1 = yb[2], w2 = yb[4], w3 = yb[6], w4 = yb[8];
-        for (int j = 0; j < 240; j += 5) {
-          float xj;
-#define PNB_STEP(A0, A1, A2, A3, A4, JJ)                                                   \
-          xj = xb[2 * (j + JJ)];                                                           \
-          acc0 = acc0 + xj * A0; acc1 = acc1 + xj * A1; acc2 = acc2 + xj * A2;            \
-          acc3 = acc3 + xj * A3; acc4 = acc4 + xj * A4;                                    \
-          A0 = yb[2 * (j + JJ + 5)];
-          PNB_STEP(w0, w1, w2, w3, w4, 0)
-          PNB_STEP(w1, w2, w3, w4, w0, 1)
-          PNB_STEP(w2, w3, w4, w0, w1, 2)
-          PNB_STEP(w3, w4, w0, w1, w2, 3)
-          PNB_STEP(w4, w0, w1, w2, w3, 4)
-#undef PNB_STEP
+        constexpr int NL = CF::kLagsPerLane;
+        const bool syy_lane = (lane == CF::kLagLanes);
+        const float *xb = syy_lane ? W.p.lp : W.p.lp + 384;
+        const int L0 = (lane < CF::kLagLanes) ? NL * lane : 0;
+        const float *yb = W.p.lp + 2 * L0;
+        float acc[NL], w[NL];
+#pragma unroll
+        for (int q = 0; q < NL; q++) { acc[q] = 0.f; w[q] = yb[2 * q]; }
+        if (syy_lane) acc[0] = 1.f;
+        for (int j = 0; j < 240; j += NL) {
+#pragma unroll
+          for (int u = 0; u < NL; u++) {
+            const float xj = xb[2 * (j + u)];
+#pragma unroll
+            for (int q = 0; q < NL; q++) acc[q] = acc[q] + xj * w[(u + q) % NL];
+            w[u] = yb[2 * (j + u + NL)];
+          }
         }
-        if (lane < 30) {
-          W.xc[L] = acc0; W.xc[L + 1] = acc1;
-          if (L + 2 < 147) { W.xc[L + 2] = acc2; W.xc[L + 3] = acc3; W.xc[L + 4] = acc4; }
+        if (lane < CF::kLagLanes) {
+#pragma unroll
+          for (int q = 0; q < NL; q++)
+            if (L0 + q < 147) W.xc[L0 + q] = acc[q];
         }
         // energy deltas of the coarse scan: y4[i+240]^2 - y4[i]^2 (pitch.cpp:101)
-        for (int i = lane; i < 147; i += 32) {
+        for (int i = lane; i < 147; i += L) {
           float yn = W.p.lp[2 * (i + 240)], yo = W.p.lp[2 * i];
           W.p.yy[i] = yn * yn - yo * yo;
         }
-        float syy_c = __shfl_sync(0xffffffffu, acc0, 30);
-        __syncwarp();
+        float syy_c = __shfl_sync(mask, acc[0], CF::kLagLanes, L);
+        __syncwarp(mask);
         b0 = 0; b1 = 0;
         if (lane == 0) best_two(W.xc, W.p.yy, 147, syy_c, b0, b1);
-        b0 = __shfl_sync(0xffffffffu, b0, 0);
-        b1 = __shfl_sync(0xffffffffu, b1, 0);
-        __syncwarp();
+        b0 = __shfl_sync(mask, b0, 0, L);
+        b1 = __shfl_sync(mask, b1, 0, L);
+        __syncwarp(mask);
       }
       // fine: at most ten lags around 2*b0 and 2*b1 (pitch.cpp:344-361); lane 10 accumulates Syy of the
       // second find_best_pitch, lane 11 the xx of remove_doubling (pitch.cpp:448)
-      for (int i = lane; i < 294; i += 32) {
+      for (int i = lane; i < 294; i += L) {
         W.xc[i] = 0.f;
         float yn = W.p.lp[i + 480], yo = W.p.lp[i];  // energy deltas of the fine scan
         W.p.yy[i] = yn * yn - yo * yo;
       }
-      __syncwarp();
+      __syncwarp(mask);
       int fl = -1;
       if (lane < 5) fl = 2 * b0 - 2 + lane;
       else if (lane < 10) fl = 2 * b1 - 2 + (lane - 5);
       const bool fine_ok = (fl >= 0 && fl < 294);
-      float s = (lane == 10) ? 1.f : 0.f;
+      float sacc = (lane == 10) ? 1.f : 0.f;
       {
         const float *a, *b;
         int n = 480;
@@ -518,27 +536,29 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         else if (lane == 10) { a = W.p.lp; b = W.p.lp; }
         else if (lane == 11) { a = W.p.lp + 384; b = W.p.lp + 384; }
         else { a = W.p.lp; b = W.p.lp; n = 0; }
-        if (n) s = seq_dot4(a, b, 480, s);
+        if (n) sacc = seq_dot4(a, b, 480, sacc);
       }
-      if (fine_ok) W.xc[fl] = (-1.f > s) ? -1.f : s;
-      float syy_f = __shfl_sync(0xffffffffu, s, 10);
-      float xx = __shfl_sync(0xffffffffu, s, 11);
-      __syncwarp();
+      if (fine_ok) W.xc[fl] = (-1.f > sacc) ? -1.f : sacc;
+      float syy_f = __shfl_sync(mask, sacc, 10, L);
+      float xx = __shfl_sync(mask, sacc, 11, L);
+      __syncwarp(mask);
       int off = 0;
       float corr = 0.f;
+      pitch_lag = 0;
       if (lane == 0) {
         int c0, c1;
         best_two_sparse(W.xc, W.p.yy, 294, syy_f, 2 * b0 - 2, 2 * b1 - 2, c0, c1);
         if (c0 > 0 && c0 < 293) {
-          float a = W.xc[c0 - 1], b = W.xc[c0], c = W.xc[c0 + 1];
-          if ((c - a) > .7f * (b - a)) off = 1;
-          else if ((a - c) > .7f * (b - c)) off = -1;
+          float a = W.xc[c0 - 1], b = W.xc[c0], cc = W.xc[c0 + 1];
+          if ((cc - a) > .7f * (b - a)) off = 1;
+          else if ((a - cc) > .7f * (b - cc)) off = -1;
         }
         pitch_lag = 2 * c0 - off;
         corr = W.xc[c0];
       }
-      pitch_lag = __shfl_sync(0xffffffffu, pitch_lag, 0);
-      pitch_corr = __shfl_sync(0xffffffffu, corr, 0);
+      pitch_lag = __shfl_sync(mask, pitch_lag, 0, L);
+      pitch_corr = __shfl_sync(mask, corr, 0, L);
+      __syncwarp(mask);  // the scan's energy deltas in W.p.yy are dead; the yy table is built next
 
       // ---- remove_doubling (pitch.cpp:423-527) with maxperiod 384, minperiod 30, N 480 ----
       const int second_check[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};
@@ -546,20 +566,22 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
       int T0 = (kMaxPeriod - pitch_lag) / 2;
       if (T0 >= 384) T0 = 383;
       const int prev_period = last_period / 2;
-      // lane 0: xy at T0; lane 1: the yy_lookup recurrence; lanes 2..29: (k, which) = (2 + (lane-2)/2, (lane-2)&1)
-      {
+      // 30 roles: 0: xy at T0; 1: the yy_lookup recurrence; 2..29: candidate (k, which) = (2 + (role-2)/2, (role-2)&1)
+#pragma unroll 1
+      for (int rbase = 0; rbase < 30; rbase += L) {
+        const int role = rbase + lane;
         int lag = -1;
-        if (lane == 0) lag = T0;
-        else if (lane >= 2 && lane < 30) {
-          int k = 2 + ((lane - 2) >> 1);
+        if (role == 0) lag = T0;
+        else if (role >= 2 && role < 30) {
+          int k = 2 + ((role - 2) >> 1);
           int T1 = (2 * T0 + k) / (2 * k);
           if (T1 >= 30) {
-            if ((lane & 1) == 0) lag = T1;
+            if ((role & 1) == 0) lag = T1;
             else if (k == 2) lag = (T1 + T0 > 384) ? T0 : T0 + T1;
             else lag = (2 * second_check[k] * T0 + k) / (2 * k);
           }
         }
-        if (lane == 1) {
+        if (role == 1) {
           // yy_lookup recurrence (pitch.cpp:449-455), strictly sequential; operands fetched four at a time.
           // Table entry i is stored at W.p.yy[i + 3] so that groups of four are 16-byte aligned.
           float yy = xx;
@@ -574,13 +596,13 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
             yy = yy + a.x * a.x - b.x * b.x; o.w = 0.f > yy ? 0.f : yy;
             *reinterpret_cast<float4 *>(&W.p.yy[i + 3]) = o;
           }
-        } else {
+        } else if (role < 30) {
           float d = 0.f;
           if (lag >= 0) d = seq_dot4(x, x - lag, 480, 0.f);
-          W.p.cand_xy[lane] = d;
+          W.p.cand_xy[role] = d;
         }
       }
-      __syncwarp();
+      __syncwarp(mask);
       int Tsel = T0;
       float g = 0.f, best_xy = 0.f, best_yy = 0.f;
       if (lane == 0) {
@@ -615,13 +637,12 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
           if (g1 > thresh) { best_xy = xy; best_yy = yy; Tsel = T1; g = g1; }
         }
       }
-      Tsel = __shfl_sync(0xffffffffu, Tsel, 0);
+      Tsel = __shfl_sync(mask, Tsel, 0, L);
       // final +-1 refinement: three dot products around the selected period (pitch.cpp:512-513)
       {
         float d = 0.f;
         if (lane < 3) d = seq_dot4(x, x - (Tsel + lane - 1), 480, 0.f);
-        float x0 = __shfl_sync(0xffffffffu, d, 0), x1 = __shfl_sync(0xffffffffu, d, 1),
-              x2 = __shfl_sync(0xffffffffu, d, 2);
+        float x0 = __shfl_sync(mask, d, 0, L), x1 = __shfl_sync(mask, d, 1, L), x2 = __shfl_sync(mask, d, 2, L);
         int Tout = 0;
         float pg = 0.f;
         if (lane == 0) {
@@ -636,20 +657,20 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
           Tout = 2 * Tsel + o2;
           if (Tout < kMinPeriod) Tout = kMinPeriod;
         }
-        T = __shfl_sync(0xffffffffu, Tout, 0);
-        gain = __shfl_sync(0xffffffffu, pg, 0);
+        T = __shfl_sync(mask, Tout, 0, L);
+        gain = __shfl_sync(mask, pg, 0, L);
       }
       last_period = T;
       last_gain = gain;
     }
 
     // ---- comb-filtered block, its spectrum P and the band statistics (denoise.cpp:416-427) ----
-    __syncwarp();  // the pitch scratch is dead from here on; its storage becomes the FFT line again
+    __syncwarp(mask);  // the pitch scratch is dead from here on; its storage becomes the FFT line again
     {
       const float *hw = B.hw;
       const float *cw = B.comb_w;
       const float *ctr = line + kOffAnalysis;
-      fft960_warp<false>(W.fft, B.ft, lane, [&](int i) {
+      fft960_warp<false, L>(W.fft, B.ft, lane, mask, [&](int i) {
         float p = 0.f;
 #pragma unroll
         for (int k = -3; k <= 3; k++) p = p + ctr[i - T * k] * cw[k + 3];
@@ -658,7 +679,7 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         return make_float2((1.f / kWin) * v, 0.f);
       });
       float2 *Pg = A.P + fs * kBins;
-      for (int k = lane; k < kBins; k += 32) {
+      for (int k = lane; k < kBins; k += L) {
         float2 p = W.fft[fpos(k)];
         Pg[k] = p;
         float e = p.x * p.x;
@@ -666,21 +687,21 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
         W.xc[k] = B.frac[k] * e;
         xo[k] = B.omf[k] * e;
       }
-      band_pool_warp(W.xc, xo, W.Ep, B.border, lane);
-      for (int k = lane; k < kBins; k += 32) {
+      band_pool_warp<L>(W.xc, xo, W.Ep, B.border, lane, mask);
+      for (int k = lane; k < kBins; k += L) {
         float2 p = W.fft[fpos(k)], x = Xg[k];
         float e = x.x * p.x;
         e += x.y * p.y;
         W.xc[k] = B.frac[k] * e;
         xo[k] = B.omf[k] * e;
       }
-      band_pool_warp(W.xc, xo, W.Exp, B.border, lane);
+      band_pool_warp<L>(W.xc, xo, W.Exp, B.border, lane, mask);
     }
 
     // ---- features (denoise.cpp:427-433, 487-496, 528-530) ----
     {
       float *F = A.feat + fs * kFeat;
-      for (int b = lane; b < kBands; b += 32) {
+      for (int b = lane; b < kBands; b += L) {
         float prod = W.Ex[b] * W.Ep[b];                       // float product, then double (H4)
         double v = (double)W.Exp[b] / sqrt(1e-15 + (double)prod);
         v = fmax(0.0, v);
@@ -702,9 +723,9 @@ __global__ void __launch_bounds__(kAnaWarps * 32) analysis_kernel(AnalysisArgs A
           A.tap_pitchf[fs * 2 + 1] = gain;
         }
       }
-      if (A.Ex) for (int b = lane; b < kBands; b += 32) A.Ex[fs * kBands + b] = W.Ex[b];
+      if (A.Ex) for (int b = lane; b < kBands; b += L) A.Ex[fs * kBands + b] = W.Ex[b];
     }
-    __syncwarp();
+    __syncwarp(mask);
   }
   if (lane == 0) {
     A.last_period[s] = last_period;
@@ -787,7 +808,7 @@ __global__ void __launch_bounds__(kSynWarps * 32) synthesis_kernel(SynthesisArgs
       const float *frac = B.frac, *omf = B.omf;
       const short *band_of = B.band_of;
       const float *gg = W.g, *rr = W.r, *ir = W.ir;
-      fft960_warp<true>(W.fft, B.ft, lane, [&](int i) {
+      fft960_warp<true, 32>(W.fft, B.ft, lane, 0xffffffffu, [&](int i) {
         int k = i <= kFrame ? i : kWin - i;
         float2 v = make_float2(0.f, 0.f);
         if (k < kBins) {
@@ -867,20 +888,36 @@ __global__ void __launch_bounds__(512) slide_history_kernel(float *pcm, size_t p
 }
 
 // ---------------------------------------------------------------------------------- launchers
-static size_t analysis_smem_bytes() { return ((sizeof(BlockSmem) + 15) / 16) * 16 + kAnaWarps * sizeof(WarpSmem); }
+template <int L>
+static size_t analysis_smem_bytes() {
+  return ((sizeof(BlockSmem) + 15) / 16) * 16 + AnaCfg<L>::kStreamsPerBlock * sizeof(WarpSmem);
+}
+// lanes per stream in the analysis kernel.  32 (a warp per stream) is faster on B200: with 16 (two streams per
+// warp) the serial pitch stretches cost half, but only 8 warps fit per SM and the kernel becomes latency-bound
+// (5.65 ms vs 5.05 ms per step, profiles/bench_history.md).  PNB_ANALYSIS_LANES=16 selects the other variant.
+static int g_ana_lanes = 32;
 static size_t synthesis_smem_bytes() { return ((sizeof(SynBlockSmem) + 15) / 16) * 16 + kSynWarps * sizeof(SynWarpSmem); }
 
 cudaError_t dsp_configure() {
-  cudaError_t e = cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)analysis_smem_bytes());
+  if (const char *v = getenv("PNB_ANALYSIS_LANES")) g_ana_lanes = (atoi(v) == 16) ? 16 : 32;
+  cudaError_t e = cudaFuncSetAttribute(analysis_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)analysis_smem_bytes<32>());
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(analysis_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)analysis_smem_bytes<16>());
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)synthesis_smem_bytes());
 }
 
 int launch_analysis(const AnalysisArgs &a, cudaStream_t st) {
-  dim3 grid((a.n_streams + kAnaWarps - 1) / kAnaWarps);
-  analysis_kernel<<<grid, kAnaWarps * 32, analysis_smem_bytes(), st>>>(a);
+  if (g_ana_lanes == 32) {
+    dim3 grid((a.n_streams + AnaCfg<32>::kStreamsPerBlock - 1) / AnaCfg<32>::kStreamsPerBlock);
+    analysis_kernel<32><<<grid, AnaCfg<32>::kWarps * 32, analysis_smem_bytes<32>(), st>>>(a);
+  } else {
+    dim3 grid((a.n_streams + AnaCfg<16>::kStreamsPerBlock - 1) / AnaCfg<16>::kStreamsPerBlock);
+    analysis_kernel<16><<<grid, AnaCfg<16>::kWarps * 32, analysis_smem_bytes<16>(), st>>>(a);
+  }
   return 1;
 }
 int launch_synthesis(const SynthesisArgs &a, cudaStream_t st) {

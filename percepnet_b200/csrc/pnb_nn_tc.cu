@@ -41,7 +41,7 @@ constexpr int TM = 128;   // streams per tile (UMMA M)
 constexpr int BK = 32;    // k per pipeline stage: 64-byte rows, SWIZZLE_64B
 constexpr int HT = 64;    // hidden units per GRU tile
 constexpr int GRU_BN = 3 * HT;  // weight rows per GRU tile (z|r|n)
-constexpr int DENSE_BN = 128;   // output columns per dense tile
+constexpr int DENSE_BN = 256;   // output columns per dense (conv) tile: the widest MMA, least operand traffic per MAC
 constexpr int kConvTerms = 2;         // bf16 terms per operand on the conv layers (2: 16-bit operands, 3 products)
 constexpr float kActScale = 1024.f;  // fp16 activations are stored x 2^10 (keeps the low term normal)
 
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
   }
 }
 
-constexpr int GRU_STAGES = 7, DENSE_STAGES = 8, SMALL_BN = 48, SMALL_STAGES = 8;
+constexpr int GRU_STAGES = 7, DENSE_STAGES = 6, SMALL_BN = 48, SMALL_STAGES = 8;
 template <int NA, int NB, int BN, int STAGES>
 constexpr size_t tc_smem_bytes() {
   return (size_t)STAGES * StageLayout<NA, NB, BN>::kBytes + (2 * STAGES + 4) * 8 + 16 + 208 * 4 + 1024;
