@@ -455,6 +455,11 @@ static int process_device(pnb_engine *e, const float *d_in, const short *d_in16,
   a.last_period = e->d_last_period; a.last_gain = e->d_last_gain;
   a.tap_pitch = e->d_tap_pitch; a.tap_pitchf = e->d_tap_pitchf;
   { ProfScope ps(e, PNB_K_ANALYSIS, st); n += launch_analysis(a, st); }
+  if (e->flags & PNB_NN_TENSOR) {
+    int k = tc_begin_call(e, F, st);
+    if (k < 0) return k;
+    n += k;
+  }
   for (int t = 0; t < F; t++) {
     if (e->flags & PNB_NN_TENSOR) {
       int k = tc_step(e, t, st);
@@ -634,8 +639,8 @@ extern "C" int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes
 extern "C" long long pnb_launch_count(const pnb_engine *e) { return e ? e->launches : 0; }
 extern "C" int pnb_launches_per_call(const pnb_engine *e, int n_frames) {
   if (!e) return 0;
-  int per_step = (e->flags & PNB_NN_TENSOR) ? tc_launches_per_step(e) : 25;
-  return 4 + per_step * n_frames;
+  if (e->flags & PNB_NN_TENSOR) return 4 + tc_launches_per_call(e) + tc_launches_per_step(e) * n_frames;
+  return 4 + 25 * n_frames;
 }
 extern "C" int pnb_n_streams(const pnb_engine *e) { return e ? e->S : 0; }
 extern "C" int pnb_max_frames(const pnb_engine *e) { return e ? e->Fmax : 0; }

@@ -79,7 +79,9 @@ struct pnb_engine {
 int tc_prepare(pnb_engine *e, const pnb_model *model);
 void tc_release(pnb_engine *e);
 int tc_reset(pnb_engine *e);
+int tc_begin_call(pnb_engine *e, int F, cudaStream_t st);  // hop-parallel front of the network, all F hops
 int tc_step(pnb_engine *e, int t, cudaStream_t st);
+int tc_launches_per_call(const pnb_engine *e);
 int tc_launches_per_step(const pnb_engine *e);
 
 // RAII marker used by the launch schedule: records an event pair around a launch when profiling

@@ -170,6 +170,8 @@ struct TcSeg {
   int k_blocks;      // K / 32
   int a_k0, b_k0;    // starting k (elements) in the A / B matrices
   int recurrent;     // GRU: 0 -> the n rows accumulate W_n x, 1 -> U_n h
+  int a_row0;        // row of the A matrix that holds tile row 0 (hop / tap offset inside a multi-hop buffer)
+  int a_term_rows;   // row distance between the split terms inside this A buffer
 };
 
 struct TcArgs {
@@ -178,7 +180,6 @@ struct TcArgs {
   int n_seg;
   int M;                // streams
   int tiles_m, tiles_n; // tile grid; a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-  int a_term_rows;      // row distance between the split terms inside an activation buffer (= S)
   int b_term_rows;      // row distance between the split terms inside a packed weight matrix
   int fmt;              // 0 fp16, 1 bf16
   float out_scale;      // 2^-(activation scale + weight scale)
@@ -189,8 +190,11 @@ struct TcArgs {
   int N;                // valid output columns
   int ldc;              // row stride of out_f32
   float *out_f32;       // [M][ldc] or null
-  __half *out_h;        // fp16 two-term split [2][M][N] (x 2^10) or null
-  __nv_bfloat16 *out_b; // bf16 three-term split [3][M][N] or null
+  int f32_row0;         // only rows >= f32_row0 are written to out_f32, at row - f32_row0
+  __half *out_h;        // fp16 two-term split [2][out_plane_rows][N] (x 2^10) or null
+  __nv_bfloat16 *out_b; // bf16 split [terms][out_plane_rows][N] or null
+  int out_row0;         // first row written inside a term plane of out_h / out_b
+  int out_plane_rows;   // rows per term plane of out_h / out_b
   // GRU epilogue
   int H;
   const float *h_old;   // [M][H] fp32
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
             uint8_t *sp = stage_base + st * SL::kBytes;
 #pragma unroll
             for (int ta = 0; ta < NA; ta++)
-              tma_load_2d_pair(sp + ta * SL::kABytes, ma, &full_bar[st], sg.a_k0 + kb * BK, ta * args.a_term_rows + m0);
+              tma_load_2d_pair(sp + ta * SL::kABytes, ma, &full_bar[st], sg.a_k0 + kb * BK, ta * sg.a_term_rows + sg.a_row0 + m0);
 #pragma unroll
             for (int tb = 0; tb < NB; tb++)
               tma_load_2d_pair(sp + NA * SL::kABytes + tb * SL::kBBytes, mb, &full_bar[st], sg.b_k0 + kb * BK,
@@ -423,8 +427,8 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
               v[i] = args.act == PNB_ACT_TANH ? tansig_s(x, tbl) : args.act == PNB_ACT_RELU ? (x < 0.f ? 0.f : x)
                    : args.act == PNB_ACT_SIGMOID ? sigmoid_s(x, tbl) : x;
             }
-            if (args.out_f32) {
-              float *op = args.out_f32 + (size_t)row * args.ldc + j0;
+            if (args.out_f32 && row >= args.f32_row0) {
+              float *op = args.out_f32 + (size_t)(row - args.f32_row0) * args.ldc + j0;
               if ((reinterpret_cast<uintptr_t>(op) & 15) == 0 && j0 + 16 <= N) {
                 float4 *o = reinterpret_cast<float4 *>(op);
 #pragma unroll
@@ -432,15 +436,16 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; i++)
-                  if (j0 + i < N) args.out_f32[(size_t)row * args.ldc + j0 + i] = v[i];
+                  if (j0 + i < N) op[i] = v[i];
               }
             }
             if (args.out_h) {
               __align__(16) __half hi[16], lo[16];
 #pragma unroll
               for (int i = 0; i < 16; i++) split_h2(v[i], hi[i], lo[i]);
-              uint4 *ph = reinterpret_cast<uint4 *>(args.out_h + (size_t)row * N + j0);
-              uint4 *pl = reinterpret_cast<uint4 *>(args.out_h + ((size_t)args.M + row) * N + j0);
+              const size_t orow = (size_t)args.out_row0 + row;
+              uint4 *ph = reinterpret_cast<uint4 *>(args.out_h + orow * N + j0);
+              uint4 *pl = reinterpret_cast<uint4 *>(args.out_h + ((size_t)args.out_plane_rows + orow) * N + j0);
               ph[0] = reinterpret_cast<uint4 *>(hi)[0]; ph[1] = reinterpret_cast<uint4 *>(hi)[1];
               pl[0] = reinterpret_cast<uint4 *>(lo)[0]; pl[1] = reinterpret_cast<uint4 *>(lo)[1];
             }
@@ -448,13 +453,14 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
               __align__(16) __nv_bfloat16 t0[16], t1[16], t2[16];
 #pragma unroll
               for (int i = 0; i < 16; i++) split_b3(v[i], t0[i], t1[i], t2[i]);
-              const size_t plane = (size_t)args.M * N;
-              uint4 *p0 = reinterpret_cast<uint4 *>(args.out_b + (size_t)row * N + j0);
-              uint4 *p1 = reinterpret_cast<uint4 *>(args.out_b + plane + (size_t)row * N + j0);
+              const size_t plane = (size_t)args.out_plane_rows * N;
+              const size_t orow = (size_t)args.out_row0 + row;
+              uint4 *p0 = reinterpret_cast<uint4 *>(args.out_b + orow * N + j0);
+              uint4 *p1 = reinterpret_cast<uint4 *>(args.out_b + plane + orow * N + j0);
               p0[0] = reinterpret_cast<uint4 *>(t0)[0]; p0[1] = reinterpret_cast<uint4 *>(t0)[1];
               p1[0] = reinterpret_cast<uint4 *>(t1)[0]; p1[1] = reinterpret_cast<uint4 *>(t1)[1];
               if (kConvTerms == 3) {
-                uint4 *p2 = reinterpret_cast<uint4 *>(args.out_b + 2 * plane + (size_t)row * N + j0);
+                uint4 *p2 = reinterpret_cast<uint4 *>(args.out_b + 2 * plane + orow * N + j0);
                 p2[0] = reinterpret_cast<uint4 *>(t2)[0]; p2[1] = reinterpret_cast<uint4 *>(t2)[1];
               }
             }
@@ -487,7 +493,7 @@ constexpr size_t tc_smem_bytes() {
 // terms conv1 consumes.  One block per 4 streams, one thread per output.
 __global__ void __launch_bounds__(128) fc_split_kernel(const float *__restrict__ feat, const float *__restrict__ W,
                                                        const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out,
-                                                       int M) {
+                                                       int M, size_t plane_rows) {
   __shared__ float f[4][72];
   const int r0 = blockIdx.x * 4;
   for (int i = threadIdx.x; i < 4 * 70; i += blockDim.x) {
@@ -502,7 +508,7 @@ __global__ void __launch_bounds__(128) fc_split_kernel(const float *__restrict__
 #pragma unroll
     for (int rr = 0; rr < 4; rr++) a[rr] = fmaf(w, f[rr][k], a[rr]);
   }
-  const size_t plane = (size_t)M * 128;
+  const size_t plane = plane_rows * 128;
   for (int rr = 0; rr < 4; rr++) {
     if (r0 + rr >= M) break;
     float v = a[rr] < 0.f ? 0.f : a[rr];
@@ -519,9 +525,12 @@ __global__ void __launch_bounds__(128) fc_split_kernel(const float *__restrict__
 // ------------------------------------------------------------------------------------------ host state
 struct pnb_tc_state {
   // split activations
-  __nv_bfloat16 *ring_fc = nullptr;  // [5][3][S][128]
-  __nv_bfloat16 *ring_c1 = nullptr;  // [3][3][S][512]
-  __half *c2_h = nullptr;            // [2][S][512]
+  // Multi-hop buffers: rows are (hop slot, stream).  The conv layers carry no recurrence, so they run once per
+  // call over all F hops (M = F S rows); a tap is the same buffer read `tap` slots later.  Slots 0..3 (0..1) hold
+  // the last hops of the previous call.
+  __nv_bfloat16 *fc_all = nullptr;   // [terms][(Fmax+4) S][128]  fc outputs, bf16 terms
+  __nv_bfloat16 *c1_all = nullptr;   // [terms][(Fmax+2) S][512]  conv1 outputs
+  __half *c2_h = nullptr;            // [2][Fmax S][512]          conv2 outputs, fp16 terms
   __half *h_h[5][2] = {};            // [2][S][H]
   // packed weights
   __nv_bfloat16 *w_conv1 = nullptr, *w_conv2 = nullptr;  // [3][512][K]
@@ -530,7 +539,7 @@ struct pnb_tc_state {
   __half *w_gb = nullptr, *w_rb = nullptr;               // [2][48][2560], [2][48][128] (34 rows used)
   float scale_gb = 0.f, scale_rb = 0.f;
   // tensor maps
-  CUtensorMap m_ring_fc[5], m_ring_c1[3], m_c2, m_h[5][2], m_wconv1, m_wconv2, m_w[5], m_u[5], m_wgb, m_wrb;
+  CUtensorMap m_fc_all, m_c1_all, m_c2, m_h[5][2], m_wconv1, m_wconv2, m_w[5], m_u[5], m_wgb, m_wrb;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -649,9 +658,10 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
   pnb_tc_state *t = new pnb_tc_state();
   e->tc = t;
   const size_t S = e->S;
-  TCK(dev_zeros(&t->ring_fc, 5 * kConvTerms * S * 128));
-  TCK(dev_zeros(&t->ring_c1, 3 * kConvTerms * S * 512));
-  TCK(dev_zeros(&t->c2_h, 2 * S * 512));
+  const size_t Fm = e->Fmax;
+  TCK(dev_zeros(&t->fc_all, kConvTerms * (Fm + 4) * S * 128));
+  TCK(dev_zeros(&t->c1_all, kConvTerms * (Fm + 2) * S * 512));
+  TCK(dev_zeros(&t->c2_h, 2 * Fm * S * 512));
   for (int i = 0; i < 5; i++)
     for (int p = 0; p < 2; p++) TCK(dev_zeros(&t->h_h[i][p], 2 * S * e->gru[i].H));
   {
@@ -689,9 +699,9 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
   int bad = 0;
   bad |= make_map(&t->m_wgb, t->w_gb, false, 2 * SMALL_BN, 2560, SMALL_BN / 2);
   bad |= make_map(&t->m_wrb, t->w_rb, false, 2 * SMALL_BN, 128, SMALL_BN / 2);
-  for (int q = 0; q < 5; q++) bad |= make_map(&t->m_ring_fc[q], t->ring_fc + (size_t)q * kConvTerms * S * 128, true, kConvTerms * S, 128, TM);
-  for (int q = 0; q < 3; q++) bad |= make_map(&t->m_ring_c1[q], t->ring_c1 + (size_t)q * kConvTerms * S * 512, true, kConvTerms * S, 512, TM);
-  bad |= make_map(&t->m_c2, t->c2_h, false, 2 * S, 512, TM);
+  bad |= make_map(&t->m_fc_all, t->fc_all, true, kConvTerms * (Fm + 4) * S, 128, TM);
+  bad |= make_map(&t->m_c1_all, t->c1_all, true, kConvTerms * (Fm + 2) * S, 512, TM);
+  bad |= make_map(&t->m_c2, t->c2_h, false, 2 * Fm * S, 512, TM);
   for (int i = 0; i < 5; i++)
     for (int p = 0; p < 2; p++) bad |= make_map(&t->m_h[i][p], t->h_h[i][p], false, 2 * S, e->gru[i].H, TM);
   bad |= make_map(&t->m_wconv1, t->w_conv1, true, kConvTerms * 512, 640, DENSE_BN / 2);
@@ -714,7 +724,7 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
 void tc_release(pnb_engine *e) {
   pnb_tc_state *t = e->tc;
   if (!t) return;
-  void *ptrs[] = {t->ring_fc, t->ring_c1, t->c2_h, t->w_conv1, t->w_conv2, t->w_gb, t->w_rb};
+  void *ptrs[] = {t->fc_all, t->c1_all, t->c2_h, t->w_conv1, t->w_conv2, t->w_gb, t->w_rb};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 5; i++) {
     for (int p = 0; p < 2; p++) if (t->h_h[i][p]) cudaFree(t->h_h[i][p]);
@@ -729,19 +739,22 @@ int tc_reset(pnb_engine *e) {
   pnb_tc_state *t = e->tc;
   if (!t) return PNB_OK;
   const size_t S = e->S;
-  TCK(cudaMemset(t->ring_fc, 0, 5 * kConvTerms * S * 128 * 2));
-  TCK(cudaMemset(t->ring_c1, 0, 3 * kConvTerms * S * 512 * 2));
-  TCK(cudaMemset(t->c2_h, 0, 2 * S * 512 * 2));
+  const size_t Fm = e->Fmax;
+  TCK(cudaMemset(t->fc_all, 0, kConvTerms * (Fm + 4) * S * 128 * 2));
+  TCK(cudaMemset(t->c1_all, 0, kConvTerms * (Fm + 2) * S * 512 * 2));
+  TCK(cudaMemset(t->c2_h, 0, 2 * Fm * S * 512 * 2));
   for (int i = 0; i < 5; i++)
     for (int p = 0; p < 2; p++) TCK(cudaMemset(t->h_h[i][p], 0, 2 * S * e->gru[i].H * 2));
   return PNB_OK;
 }
 
-int tc_launches_per_step(const pnb_engine *) { return 1 + 2 + 5 + 2; }
+int tc_launches_per_step(const pnb_engine *) { return 5 + 2; }
+int tc_launches_per_call(const pnb_engine *) { return 3; }  // kernels only; the slot carry uses copy engines
 
 template <int NA, int NB, int BN, int STAGES, bool GRU>
-static void tc_launch(pnb_engine *e, TcArgs &a, int tiles_n, cudaStream_t st) {
-  a.tiles_m = (e->S + TM - 1) / TM;
+static void tc_launch(pnb_engine *e, TcArgs &a, int rows, int tiles_n, cudaStream_t st) {
+  a.M = rows;
+  a.tiles_m = (rows + TM - 1) / TM;
   a.tiles_n = tiles_n;
   int pairs = ((a.tiles_m + 1) / 2) * a.tiles_n;
   int clusters = pairs < e->sm_count / 2 ? pairs : e->sm_count / 2;
@@ -759,82 +772,107 @@ static void tc_launch(pnb_engine *e, TcArgs &a, int tiles_n, cudaStream_t st) {
   cudaLaunchKernelEx(&cfg, tc_gemm_kernel<NA, NB, BN, STAGES, GRU>, a);
 }
 
-static TcSeg mkseg(int a_map, int b_map, int K, int a_k0, int b_k0, int rec) {
+static TcSeg mkseg(int a_map, int b_map, int K, int a_k0, int b_k0, int rec, int a_row0, int a_term_rows) {
   TcSeg s;
   s.a_map = a_map; s.b_map = b_map; s.k_blocks = K / BK; s.a_k0 = a_k0; s.b_k0 = b_k0; s.recurrent = rec;
+  s.a_row0 = a_row0; s.a_term_rows = a_term_rows;
   return s;
 }
 
-int tc_step(pnb_engine *e, int tstep, cudaStream_t st) {
+// The non-recurrent front of the network for all F hops of the call at once (rnn.cpp:50-52 on F S rows):
+// fc -> conv1 -> conv2.  Returns the number of launches.
+int tc_begin_call(pnb_engine *e, int F, cudaStream_t st) {
   pnb_tc_state *t = e->tc;
-  const int S = e->S;
-  const long c = e->hop + tstep;
+  const int S = e->S, Fm = e->Fmax;
   const float *tbl = e->tansig();
+  const int rows = F * S;
   int n = 0;
-  // fc (fp32 FMA) -> three bf16 terms into ring slot c % 5
+  // fc (fp32 FMA) for every hop -> bf16 terms at slots 4 .. F+3
   {
     ProfScope ps(e, PNB_K_TC_AUX, st);
-    fc_split_kernel<<<(S + 3) / 4, 128, 0, st>>>(e->d_feat + (size_t)tstep * S * kFeat, e->fc.W, e->fc.b,
-                                                 t->ring_fc + (size_t)(c % 5) * kConvTerms * S * 128, S);
+    fc_split_kernel<<<(rows + 3) / 4, 128, 0, st>>>(e->d_feat, e->fc.W, e->fc.b, t->fc_all + (size_t)4 * S * 128, rows,
+                                                    (size_t)(Fm + 4) * S);
     n++;
   }
   TcArgs a;
-  // conv1: five taps, oldest first (nnet.cpp:182-200)
+  // conv1: tap q of hop t reads fc slot t + q (oldest first, nnet.cpp:182-200); output -> c1 slots 2 .. F+1
   memset(&a, 0, sizeof a);
-  for (int q = 0; q < 5; q++) {
-    a.maps[q] = t->m_ring_fc[((c - 4 + q) % 5 + 5) % 5];
-    a.seg[q] = mkseg(q, 5, 128, 0, q * 128, 0);
-  }
-  a.maps[5] = t->m_wconv1;
-  a.n_seg = 5; a.M = S; a.a_term_rows = S; a.b_term_rows = 512; a.fmt = 1; a.out_scale = 1.f; a.tansig = tbl;
+  a.maps[0] = t->m_fc_all;
+  a.maps[1] = t->m_wconv1;
+  for (int q = 0; q < 5; q++) a.seg[q] = mkseg(0, 1, 128, 0, q * 128, 0, q * S, (Fm + 4) * S);
+  a.n_seg = 5; a.b_term_rows = 512; a.fmt = 1; a.out_scale = 1.f; a.tansig = tbl;
   a.bias = e->conv1.b; a.act = e->act_conv1; a.N = 512;
-  a.out_b = t->ring_c1 + (size_t)(c % 3) * kConvTerms * S * 512;
+  a.out_b = t->c1_all; a.out_row0 = 2 * S; a.out_plane_rows = (Fm + 2) * S;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    tc_launch<kConvTerms, kConvTerms, DENSE_BN, DENSE_STAGES, false>(e, a, 512 / DENSE_BN, st);
+    tc_launch<kConvTerms, kConvTerms, DENSE_BN, DENSE_STAGES, false>(e, a, rows, 512 / DENSE_BN, st);
     n++;
   }
-  // conv2: three taps -> tanh -> fp32 (fc_gb input) and fp16 split (gru1 / gru_rb input)
+  // conv2: three taps -> tanh -> fp16 terms for every hop (gru1 / gru_rb / fc_gb inputs); fp32 copy of the last hop
   memset(&a, 0, sizeof a);
-  for (int q = 0; q < 3; q++) {
-    a.maps[q] = t->m_ring_c1[((c - 2 + q) % 3 + 3) % 3];
-    a.seg[q] = mkseg(q, 3, 512, 0, q * 512, 0);
-  }
-  a.maps[3] = t->m_wconv2;
-  a.n_seg = 3; a.M = S; a.a_term_rows = S; a.b_term_rows = 512; a.fmt = 1; a.out_scale = 1.f; a.tansig = tbl;
-  a.bias = e->conv2.b; a.act = e->act_conv2; a.N = 512; a.out_f32 = e->c2; a.ldc = 512; a.out_h = t->c2_h;
+  a.maps[0] = t->m_c1_all;
+  a.maps[1] = t->m_wconv2;
+  for (int q = 0; q < 3; q++) a.seg[q] = mkseg(0, 1, 512, 0, q * 512, 0, q * S, (Fm + 2) * S);
+  a.n_seg = 3; a.b_term_rows = 512; a.fmt = 1; a.out_scale = 1.f; a.tansig = tbl;
+  a.bias = e->conv2.b; a.act = e->act_conv2; a.N = 512;
+  a.out_f32 = e->c2; a.ldc = 512; a.f32_row0 = (F - 1) * S;
+  a.out_h = t->c2_h; a.out_row0 = 0; a.out_plane_rows = Fm * S;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    tc_launch<kConvTerms, kConvTerms, DENSE_BN, DENSE_STAGES, false>(e, a, 512 / DENSE_BN, st);
+    tc_launch<kConvTerms, kConvTerms, DENSE_BN, DENSE_STAGES, false>(e, a, rows, 512 / DENSE_BN, st);
     n++;
   }
-  // GRUs (rnn.cpp:58-71): each consumes the freshly written state of the layer below
+  // carry the last 4 (2) hop slots to the front for the next call; slot by slot, ascending (ranges may overlap)
+  for (int tm = 0; tm < kConvTerms; tm++) {
+    for (int i = 0; i < 4; i++) {
+      __nv_bfloat16 *base = t->fc_all + (size_t)tm * (Fm + 4) * S * 128;
+      cudaMemcpyAsync(base + (size_t)i * S * 128, base + (size_t)(F + i) * S * 128, (size_t)S * 128 * 2,
+                      cudaMemcpyDeviceToDevice, st);
+    }
+    for (int i = 0; i < 2; i++) {
+      __nv_bfloat16 *base = t->c1_all + (size_t)tm * (Fm + 2) * S * 512;
+      cudaMemcpyAsync(base + (size_t)i * S * 512, base + (size_t)(F + i) * S * 512, (size_t)S * 512 * 2,
+                      cudaMemcpyDeviceToDevice, st);
+    }
+  }
+  return n;
+}
+
+// The recurrent part of one hop: five GRUs and the two output layers (rnn.cpp:58-80).
+int tc_step(pnb_engine *e, int tstep, cudaStream_t st) {
+  pnb_tc_state *t = e->tc;
+  const int S = e->S, Fm = e->Fmax;
+  const float *tbl = e->tansig();
+  int n = 0;
+  TcArgs a;
+  const int c2_row0 = tstep * S, c2_terms = Fm * S;
+  // GRUs: each consumes the freshly written state of the layer below
   for (int li = 0; li < 5; li++) {
     const int H = e->gru[li].H, p = e->par[li];
     memset(&a, 0, sizeof a);
     int ns = 0;
     if (li == 0) {
       a.maps[0] = t->m_c2;
-      a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0);
+      a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0, c2_row0, c2_terms);
     } else if (li < 4) {
       a.maps[0] = t->m_h[li - 1][e->par[li - 1]];
-      a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0);
+      a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0, 0, S);
     } else {  // gru_rb input = [gru3 state, conv2 out]
       a.maps[0] = t->m_h[2][e->par[2]];
       a.maps[4] = t->m_c2;
-      a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0);
-      a.seg[ns++] = mkseg(4, 2, 512, 0, 512, 0);
+      a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0, 0, S);
+      a.seg[ns++] = mkseg(4, 2, 512, 0, 512, 0, c2_row0, c2_terms);
     }
     a.maps[1] = t->m_h[li][p];
     a.maps[2] = t->m_w[li];
     a.maps[3] = t->m_u[li];
-    a.seg[ns++] = mkseg(1, 3, H, 0, 0, 1);
-    a.n_seg = ns; a.M = S; a.a_term_rows = S; a.b_term_rows = (H / HT) * GRU_BN; a.fmt = 0;
+    a.seg[ns++] = mkseg(1, 3, H, 0, 0, 1, 0, S);
+    a.n_seg = ns; a.b_term_rows = (H / HT) * GRU_BN; a.fmt = 0;
     a.out_scale = t->scale_gru[li]; a.tansig = tbl; a.bias = e->gru[li].b; a.H = H;
     a.h_old = e->h[li][p]; a.h_new = e->h[li][p ^ 1]; a.h_new_h = t->h_h[li][p ^ 1];
     {
       ProfScope ps(e, PNB_K_TC_GEMM, st);
-      tc_launch<2, 2, GRU_BN, GRU_STAGES, true>(e, a, H / HT, st);
+      tc_launch<2, 2, GRU_BN, GRU_STAGES, true>(e, a, S, H / HT, st);
       n++;
     }
     e->par[li] ^= 1;
@@ -845,23 +883,24 @@ int tc_step(pnb_engine *e, int tstep, cudaStream_t st) {
   a.maps[0] = t->m_c2;
   for (int q = 0; q < 4; q++) a.maps[1 + q] = t->m_h[q][e->par[q]];
   a.maps[5] = t->m_wgb;
-  for (int q = 0; q < 5; q++) a.seg[q] = mkseg(q, 5, 512, 0, q * 512, 0);
-  a.n_seg = 5; a.M = S; a.a_term_rows = S; a.b_term_rows = SMALL_BN; a.fmt = 0; a.out_scale = t->scale_gb; a.tansig = tbl;
+  a.seg[0] = mkseg(0, 5, 512, 0, 0, 0, c2_row0, c2_terms);
+  for (int q = 1; q < 5; q++) a.seg[q] = mkseg(q, 5, 512, 0, q * 512, 0, 0, S);
+  a.n_seg = 5; a.b_term_rows = SMALL_BN; a.fmt = 0; a.out_scale = t->scale_gb; a.tansig = tbl;
   a.bias = e->fc_gb.b; a.act = e->act_gb; a.N = 34; a.ldc = 68; a.out_f32 = gr;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    tc_launch<2, 2, SMALL_BN, SMALL_STAGES, false>(e, a, 1, st);
+    tc_launch<2, 2, SMALL_BN, SMALL_STAGES, false>(e, a, S, 1, st);
     n++;
   }
   memset(&a, 0, sizeof a);
   a.maps[0] = t->m_h[4][e->par[4]];
   a.maps[1] = t->m_wrb;
-  a.seg[0] = mkseg(0, 1, 128, 0, 0, 0);
-  a.n_seg = 1; a.M = S; a.a_term_rows = S; a.b_term_rows = SMALL_BN; a.fmt = 0; a.out_scale = t->scale_rb; a.tansig = tbl;
+  a.seg[0] = mkseg(0, 1, 128, 0, 0, 0, 0, S);
+  a.n_seg = 1; a.b_term_rows = SMALL_BN; a.fmt = 0; a.out_scale = t->scale_rb; a.tansig = tbl;
   a.bias = e->fc_rb.b; a.act = e->act_rb; a.N = 34; a.ldc = 68; a.out_f32 = gr + 34;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    tc_launch<2, 2, SMALL_BN, SMALL_STAGES, false>(e, a, 1, st);
+    tc_launch<2, 2, SMALL_BN, SMALL_STAGES, false>(e, a, S, 1, st);
     n++;
   }
   return n;
