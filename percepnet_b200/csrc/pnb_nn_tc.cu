@@ -217,17 +217,6 @@ template <> struct Products<2, 2> {
   __device__ static constexpr int a(int i) { return i == 2 ? 1 : 0; }
   __device__ static constexpr int b(int i) { return i == 1 ? 1 : 0; }
 };
-template <> struct Products<3, 3> {
-  static constexpr int n = 6;
-  __device__ static constexpr int a(int i) { return i == 0 ? 0 : i == 1 ? 0 : i == 2 ? 1 : i == 3 ? 0 : i == 4 ? 1 : 2; }
-  __device__ static constexpr int b(int i) { return i == 0 ? 0 : i == 1 ? 1 : i == 2 ? 0 : i == 3 ? 2 : i == 4 ? 1 : 0; }
-};
-template <> struct Products<3, 2> {  // a = a0 + a1 + a2 (24 bits), b = b0 + b1 (16 bits): all products >= 2^-16
-  static constexpr int n = 5;
-  __device__ static constexpr int a(int i) { return i == 0 ? 0 : i == 1 ? 0 : i == 2 ? 1 : i == 3 ? 1 : 2; }
-  __device__ static constexpr int b(int i) { return i == 0 ? 0 : i == 1 ? 1 : i == 2 ? 0 : i == 3 ? 1 : 0; }
-};
-
 __device__ __forceinline__ void split_h2(float v, __half &hi, __half &lo) {
   // fp16 operands hold |x| < 64 (x 2^10 < 65504).  GRU inputs are tanh / state values in [-1, 1]; only when
   // the reference's own tansig_approx leaves its defined domain (|pre-activation| >= 8.6e7, see tests) does

@@ -87,3 +87,33 @@ def test_tensor_path_batch_independence(api, model0):
     o_s, g_s = small.process(base, want_gr=True)
     small.close()
     assert np.array_equal(o_s, out[:8]) and np.array_equal(g_s, gr[:, :8])
+
+
+def test_tensor_path_long_run_no_drift(api, oracle, model0):
+    """Three seconds of audio (300 hops): the split-operand arithmetic feeds five recurrent layers, so check that
+    the error against the oracle does not grow with time (first vs last third of the run)."""
+    from percepnet_b200.synth import synth_pcm
+    F = 300
+    x = synth_pcm(3, F, seed=77)
+    ref_out, ref_gr, _ = _oracle_run(oracle, model0, x)
+    eng = api.Engine(3, 16, model0, api.NN_TENSOR)
+    out, gr = eng.process_stream_chunks(x, want_gr=True)
+    eng.close()
+    rel = np.abs(gr - ref_gr) / np.maximum(np.abs(ref_gr), 1e-6)
+    first, last = rel[:100].max(), rel[200:].max()
+    print(f"g/r max rel err: hops 0-99 {first:.2e}, hops 200-299 {last:.2e}")
+    assert rel.max() < GR_RTOL
+    assert last < 4 * max(first, 2e-6)
+    assert _lsb_diff(out, ref_out, True) <= PCM_LSB
+
+
+def test_tensor_path_single_hop_calls_and_odd_batch(api, oracle, model0):
+    """F = 1 per call (the latency-minimal way to drive the engine) on a batch that is not a multiple of anything."""
+    x = _inputs(1.0, 12, n_synth=5)[:7]
+    ref_out, ref_gr, _ = _oracle_run(oracle, model0, x)
+    eng = api.Engine(7, 1, model0, api.NN_TENSOR)
+    out, gr = eng.process_stream_chunks(x, want_gr=True)
+    eng.close()
+    rel = np.abs(gr - ref_gr) / np.maximum(np.abs(ref_gr), 1e-6)
+    assert rel.max() < GR_RTOL
+    assert _lsb_diff(out, ref_out, True) <= PCM_LSB
