@@ -469,6 +469,11 @@ static int process_device(pnb_engine *e, const float *d_in, const short *d_in16,
       n += nn_step_f32(e, t, st);
     }
   }
+  if (e->flags & PNB_NN_TENSOR) {
+    int k = tc_end_call(e, F, st);
+    if (k < 0) return k;
+    n += k;
+  }
   SynthesisArgs s;
   s.zring = e->d_zring; s.ring = e->ring; s.hop0 = e->hop; s.P = e->d_P; s.gr = e->d_gr; s.Ex = e->d_Ex; s.silence = e->d_sil; s.n_streams = S; s.n_frames = F;
   s.tab = e->d_tab; s.synth_mem = e->d_synth; s.out = d_out; s.out16 = d_out16; s.out_stride = out_stride;

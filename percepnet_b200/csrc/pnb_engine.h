@@ -81,6 +81,7 @@ void tc_release(pnb_engine *e);
 int tc_reset(pnb_engine *e);
 int tc_begin_call(pnb_engine *e, int F, cudaStream_t st);  // hop-parallel front of the network, all F hops
 int tc_step(pnb_engine *e, int t, cudaStream_t st);
+int tc_end_call(pnb_engine *e, int F, cudaStream_t st);    // hop-parallel tail: the two output layers, state carry
 int tc_launches_per_call(const pnb_engine *e);
 int tc_launches_per_step(const pnb_engine *e);
 

@@ -199,7 +199,7 @@ struct TcArgs {
   int H;
   const float *h_old;   // [M][H] fp32
   float *h_new;         // [M][H] fp32
-  __half *h_new_h;      // [2][M][H] fp16 split (x 2^10)
+  __half *h_new_h;      // fp16 split of the new state (x 2^10): [2][out_plane_rows][H], first row out_row0
 };
 
 template <int NA, int NB, int BN>
@@ -396,8 +396,9 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
             __align__(16) __half hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) split_h2(hn[i], hi[i], lo[i]);
-            uint4 *ph = reinterpret_cast<uint4 *>(args.h_new_h + (size_t)row * H + j0);
-            uint4 *pl = reinterpret_cast<uint4 *>(args.h_new_h + ((size_t)args.M + row) * H + j0);
+            const size_t orow = (size_t)args.out_row0 + row;
+            uint4 *ph = reinterpret_cast<uint4 *>(args.h_new_h + orow * H + j0);
+            uint4 *pl = reinterpret_cast<uint4 *>(args.h_new_h + ((size_t)args.out_plane_rows + orow) * H + j0);
             ph[0] = reinterpret_cast<uint4 *>(hi)[0]; ph[1] = reinterpret_cast<uint4 *>(hi)[1];
             pl[0] = reinterpret_cast<uint4 *>(lo)[0]; pl[1] = reinterpret_cast<uint4 *>(lo)[1];
           }
@@ -520,7 +521,8 @@ struct pnb_tc_state {
   __nv_bfloat16 *fc_all = nullptr;   // [terms][(Fmax+4) S][128]  fc outputs, bf16 terms
   __nv_bfloat16 *c1_all = nullptr;   // [terms][(Fmax+2) S][512]  conv1 outputs
   __half *c2_h = nullptr;            // [2][Fmax S][512]          conv2 outputs, fp16 terms
-  __half *h_h[5][2] = {};            // [2][S][H]
+  __half *h_all[5] = {};             // [2][(Fmax+1) S][H]        GRU states as fp16 terms, slot t+1 = after hop t,
+                                     //                           slot 0 = carried from the previous call
   // packed weights
   __nv_bfloat16 *w_conv1 = nullptr, *w_conv2 = nullptr;  // [3][512][K]
   __half *w_gru[5] = {}, *u_gru[5] = {};                 // [2][tiles*192][K]
@@ -528,7 +530,7 @@ struct pnb_tc_state {
   __half *w_gb = nullptr, *w_rb = nullptr;               // [2][48][2560], [2][48][128] (34 rows used)
   float scale_gb = 0.f, scale_rb = 0.f;
   // tensor maps
-  CUtensorMap m_fc_all, m_c1_all, m_c2, m_h[5][2], m_wconv1, m_wconv2, m_w[5], m_u[5], m_wgb, m_wrb;
+  CUtensorMap m_fc_all, m_c1_all, m_c2, m_h[5], m_wconv1, m_wconv2, m_w[5], m_u[5], m_wgb, m_wrb;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -651,8 +653,7 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
   TCK(dev_zeros(&t->fc_all, kConvTerms * (Fm + 4) * S * 128));
   TCK(dev_zeros(&t->c1_all, kConvTerms * (Fm + 2) * S * 512));
   TCK(dev_zeros(&t->c2_h, 2 * Fm * S * 512));
-  for (int i = 0; i < 5; i++)
-    for (int p = 0; p < 2; p++) TCK(dev_zeros(&t->h_h[i][p], 2 * S * e->gru[i].H));
+  for (int i = 0; i < 5; i++) TCK(dev_zeros(&t->h_all[i], 2 * (Fm + 1) * S * e->gru[i].H));
   {
     std::vector<__nv_bfloat16> p;
     pack_dense_b3(model->conv1->input_weights, 640, 512, p);
@@ -692,7 +693,7 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
   bad |= make_map(&t->m_c1_all, t->c1_all, true, kConvTerms * (Fm + 2) * S, 512, TM);
   bad |= make_map(&t->m_c2, t->c2_h, false, 2 * Fm * S, 512, TM);
   for (int i = 0; i < 5; i++)
-    for (int p = 0; p < 2; p++) bad |= make_map(&t->m_h[i][p], t->h_h[i][p], false, 2 * S, e->gru[i].H, TM);
+    bad |= make_map(&t->m_h[i], t->h_all[i], false, 2 * (Fm + 1) * S, e->gru[i].H, TM);
   bad |= make_map(&t->m_wconv1, t->w_conv1, true, kConvTerms * 512, 640, DENSE_BN / 2);
   bad |= make_map(&t->m_wconv2, t->w_conv2, true, kConvTerms * 512, 1536, DENSE_BN / 2);
   for (int i = 0; i < 5; i++) {
@@ -716,7 +717,7 @@ void tc_release(pnb_engine *e) {
   void *ptrs[] = {t->fc_all, t->c1_all, t->c2_h, t->w_conv1, t->w_conv2, t->w_gb, t->w_rb};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 5; i++) {
-    for (int p = 0; p < 2; p++) if (t->h_h[i][p]) cudaFree(t->h_h[i][p]);
+    if (t->h_all[i]) cudaFree(t->h_all[i]);
     if (t->w_gru[i]) cudaFree(t->w_gru[i]);
     if (t->u_gru[i]) cudaFree(t->u_gru[i]);
   }
@@ -732,13 +733,12 @@ int tc_reset(pnb_engine *e) {
   TCK(cudaMemset(t->fc_all, 0, kConvTerms * (Fm + 4) * S * 128 * 2));
   TCK(cudaMemset(t->c1_all, 0, kConvTerms * (Fm + 2) * S * 512 * 2));
   TCK(cudaMemset(t->c2_h, 0, 2 * Fm * S * 512 * 2));
-  for (int i = 0; i < 5; i++)
-    for (int p = 0; p < 2; p++) TCK(cudaMemset(t->h_h[i][p], 0, 2 * S * e->gru[i].H * 2));
+  for (int i = 0; i < 5; i++) TCK(cudaMemset(t->h_all[i], 0, 2 * (Fm + 1) * S * e->gru[i].H * 2));
   return PNB_OK;
 }
 
-int tc_launches_per_step(const pnb_engine *) { return 5 + 2; }
-int tc_launches_per_call(const pnb_engine *) { return 3; }  // kernels only; the slot carry uses copy engines
+int tc_launches_per_step(const pnb_engine *) { return 5; }
+int tc_launches_per_call(const pnb_engine *) { return 3 + 2; }  // kernels only; the slot carry uses copy engines
 
 template <int NA, int NB, int BN, int STAGES, bool GRU>
 static void tc_launch(pnb_engine *e, TcArgs &a, int rows, int tiles_n, cudaStream_t st) {
@@ -827,7 +827,7 @@ int tc_begin_call(pnb_engine *e, int F, cudaStream_t st) {
   return n;
 }
 
-// The recurrent part of one hop: five GRUs and the two output layers (rnn.cpp:58-80).
+// The recurrent part of one hop: the five GRUs (rnn.cpp:58-71).  State slot t holds the state BEFORE hop t.
 int tc_step(pnb_engine *e, int tstep, cudaStream_t st) {
   pnb_tc_state *t = e->tc;
   const int S = e->S, Fm = e->Fmax;
@@ -835,7 +835,8 @@ int tc_step(pnb_engine *e, int tstep, cudaStream_t st) {
   int n = 0;
   TcArgs a;
   const int c2_row0 = tstep * S, c2_terms = Fm * S;
-  // GRUs: each consumes the freshly written state of the layer below
+  const int h_terms = (Fm + 1) * S, h_prev = tstep * S, h_next = (tstep + 1) * S;
+  // each GRU consumes the freshly written state (slot t+1) of the layer below and its own previous state (slot t)
   for (int li = 0; li < 5; li++) {
     const int H = e->gru[li].H, p = e->par[li];
     memset(&a, 0, sizeof a);
@@ -844,21 +845,22 @@ int tc_step(pnb_engine *e, int tstep, cudaStream_t st) {
       a.maps[0] = t->m_c2;
       a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0, c2_row0, c2_terms);
     } else if (li < 4) {
-      a.maps[0] = t->m_h[li - 1][e->par[li - 1]];
-      a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0, 0, S);
+      a.maps[0] = t->m_h[li - 1];
+      a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0, h_next, h_terms);
     } else {  // gru_rb input = [gru3 state, conv2 out]
-      a.maps[0] = t->m_h[2][e->par[2]];
+      a.maps[0] = t->m_h[2];
       a.maps[4] = t->m_c2;
-      a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0, 0, S);
+      a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0, h_next, h_terms);
       a.seg[ns++] = mkseg(4, 2, 512, 0, 512, 0, c2_row0, c2_terms);
     }
-    a.maps[1] = t->m_h[li][p];
+    a.maps[1] = t->m_h[li];
     a.maps[2] = t->m_w[li];
     a.maps[3] = t->m_u[li];
-    a.seg[ns++] = mkseg(1, 3, H, 0, 0, 1, 0, S);
+    a.seg[ns++] = mkseg(1, 3, H, 0, 0, 1, h_prev, h_terms);
     a.n_seg = ns; a.b_term_rows = (H / HT) * GRU_BN; a.fmt = 0;
     a.out_scale = t->scale_gru[li]; a.tansig = tbl; a.bias = e->gru[li].b; a.H = H;
-    a.h_old = e->h[li][p]; a.h_new = e->h[li][p ^ 1]; a.h_new_h = t->h_h[li][p ^ 1];
+    a.h_old = e->h[li][p]; a.h_new = e->h[li][p ^ 1];
+    a.h_new_h = t->h_all[li]; a.out_row0 = h_next; a.out_plane_rows = h_terms;
     {
       ProfScope ps(e, PNB_K_TC_GEMM, st);
       tc_launch<2, 2, GRU_BN, GRU_STAGES, true>(e, a, S, H / HT, st);
@@ -866,31 +868,48 @@ int tc_step(pnb_engine *e, int tstep, cudaStream_t st) {
     }
     e->par[li] ^= 1;
   }
-  // the two 34-wide output layers (rnn.cpp:73-80): N padded to 48, fp16 two-term split, sigmoid epilogue
-  float *gr = e->d_gr + (size_t)tstep * S * 68;
+  return n;
+}
+
+// The two 34-wide output layers for all F hops at once (rnn.cpp:73-80; N padded to 48, fp16 two-term split,
+// sigmoid epilogue), then the carry of the last state slot to slot 0 for the next call.
+int tc_end_call(pnb_engine *e, int F, cudaStream_t st) {
+  pnb_tc_state *t = e->tc;
+  const int S = e->S, Fm = e->Fmax;
+  const float *tbl = e->tansig();
+  const int rows = F * S, h_terms = (Fm + 1) * S;
+  int n = 0;
+  TcArgs a;
   memset(&a, 0, sizeof a);
   a.maps[0] = t->m_c2;
-  for (int q = 0; q < 4; q++) a.maps[1 + q] = t->m_h[q][e->par[q]];
+  for (int q = 0; q < 4; q++) a.maps[1 + q] = t->m_h[q];
   a.maps[5] = t->m_wgb;
-  a.seg[0] = mkseg(0, 5, 512, 0, 0, 0, c2_row0, c2_terms);
-  for (int q = 1; q < 5; q++) a.seg[q] = mkseg(q, 5, 512, 0, q * 512, 0, 0, S);
+  a.seg[0] = mkseg(0, 5, 512, 0, 0, 0, 0, Fm * S);
+  for (int q = 1; q < 5; q++) a.seg[q] = mkseg(q, 5, 512, 0, q * 512, 0, S, h_terms);  // state after hop t = slot t+1
   a.n_seg = 5; a.b_term_rows = SMALL_BN; a.fmt = 0; a.out_scale = t->scale_gb; a.tansig = tbl;
-  a.bias = e->fc_gb.b; a.act = e->act_gb; a.N = 34; a.ldc = 68; a.out_f32 = gr;
+  a.bias = e->fc_gb.b; a.act = e->act_gb; a.N = 34; a.ldc = 68; a.out_f32 = e->d_gr;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    tc_launch<2, 2, SMALL_BN, SMALL_STAGES, false>(e, a, S, 1, st);
+    tc_launch<2, 2, SMALL_BN, SMALL_STAGES, false>(e, a, rows, 1, st);
     n++;
   }
   memset(&a, 0, sizeof a);
-  a.maps[0] = t->m_h[4][e->par[4]];
+  a.maps[0] = t->m_h[4];
   a.maps[1] = t->m_wrb;
-  a.seg[0] = mkseg(0, 1, 128, 0, 0, 0, 0, S);
+  a.seg[0] = mkseg(0, 1, 128, 0, 0, 0, S, h_terms);
   a.n_seg = 1; a.b_term_rows = SMALL_BN; a.fmt = 0; a.out_scale = t->scale_rb; a.tansig = tbl;
-  a.bias = e->fc_rb.b; a.act = e->act_rb; a.N = 34; a.ldc = 68; a.out_f32 = gr + 34;
+  a.bias = e->fc_rb.b; a.act = e->act_rb; a.N = 34; a.ldc = 68; a.out_f32 = e->d_gr + 34;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    tc_launch<2, 2, SMALL_BN, SMALL_STAGES, false>(e, a, S, 1, st);
+    tc_launch<2, 2, SMALL_BN, SMALL_STAGES, false>(e, a, rows, 1, st);
     n++;
+  }
+  for (int li = 0; li < 5; li++) {
+    const size_t H = e->gru[li].H;
+    for (int tm = 0; tm < 2; tm++) {
+      __half *base = t->h_all[li] + (size_t)tm * h_terms * H;
+      cudaMemcpyAsync(base, base + (size_t)F * S * H, (size_t)S * H * 2, cudaMemcpyDeviceToDevice, st);
+    }
   }
   return n;
 }
