@@ -11,9 +11,9 @@ is config 2.  One JSON line on stdout (rank 0).
 
   value    whole-job frames/s with the input PCM already resident in HBM (device-pointer entry),
            timed with CUDA events on the launching stream, max over ranks
-  e2e      the same metric through the public host-buffer call (Engine.process == pnb_process_host_f32)
-           from pinned host memory: H2D of the step's PCM + compute + D2H of the enhanced PCM inside
-           the timed region
+  e2e      the same metric through the public pipelined host call (Engine.submit/wait ==
+           pnb_submit_host_i16 + pnb_wait): int16 PCM in pinned host memory -> H2D -> hot path -> D2H ->
+           int16 PCM in pinned host memory, every step, inside the timed region (host clock)
   roofline the dominant kernel (the network contraction) against the measured tensor peak
   cpu_baseline  the reference's CPU path timed on this box's host cores on a bounded sample
 
@@ -282,8 +282,15 @@ def main():
         flops_per_launch = S * F * FLOP_PER_FRAME / nn_n       # algorithmic flops of the step / contraction launches
         achieved = flops_per_launch / (nn_ms / nn_n * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if nn_mode == "tensor" and os.path.exists(tp):   # dram__bytes_read+write of the dominant instance, from the last ncu capture
+            tj = json.load(open(tp)).get(nn_cls, {})
+            if tj:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         roof = {"bound": "tensor", "kernel": nn_cls, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "DRAM bytes of one GRU-512 launch (ncu, profiles/ncu_traffic.json); the kernel is tensor/L2-bound, DRAM is at 9 % of peak", "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
                 "launches_per_step": nn_n, "avg_launch_ms": nn_ms / nn_n,
                 "share_of_step": nn_ms / step_ms_prof if step_ms_prof else None,
                 "pipe": "tcgen05 split-fp16 (3 MMA per product)" if nn_mode == "tensor" else "fp32 FMA (CUDA cores)",
