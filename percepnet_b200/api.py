@@ -40,6 +40,9 @@ def load_library() -> C.CDLL:
     L = C.CDLL(LIB_PATH)
     vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
     L.pnb_create.argtypes = [C.POINTER(vp), i, i, vp, C.c_uint, i]
+    L.pnb_model_load_blob.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.pnb_model_free.argtypes = [vp]
+    L.pnb_model_free.restype = None
     L.pnb_destroy.argtypes = [vp]
     L.pnb_destroy.restype = None
     L.pnb_reset.argtypes = [vp]
@@ -67,18 +70,35 @@ def load_library() -> C.CDLL:
 
 
 EXPORTS = ("pnb_create", "pnb_destroy", "pnb_reset", "pnb_process_host_f32", "pnb_process_host_i16",
-           "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_wait",
+           "pnb_model_load_blob", "pnb_model_free", "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_wait",
            "pnb_read_tap", "pnb_launch_count",
            "pnb_launches_per_call", "pnb_profile_enable", "pnb_profile_read", "pnb_kernel_class_name", "pnb_n_streams", "pnb_max_frames", "pnb_last_error", "pnb_version")
 
 
+class BlobModel:
+    """A model read from a binary weight file by the C loader (pnb_model_load_blob)."""
+
+    def __init__(self, path: str):
+        self.L = load_library()
+        self.ptr = C.c_void_p()
+        rc = self.L.pnb_model_load_blob(path.encode(), C.byref(self.ptr))
+        if rc != 0:
+            raise PnbError(f"pnb_model_load_blob failed ({rc}): {self.L.pnb_last_error().decode()}")
+
+    def free(self):
+        if self.ptr:
+            self.L.pnb_model_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
 class Engine:
-    def __init__(self, n_streams: int, max_frames: int, model: PackedModel, flags: int = NN_FP32, device: int = 0):
+    def __init__(self, n_streams: int, max_frames: int, model, flags: int = NN_FP32, device: int = 0):
         self.L = load_library()
         self.n_streams, self.max_frames, self.flags, self.device = n_streams, max_frames, flags, device
         self._model = model
         h = C.c_void_p()
-        rc = self.L.pnb_create(C.byref(h), n_streams, max_frames, C.addressof(model.as_c_model()), flags, device)
+        mptr = model.ptr if isinstance(model, BlobModel) else C.addressof(model.as_c_model())
+        rc = self.L.pnb_create(C.byref(h), n_streams, max_frames, mptr, flags, device)
         if rc != 0:
             raise PnbError(f"pnb_create failed ({rc}): {self.L.pnb_last_error().decode()}")
         self.h = h

@@ -641,6 +641,72 @@ extern "C" int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes
   return PNB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// binary weight file -> pnb_model (layout of the generated nnet_data.cpp)
+// ------------------------------------------------------------------------------------------
+namespace {
+struct BlobModel {
+  pnb_model m;
+  pnb_dense_layer fc, fc_gb, fc_rb;
+  pnb_conv1d_layer conv1, conv2;
+  pnb_gru_layer gru[5];
+  std::vector<std::vector<float>> arrays;
+};
+bool read_array(FILE *f, size_t expect, std::vector<float> &dst) {
+  unsigned long long n = 0;
+  if (fread(&n, 8, 1, f) != 1 || n != expect) return false;
+  dst.resize(n);
+  return fread(dst.data(), 4, n, f) == n;
+}
+}  // namespace
+
+extern "C" int pnb_model_load_blob(const char *path, pnb_model **out) {
+  if (!path || !out) return fail(PNB_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  FILE *f = fopen(path, "rb");
+  if (!f) return fail(PNB_ERR_ARG, "cannot open %s", path);
+  char magic[8];
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "PNBW0001", 8) != 0) { fclose(f); return fail(PNB_ERR_ARG, "%s is not a PNBW0001 weight file", path); }
+  BlobModel *b = new BlobModel();
+  b->arrays.resize(25);
+  int ai = 0;
+  bool ok = true;
+  auto dense = [&](pnb_dense_layer &l, int M, int N, int act) {
+    ok = ok && read_array(f, (size_t)M * N, b->arrays[ai]) && read_array(f, N, b->arrays[ai + 1]);
+    l.input_weights = b->arrays[ai].data(); l.bias = b->arrays[ai + 1].data(); l.nb_inputs = M; l.nb_neurons = N; l.activation = act;
+    ai += 2;
+  };
+  auto conv = [&](pnb_conv1d_layer &l, int C, int K, int N, int act) {
+    ok = ok && read_array(f, (size_t)C * K * N, b->arrays[ai]) && read_array(f, N, b->arrays[ai + 1]);
+    l.input_weights = b->arrays[ai].data(); l.bias = b->arrays[ai + 1].data(); l.nb_inputs = C; l.kernel_size = K; l.nb_neurons = N; l.activation = act;
+    ai += 2;
+  };
+  auto gru = [&](pnb_gru_layer &l, int M, int H) {
+    ok = ok && read_array(f, (size_t)M * 3 * H, b->arrays[ai]) && read_array(f, (size_t)H * 3 * H, b->arrays[ai + 1]) &&
+         read_array(f, 6 * (size_t)H, b->arrays[ai + 2]);
+    l.input_weights = b->arrays[ai].data(); l.recurrent_weights = b->arrays[ai + 1].data(); l.bias = b->arrays[ai + 2].data();
+    l.nb_inputs = M; l.nb_neurons = H; l.activation = PNB_ACT_TANH; l.reset_after = 1;
+    ai += 3;
+  };
+  dense(b->fc, 70, 128, PNB_ACT_RELU);
+  conv(b->conv1, 128, 5, 512, PNB_ACT_RELU);
+  conv(b->conv2, 512, 3, 512, PNB_ACT_TANH);
+  for (int i = 0; i < 4; i++) gru(b->gru[i], 512, 512);
+  gru(b->gru[4], 1024, 128);
+  dense(b->fc_gb, 2560, 34, PNB_ACT_SIGMOID);
+  dense(b->fc_rb, 128, 34, PNB_ACT_SIGMOID);
+  fclose(f);
+  if (!ok) { delete b; return fail(PNB_ERR_ARG, "%s is truncated or has unexpected layer sizes", path); }
+  b->m.fc = &b->fc; b->m.conv1 = &b->conv1; b->m.conv2 = &b->conv2;
+  b->m.gru1 = &b->gru[0]; b->m.gru2 = &b->gru[1]; b->m.gru3 = &b->gru[2]; b->m.gru_gb = &b->gru[3]; b->m.gru_rb = &b->gru[4];
+  b->m.fc_gb = &b->fc_gb; b->m.fc_rb = &b->fc_rb;
+  *out = &b->m;  // first member: the BlobModel is recovered from the pointer in pnb_model_free
+  return PNB_OK;
+}
+extern "C" void pnb_model_free(pnb_model *m) {
+  if (m) delete reinterpret_cast<BlobModel *>(m);
+}
+
 extern "C" long long pnb_launch_count(const pnb_engine *e) { return e ? e->launches : 0; }
 extern "C" int pnb_launches_per_call(const pnb_engine *e, int n_frames) {
   if (!e) return 0;

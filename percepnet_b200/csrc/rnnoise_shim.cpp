@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "../../include/percepnet_b200.h"
 
@@ -25,6 +26,30 @@ struct DenoiseState { // opaque to callers (rnnoise.h:49)
 };
 
 extern const RNNModel percepnet_model_orig __attribute__((weak));
+
+// Declared by the reference (src/rnnoise.h:62-64) but defined nowhere in it: here they read the
+// binary weight file of pnb_model_load_blob, so a host can run without compiling nnet_data.cpp.
+RNNModel *rnnoise_model_from_file(FILE *f) {
+  if (!f) return NULL;
+  // the C-ABI loader takes a path; copy the stream to a temporary file so that any FILE* works
+  char tmpl[] = "/tmp/pnb_model_XXXXXX";
+  int fd = mkstemp(tmpl);
+  if (fd < 0) return NULL;
+  FILE *t = fdopen(fd, "wb");
+  char buf[1 << 16];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof buf, f)) > 0) fwrite(buf, 1, n, t);
+  fclose(t);
+  pnb_model *m = NULL;
+  int rc = pnb_model_load_blob(tmpl, &m);
+  remove(tmpl);
+  if (rc != PNB_OK) {
+    fprintf(stderr, "rnnoise_model_from_file: %s\n", pnb_last_error());
+    return NULL;
+  }
+  return reinterpret_cast<RNNModel *>(m);
+}
+void rnnoise_model_free(RNNModel *model) { pnb_model_free(reinterpret_cast<pnb_model *>(model)); }
 
 int rnnoise_get_size() { return (int)sizeof(DenoiseState); }
 

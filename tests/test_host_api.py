@@ -84,3 +84,30 @@ def test_synthetic_weights_are_reproducible(model0):
     assert synth_model(1).digest() != model0.digest()
     w = model0.arrays["gru1_weights"]
     assert w.shape == (512, 1536) and abs(float(w.std()) - (1 / np.sqrt(512)) / np.sqrt(3)) < 1e-3
+
+
+def test_weight_blob_roundtrip(built, model0, tmp_path):
+    """f4: PackedModel.save_blob -> pnb_model_load_blob gives back the same arrays in the RNNModel layout; a
+    truncated or foreign file is refused."""
+    from percepnet_b200 import api
+    from percepnet_b200.weights import ModelC
+    path = str(tmp_path / "w.pnbw")
+    model0.save_blob(path)
+    assert os.path.getsize(path) < 33_000_000
+    bm = api.BlobModel(path)
+    m = C.cast(bm.ptr, C.POINTER(ModelC)).contents
+    ref = model0.as_c_model()
+    for name, n in (("fc", 70 * 128), ("conv2", 3 * 512 * 512), ("fc_gb", 2560 * 34)):
+        a = np.ctypeslib.as_array(getattr(m, name).contents.input_weights, (n,))
+        b = np.ctypeslib.as_array(getattr(ref, name).contents.input_weights, (n,))
+        assert np.array_equal(a, b)
+    g = m.gru_rb.contents
+    assert (g.nb_inputs, g.nb_neurons, g.reset_after) == (1024, 128, 1)
+    assert np.array_equal(np.ctypeslib.as_array(g.recurrent_weights, (128 * 384,)), model0.arrays["gru_rb_recurrent_weights"].ravel())
+    assert np.array_equal(np.ctypeslib.as_array(g.bias, (768,)), model0.arrays["gru_rb_bias"])
+    bm.free()
+    open(path, "r+b").truncate(1_000_000)
+    with pytest.raises(api.PnbError):
+        api.BlobModel(path)
+    out = subprocess.run(["nm", "-D", "--defined-only", built.SHIM], capture_output=True, text=True, check=True).stdout
+    assert "_Z23rnnoise_model_from_fileP8_IO_FILE" in out and "_Z18rnnoise_model_freeP8RNNModel" in out
