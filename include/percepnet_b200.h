@@ -57,7 +57,9 @@ enum {
   PNB_NN_FP32 = 0,       /* network contraction in fp32 FMA (BASELINE.json config 2)                  */
   PNB_NN_TENSOR = 1,     /* network contraction on tcgen05 tensor cores, split-fp16 operands, fp32 accumulate */
   PNB_POSTFILTER = 2,    /* apply the envelope post-filter (src/denoise.cpp:216-250) to g; off in the reference */
-  PNB_KEEP_TAPS = 4      /* keep per-frame intermediates of the last call readable through pnb_read_tap    */
+  PNB_KEEP_TAPS = 4,     /* keep per-frame intermediates of the last call readable through pnb_read_tap    */
+  PNB_TRAIN_DATA = 8     /* training-data generator (pnb_train_records_*): n_streams = 2 x pairs, no network,
+                            no synthesis; model may be NULL; the pnb_process_* entry points are refused      */
 };
 
 typedef struct pnb_engine pnb_engine;
@@ -102,6 +104,21 @@ int pnb_process_device_f32(pnb_engine *e, const float *d_in, size_t in_stride, f
 int pnb_process_device_i16(pnb_engine *e, const short *d_in, size_t in_stride, short *d_out, size_t out_stride,
                            int n_frames, float *d_gr, void *cuda_stream);
 
+/* Training-data generator: the per-frame loop of the reference's train() (src/denoise.cpp:600-787, as shipped:
+ * gains fixed at 1, no biquads, the second file is the finished noisy mixture, TEST defined so g is post-filtered).
+ * The engine must have been created with PNB_TRAIN_DATA and n_streams = 2 x n_pairs.  speech/noisy hold n_pairs
+ * rows of int16 PCM (row strides in samples); for pair p and frame t of the call the 138 floats
+ *   Ey_lookahead[34] Ephaty[34] T pitchcorr g[34] r[34]                      (src/denoise.cpp:761-773)
+ * are written to records + p*records_stride + t*138 -- a row is what train() writes to its <output> file for that
+ * pair of files.  State carries over between calls, so a long pair of files can be fed in chunks of at most
+ * max_frames_per_call frames.  The test_input.pcm / test_output.pcm debug audio of train() is not produced. */
+#define PNB_RECORD_FLOATS 138
+int pnb_train_records_host(pnb_engine *e, const short *speech, size_t speech_stride, const short *noisy,
+                           size_t noisy_stride, int n_frames, float *records, size_t records_stride);
+int pnb_train_records_device(pnb_engine *e, const short *d_speech, size_t speech_stride, const short *d_noisy,
+                             size_t noisy_stride, int n_frames, float *d_records, size_t records_stride,
+                             void *cuda_stream);
+
 /* Per-frame intermediates of the LAST call (requires PNB_KEEP_TAPS); copies to host memory.
  * Layouts are [n_frames][n_streams][...]:                                                   */
 enum {
@@ -123,7 +140,8 @@ int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes);
  * milliseconds and launch counts per class since the last read (arrays of PNB_NUM_KERNEL_CLASSES). */
 enum {
   PNB_K_STAGE_IN = 0, PNB_K_ANALYSIS = 1, PNB_K_FC = 2, PNB_K_GEMM_F32 = 3, PNB_K_GRU_GATES = 4,
-  PNB_K_SYNTHESIS = 5, PNB_K_SLIDE = 6, PNB_K_TC_GEMM = 7, PNB_K_TC_AUX = 8, PNB_NUM_KERNEL_CLASSES = 9
+  PNB_K_SYNTHESIS = 5, PNB_K_SLIDE = 6, PNB_K_TC_GEMM = 7, PNB_K_TC_AUX = 8, PNB_K_LABELS = 9,
+  PNB_NUM_KERNEL_CLASSES = 10
 };
 int pnb_profile_enable(pnb_engine *e, int on);
 int pnb_profile_read(pnb_engine *e, double *ms, long long *counts);

@@ -72,6 +72,25 @@ class Oracle:
         L.pn_oracle_remove_doubling.restype = C.c_float
         L.pn_oracle_remove_doubling.argtypes = [F32P, I32P, C.c_int, C.c_float]
 
+    # -- training-data path (row f1) ----------------------------------------------------
+    def train_records(self, speech16, noisy16):
+        """[count*480] int16 each -> [count, 138] float32 (train(), denoise.cpp:600-787)."""
+        speech16 = np.ascontiguousarray(speech16, np.int16)
+        noisy16 = np.ascontiguousarray(noisy16, np.int16)
+        count = speech16.size // 480
+        rec = np.empty((count, 138), np.float32)
+        self.lib.pn_oracle_train_records.argtypes = [I16P, I16P, C.c_int, F32P]
+        self.lib.pn_oracle_train_records(speech16.ctypes.data_as(I16P), noisy16.ctypes.data_as(I16P), count,
+                                         rec.ctypes.data_as(F32P))
+        return rec
+
+    def ideal_labels(self, Ex, Ey, Exp, Ephaty):
+        a = [np.ascontiguousarray(v, np.float32) for v in (Ex, Ey, Exp, Ephaty)]
+        g, r = np.empty(34, np.float32), np.empty(34, np.float32)
+        self.lib.pn_oracle_ideal_labels.argtypes = [F32P] * 6
+        self.lib.pn_oracle_ideal_labels(*[v.ctypes.data_as(F32P) for v in a + [g, r]])
+        return g, r
+
     # -- engine -------------------------------------------------------------------------
     def create(self, model):
         self._model = model  # keep the weight arrays alive
@@ -251,6 +270,11 @@ class Reference:
         L.ref_process_streams_omp.argtypes = [C.c_int, C.c_int, F32P, F32P, C.c_int]
         L.ref_remove_doubling.restype = C.c_float
         L.ref_remove_doubling.argtypes = [F32P, I32P, C.c_int, C.c_float]
+
+    def train_files(self, speech_path, noisy_path, count, out_path):
+        """The reference's own train() (denoise.cpp:600) on files."""
+        self.lib.ref_train_files.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p]
+        return self.lib.ref_train_files(speech_path.encode(), noisy_path.encode(), count, out_path.encode())
 
     def set_model(self, model):
         self._model = model

@@ -653,11 +653,19 @@ void pn_oracle_reset(pn_oracle *o) {
   o->model = m;
 }
 
-void pn_oracle_process_frame(pn_oracle *o, float *out, const float *in, pn_oracle_taps *tp, int flags) {
+/* compute_frame_features (denoise.cpp:364-434) followed by compute_lookahead_band_energy (:498-506): everything
+ * the enhancement path and the training-data path share. */
+typedef struct {
   cpx X[NFREQ], P[NFREQ], Y[NFREQ];
-  float Ex[NB], Ep[NB], Exp[NB], Ey[NB], feat[PNO_FEATURES], g[NB], r[NB], gbin[NFREQ];
-  float buf[WIN], lp[864], corr, gain, E = 0;
-  int i, k, pitch, T, silence;
+  float Ex[NB], Ep[NB], Exp[NB], Ey[NB], lp[864], corr, gain;
+  int pitch, T, silence;
+} frame_analysis;
+
+static void analyse_frame(pn_oracle *o, const float *in, frame_analysis *a, pn_oracle_taps *tp) {
+  cpx *X = a->X, *P = a->P, *Y = a->Y;
+  float *Ex = a->Ex, *Ep = a->Ep, *Exp = a->Exp, *Ey = a->Ey, *lp = a->lp;
+  float buf[WIN], corr, gain, E = 0;
+  int i, k, pitch, T;
 
   /* slide the history line and append the new hop (denoise.cpp:388-389) */
   memmove(o->hist, o->hist + FRAME, (PNO_HIST - FRAME) * sizeof(float));
@@ -673,7 +681,6 @@ void pn_oracle_process_frame(pn_oracle *o, float *out, const float *in, pn_oracl
   pn_oracle_pitch_downsample(o->hist + 1632, lp);
   pn_oracle_pitch_search(lp, &pitch, &corr, tp ? tp->xcorr_coarse : NULL, tp ? tp->best_coarse : NULL);
   T = 768 - pitch;
-  if (tp) tp->pitch_search = pitch;
   gain = pn_oracle_remove_doubling(lp, &T, o->last_period, o->last_gain);
   o->last_period = T;
   o->last_gain = gain;
@@ -692,13 +699,26 @@ void pn_oracle_process_frame(pn_oracle *o, float *out, const float *in, pn_oracl
     Exp[i] = (float)fmin(1, v);
   }
   for (i = 0; i < NB; i++) E += Ex[i];
-  silence = E < 0.1; /* float promoted to double against the double literal, :433 */
+  a->silence = E < 0.1; /* float promoted to double against the double literal, :433 */
 
   /* look-ahead band energies from the newest 960 samples (denoise.cpp:498-506) */
   memcpy(buf, o->hist + PNO_HIST - WIN, sizeof buf);
   window_inplace(buf);
   spectrum_of(buf, Y);
   band_pool(Ey, Y, Y);
+  a->corr = corr; a->gain = gain; a->pitch = pitch; a->T = T;
+}
+
+void pn_oracle_process_frame(pn_oracle *o, float *out, const float *in, pn_oracle_taps *tp, int flags) {
+  frame_analysis fa;
+  cpx *X = fa.X, *P = fa.P, *Y = fa.Y;
+  float *Ex = fa.Ex, *Ep = fa.Ep, *Exp = fa.Exp, *Ey = fa.Ey, *lp = fa.lp;
+  float feat[PNO_FEATURES], g[NB], r[NB], gbin[NFREQ], buf[WIN], corr, gain;
+  int i, T, silence;
+
+  analyse_frame(o, in, &fa, tp);
+  corr = fa.corr; gain = fa.gain; T = fa.T; silence = fa.silence;
+  if (tp) tp->pitch_search = fa.pitch;
 
   /* features (denoise.cpp:487-496, 528-530) */
   for (i = 0; i < NB; i++) feat[i] = Ey[i] * 30;
@@ -709,10 +729,10 @@ void pn_oracle_process_frame(pn_oracle *o, float *out, const float *in, pn_oracl
   pn_oracle_compute_rnn(o->model, o->nn, g, r, feat);
 
   if (tp) {
-    memcpy(tp->X, X, sizeof X); memcpy(tp->P, P, sizeof P); memcpy(tp->Y, Y, sizeof Y);
-    memcpy(tp->Ex, Ex, sizeof Ex); memcpy(tp->Ep, Ep, sizeof Ep); memcpy(tp->Exp, Exp, sizeof Exp);
-    memcpy(tp->Ex_look, Ey, sizeof Ey); memcpy(tp->features, feat, sizeof feat);
-    memcpy(tp->g, g, sizeof g); memcpy(tp->r, r, sizeof r); memcpy(tp->lp, lp, sizeof lp);
+    memcpy(tp->X, X, sizeof fa.X); memcpy(tp->P, P, sizeof fa.P); memcpy(tp->Y, Y, sizeof fa.Y);
+    memcpy(tp->Ex, Ex, sizeof fa.Ex); memcpy(tp->Ep, Ep, sizeof fa.Ep); memcpy(tp->Exp, Exp, sizeof fa.Exp);
+    memcpy(tp->Ex_look, Ey, sizeof fa.Ey); memcpy(tp->features, feat, sizeof feat);
+    memcpy(tp->g, g, sizeof g); memcpy(tp->r, r, sizeof r); memcpy(tp->lp, lp, sizeof fa.lp);
     tp->pitch_corr = corr; tp->pitch_index = T; tp->pitch_gain = gain; tp->silence = silence;
   }
 
@@ -722,13 +742,75 @@ void pn_oracle_process_frame(pn_oracle *o, float *out, const float *in, pn_oracl
   if (!silence) comb_mix(X, P, r);  /* denoise.cpp:536-538 */
   band_to_bins(gbin, g);            /* :539 */
   for (i = 0; i < NFREQ; i++) { X[i].r *= gbin[i]; X[i].i *= gbin[i]; }
-  if (tp) memcpy(tp->Xout, X, sizeof X);
+  if (tp) memcpy(tp->Xout, X, sizeof fa.X);
 
   /* synthesis: inverse transform, window, overlap-add (denoise.cpp:352-359) */
   signal_of(X, buf);
   window_inplace(buf);
   for (i = 0; i < FRAME; i++) out[i] = buf[i] + o->synth_mem[i];
   memcpy(o->synth_mem, buf + FRAME, FRAME * sizeof(float));
+}
+
+/* ------------------------------------------------------------------------------------ */
+/*  Training-data path: the labels of denoise.cpp:549-589 and the      */
+/*  per-frame record of train() (denoise.cpp:600-787, as shipped: gains fixed at 1, no      */
+/*  biquads, the second file is the already-mixed noisy signal).  denoise.cpp is C++, so    */
+/*  sqrt() of a float expression is the float overload; of a double expression, double.     */
+/* ------------------------------------------------------------------------------------ */
+void pn_oracle_ideal_labels(const float *Ex, const float *Ey, const float *Exp, const float *Ephaty, float *g, float *r) {
+  float pna = 0, n0 = (float)0.03, Ephatp[NB];
+  int i;
+  build_tables();
+  for (i = 0; i < 7; i++) pna += K.comb_w[i] * K.comb_w[i];                 /* denoise.cpp:207-210 */
+  for (i = 0; i < NB; i++) {                                                /* calc_ideal_gain, :571-577 */
+    g[i] = (float)(Ex[i] / (.0001 + Ey[i]));
+    if (g[i] > 1) g[i] = 1;
+    if (g[i] < 0) g[i] = 0;
+  }
+  for (i = 0; i < NB; i++)                                                  /* estimate_phat_corr, :549-553 */
+    Ephatp[i] = (float)(Ephaty[i] / sqrt((1 - pna) * pow(Ephaty[i], 2) + pna));
+  for (i = 0; i < NB; i++) {                                                /* filter_strength_calc, :555-569 */
+    float a, b, c, alpha, q = Ephaty[i];
+    a = Ephatp[i] * Ephatp[i] - Exp[i] * Exp[i];
+    if (a < 0) a = 0;
+    b = Ephatp[i] * q * (1 - Exp[i] * Exp[i]);
+    c = Exp[i] * Exp[i] - q * q;
+    if (c < 0) c = 0;
+    alpha = (float)((sqrtf(b * b + a * c) - b) / (a + 1e-8));
+    r[i] = alpha / (1 + alpha);
+  }
+  for (i = 0; i < NB; i++)                                                  /* adjust_gain_strength_by_condition, :579-589 */
+    if (Ephatp[i] < Exp[i]) {
+      float g_att = sqrtf((1 + n0 - Exp[i] * Exp[i]) / (1 + n0 - Ephatp[i] * Ephatp[i]));
+      r[i] = (float)0.99;
+      g[i] *= g_att;
+    }
+}
+
+/* train() on in-memory files: speech/noisy hold count*480 int16 samples each (no wrap-around);
+ * records gets count*138 floats: Ey_lookahead[34] Ephaty[34] T pitchcorr g[34] r[34] (denoise.cpp:761-773). */
+void pn_oracle_train_records(const short *speech, const short *noisy, int count, float *records) {
+  pn_oracle *st = pn_oracle_create(NULL), *ns = pn_oracle_create(NULL);
+  frame_analysis *fx = (frame_analysis *)malloc(sizeof *fx), *fy = (frame_analysis *)malloc(sizeof *fy);
+  float x[FRAME], xn[FRAME];
+  int t, i;
+  for (t = 0; t < count; t++) {
+    float *rec = records + (size_t)t * 138;
+    for (i = 0; i < FRAME; i++) x[i] = (float)speech[(size_t)t * FRAME + i];  /* NORM_RATIO 1, speech_gain 1 */
+    for (i = 0; i < FRAME; i++) xn[i] = (float)noisy[(size_t)t * FRAME + i];
+    analyse_frame(ns, xn, fy, NULL);
+    analyse_frame(st, x, fx, NULL);
+    memcpy(rec, fy->Ey, NB * sizeof(float));
+    memcpy(rec + NB, fy->Exp, NB * sizeof(float));
+    rec[68] = (float)ns->last_period / (768 - 3 * 60);
+    rec[69] = fy->corr;
+    pn_oracle_ideal_labels(fx->Ex, fy->Ex, fx->Exp, fy->Exp, rec + 70, rec + 104);
+    /* denoise.cpp:45-46 defines TEST, so the shipped train() post-filters g in place (:742-743) before it is
+     * written; the rest of the TEST block (test_input.pcm / test_output.pcm debug audio) does not touch the record. */
+    pn_oracle_post_filter(rec + 70, fy->Ex);
+  }
+  free(fx); free(fy);
+  pn_oracle_destroy(st); pn_oracle_destroy(ns);
 }
 
 void pn_oracle_process_stream(pn_oracle *o, float *out, const float *in, int n_frames, float *gr, int flags) {

@@ -71,6 +71,12 @@ void pn_oracle_run_pcm16(const pnb_model *m, const short *in16, int n_frames, sh
 void pn_oracle_process_streams(const pnb_model *m, int n_streams, int n_frames, const float *in, float *out,
                                int n_threads, int flags);
 
+/* ---- training-data path (row f1): train() of denoise.cpp:600-787 on in-memory int16 "files" ---- */
+#define PNO_RECORD 138 /* Ey_lookahead[34] Ephaty[34] T pitchcorr g[34] r[34], denoise.cpp:761-773 */
+void pn_oracle_train_records(const short *speech, const short *noisy, int count, float *records);
+/* labels of denoise.cpp:549-589 from clean (Ex, Exp) and noisy (Ey, Ephaty) band statistics */
+void pn_oracle_ideal_labels(const float *Ex, const float *Ey, const float *Exp, const float *Ephaty, float *g, float *r);
+
 /* ---- stage-level entry points (each pinned against the reference's function) ---- */
 void pn_oracle_erb_borders(int *out34);                                   /* erbband.h:34-99         */
 void pn_oracle_tables(float *half_window480, float *comb_window7);        /* denoise.cpp:186-214     */

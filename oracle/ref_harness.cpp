@@ -21,6 +21,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include <vector>
 
 #include "rnnoise.h"   /* reference: pulls nnet_data.h / nnet.h */
@@ -61,6 +62,8 @@ static void put_gru(GRULayer &d, const pnb_gru_layer *s) {
   d.nb_inputs = s->nb_inputs; d.nb_neurons = s->nb_neurons; d.activation = s->activation;
   d.reset_after = s->reset_after;
 }
+
+int train(int argc, char **argv); /* denoise.cpp:600 */
 
 extern "C" {
 
@@ -215,6 +218,26 @@ void ref_compute_rnn(float *state, float *gains, float *strengths, const float *
   r.gb_gru_state = r.gru3_state + 512;
   r.rb_gru_state = r.gb_gru_state + 512;
   compute_rnn(&r, gains, strengths, features);
+}
+
+/* The reference's training-data generator, denoise.cpp:600 (non-static, compiled into every build of
+ * denoise.cpp): <speech.pcm> <noisy.pcm> <count> <out.f32>. */
+int ref_train_files(const char *speech, const char *noisy, int count, const char *out) {
+  char cnt[32];
+  snprintf(cnt, sizeof cnt, "%d", count);
+  char *argv[5] = {(char *)"percepNet", (char *)speech, (char *)noisy, cnt, (char *)out};
+  /* train() also drops test_input.pcm / test_output.pcm into the working directory (TEST is defined at
+   * denoise.cpp:45-46): run it from the directory of the output file (all paths must be absolute). */
+  char cwd[4096], dir[4096];
+  if (!getcwd(cwd, sizeof cwd)) return -1;
+  snprintf(dir, sizeof dir, "%s", out);
+  char *slash = strrchr(dir, '/');
+  if (!slash) return -1;
+  *slash = 0;
+  if (chdir(dir) != 0) return -1;
+  int rc = train(5, argv);
+  if (chdir(cwd) != 0) return -1;
+  return rc;
 }
 
 } /* extern "C" */

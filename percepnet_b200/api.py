@@ -18,7 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpercepnet_b200.so")
 
 FRAME = 480
-NN_FP32, NN_TENSOR, POSTFILTER, KEEP_TAPS = 0, 1, 2, 4
+NN_FP32, NN_TENSOR, POSTFILTER, KEEP_TAPS, TRAIN_DATA = 0, 1, 2, 4, 8
+RECORD = 138
 TAPS = {"features": (0, np.float32, 70), "pitch": (1, np.int32, 4), "pitchf": (2, np.float32, 2),
         "X": (3, np.float32, 800), "P": (4, np.float32, 800), "Ex": (5, np.float32, 34), "gr": (6, np.float32, 68)}
 
@@ -43,6 +44,8 @@ def load_library() -> C.CDLL:
     L.pnb_model_load_blob.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.pnb_model_free.argtypes = [vp]
     L.pnb_model_free.restype = None
+    L.pnb_train_records_host.argtypes = [vp, vp, sz, vp, sz, i, vp, sz]
+    L.pnb_train_records_device.argtypes = [vp, vp, sz, vp, sz, i, vp, sz, vp]
     L.pnb_destroy.argtypes = [vp]
     L.pnb_destroy.restype = None
     L.pnb_reset.argtypes = [vp]
@@ -70,7 +73,7 @@ def load_library() -> C.CDLL:
 
 
 EXPORTS = ("pnb_create", "pnb_destroy", "pnb_reset", "pnb_process_host_f32", "pnb_process_host_i16",
-           "pnb_model_load_blob", "pnb_model_free", "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_wait",
+           "pnb_model_load_blob", "pnb_model_free", "pnb_train_records_host", "pnb_train_records_device", "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_wait",
            "pnb_read_tap", "pnb_launch_count",
            "pnb_launches_per_call", "pnb_profile_enable", "pnb_profile_read", "pnb_kernel_class_name", "pnb_n_streams", "pnb_max_frames", "pnb_last_error", "pnb_version")
 
@@ -97,7 +100,7 @@ class Engine:
         self.n_streams, self.max_frames, self.flags, self.device = n_streams, max_frames, flags, device
         self._model = model
         h = C.c_void_p()
-        mptr = model.ptr if isinstance(model, BlobModel) else C.addressof(model.as_c_model())
+        mptr = None if model is None else (model.ptr if isinstance(model, BlobModel) else C.addressof(model.as_c_model()))
         rc = self.L.pnb_create(C.byref(h), n_streams, max_frames, mptr, flags, device)
         if rc != 0:
             raise PnbError(f"pnb_create failed ({rc}): {self.L.pnb_last_error().decode()}")
@@ -184,12 +187,31 @@ class Engine:
             out[name] = a
         return out
 
+    def train_records(self, speech: np.ndarray, noisy: np.ndarray) -> np.ndarray:
+        """speech, noisy: [n_pairs, F*480] int16 -> [n_pairs, F, 138] float32, the records the reference's train()
+        (src/denoise.cpp:600-787) writes for each pair of files.  Engine must have flags=TRAIN_DATA and
+        n_streams = 2*n_pairs; state carries over, so call repeatedly with consecutive chunks."""
+        N = self.n_streams // 2
+        assert speech.shape == noisy.shape and speech.shape[0] == N and speech.shape[1] % FRAME == 0
+        assert speech.dtype == np.int16 and noisy.dtype == np.int16
+        F = speech.shape[1] // FRAME
+        speech, noisy = np.ascontiguousarray(speech), np.ascontiguousarray(noisy)
+        rec = np.empty((N, F, RECORD), np.float32)
+        self._ck(self.L.pnb_train_records_host(self.h, speech.ctypes.data, speech.shape[1], noisy.ctypes.data,
+                                               noisy.shape[1], F, rec.ctypes.data, F * RECORD), "pnb_train_records_host")
+        return rec
+
+    def train_records_device(self, d_speech: int, speech_stride: int, d_noisy: int, noisy_stride: int, n_frames: int,
+                             d_records: int, records_stride: int, stream: int = 0):
+        self._ck(self.L.pnb_train_records_device(self.h, d_speech, speech_stride, d_noisy, noisy_stride, n_frames,
+                                                 d_records, records_stride, stream), "pnb_train_records_device")
+
     def profile(self, on: bool):
         self._ck(self.L.pnb_profile_enable(self.h, 1 if on else 0), "pnb_profile_enable")
 
     def profile_read(self) -> dict:
         """{kernel class name: (total ms, launches)} since the last read; waits for the device."""
-        n = 9
+        n = 10
         ms = (C.c_double * n)()
         cnt = (C.c_longlong * n)()
         self._ck(self.L.pnb_profile_read(self.h, ms, cnt), "pnb_profile_read")

@@ -678,10 +678,10 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
         float v = p * w;
         return make_float2((1.f / kWin) * v, 0.f);
       });
-      float2 *Pg = A.P + fs * kBins;
+      float2 *Pg = A.P ? A.P + fs * kBins : nullptr;
       for (int k = lane; k < kBins; k += L) {
         float2 p = W.fft[fpos(k)];
-        Pg[k] = p;
+        if (Pg) Pg[k] = p;
         float e = p.x * p.x;
         e += p.y * p.y;
         W.xc[k] = B.frac[k] * e;
@@ -708,6 +708,10 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
         float coh = (float)fmin(1.0, v);
         F[b] = W.Ey[b] * 30.f;
         F[kBands + b] = coh * 30.f;
+        if (A.raw) {
+          A.raw[fs * 68 + b] = W.Ey[b];
+          A.raw[fs * 68 + kBands + b] = coh;
+        }
       }
       if (lane == 0) {
         float E = 0.f;
@@ -857,13 +861,13 @@ __global__ void __launch_bounds__(kSynWarps * 32) synthesis_kernel(SynthesisArgs
 // staging: append the new hops to each stream's PCM line / slide the history forward
 // ------------------------------------------------------------------------------------------
 __global__ void stage_in_kernel(float *pcm, size_t pcm_stride, const float *in, const short *in16, size_t in_stride,
-                                int n_streams, int n_samples) {
+                                int n_streams, int n_samples, float i16_div) {
   const int s = blockIdx.y;
   float *dst = pcm + (size_t)s * pcm_stride + kKeep;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_samples; i += gridDim.x * blockDim.x) {
     float v;
     if (in) v = in[(size_t)s * in_stride + i];
-    else v = ((float)in16[(size_t)s * in_stride + i]) / 32768.f;  // main.cpp:34
+    else v = ((float)in16[(size_t)s * in_stride + i]) / i16_div;  // main.cpp:34 (32768) / denoise.cpp:681 (NORM_RATIO 1)
     dst[i] = v;
   }
 }
@@ -920,15 +924,84 @@ int launch_analysis(const AnalysisArgs &a, cudaStream_t st) {
   }
   return 1;
 }
+// ------------------------------------------------------------------------------------------
+// Training-data labels.  One warp per (frame, pair); lane b and b+32 own a band.
+// Follows the reference's mixed float/double arithmetic literally (denoise.cpp is C++: sqrt of a float
+// expression is sqrtf, of a double expression sqrt); this file is compiled with -fmad=false.
+//   calc_ideal_gain :571-577, estimate_phat_corr :549-553, filter_strength_calc :555-569,
+//   adjust_gain_strength_by_condition :579-589, post_filtering :216-250 (applied in train() because
+//   denoise.cpp:45-46 defines TEST), record layout :761-773.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) train_labels_kernel(LabelArgs A) {
+  __shared__ float sh_g[8][kBands], sh_gw[8][kBands];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long wid = (long)blockIdx.x * 8 + wib;
+  const long total = (long)A.n_frames * A.n_pairs;
+  if (wid >= total) return;
+  const int t = (int)(wid / A.n_pairs), p = (int)(wid % A.n_pairs);
+  const int S = 2 * A.n_pairs;
+  const size_t fn = (size_t)t * S + p, fc = fn + A.n_pairs;   // noisy / clean rows of hop t
+  float *rec = A.records + (size_t)p * A.pair_stride + (size_t)t * 138;
+  const float *Ey = A.Ex + fn * kBands;
+  float pna = 0.f;                                            // denoise.cpp:207-210
+  for (int i = 0; i < 7; i++) pna += A.tab->comb_w[i] * A.tab->comb_w[i];
+  const float n0 = (float)0.03;
+  for (int b = lane; b < kBands; b += 32) {
+    const float ex = A.Ex[fc * kBands + b], ey = Ey[b];
+    const float exp_c = A.raw[fc * 68 + kBands + b], q = A.raw[fn * 68 + kBands + b];
+    rec[b] = A.raw[fn * 68 + b];
+    rec[kBands + b] = q;
+    float g = (float)((double)ex / (.0001 + (double)ey));
+    if (g > 1.f) g = 1.f;
+    if (g < 0.f) g = 0.f;
+    const float ephatp = (float)((double)q / sqrt((double)(1.f - pna) * ((double)q * (double)q) + (double)pna));
+    float a = ephatp * ephatp - exp_c * exp_c;
+    if (a < 0.f) a = 0.f;
+    const float bb = ephatp * q * (1.f - exp_c * exp_c);
+    float c = exp_c * exp_c - q * q;
+    if (c < 0.f) c = 0.f;
+    const float alpha = (float)((double)(sqrtf(bb * bb + a * c) - bb) / ((double)a + 1e-8));
+    float r = alpha / (1.f + alpha);
+    if (ephatp < exp_c) {
+      const float g_att = sqrtf((1.f + n0 - exp_c * exp_c) / (1.f + n0 - ephatp * ephatp));
+      r = (float)0.99;
+      g *= g_att;
+    }
+    rec[104 + b] = r;
+    sh_g[wib][b] = g;
+    // sinf of the reference's libm is correctly rounded in all but rare cases; so is the rounded double sine
+    sh_gw[wib][b] = g * (float)sin((double)(float)(M_PI / 2 * (double)g));
+  }
+  __syncwarp();
+  float G = 0.f;
+  if (lane == 0) {
+    float e0 = 0.f, e1 = 0.f;
+    for (int b = 0; b < kBands; b++) e0 += sh_g[wib][b] * Ey[b];
+    for (int b = 0; b < kBands; b++) e1 += sh_gw[wib][b] * Ey[b];
+    const float qq = e0 / (e1 + 1e-6f);
+    G = sqrtf(((1.f + 0.02f) * qq) / (1.f + 0.02f * (qq * qq)));
+    rec[68] = A.feat[fn * kFeat + 68];
+    rec[69] = A.feat[fn * kFeat + 69];
+  }
+  G = __shfl_sync(0xffffffffu, G, 0);
+  for (int b = lane; b < kBands; b += 32) rec[70 + b] = G * sh_gw[wib][b];
+}
+
+int launch_train_labels(const LabelArgs &a, cudaStream_t st) {
+  const long total = (long)a.n_frames * a.n_pairs;
+  train_labels_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(a);
+  return 1;
+}
+
 int launch_synthesis(const SynthesisArgs &a, cudaStream_t st) {
   dim3 grid((a.n_streams + kSynWarps - 1) / kSynWarps);
   synthesis_kernel<<<grid, kSynWarps * 32, synthesis_smem_bytes(), st>>>(a);
   return 1;
 }
 int launch_stage_in(float *pcm, size_t pcm_stride, const float *in, const short *in16, size_t in_stride,
-                    int n_streams, int n_samples, cudaStream_t st) {
+                    int n_streams, int n_samples, cudaStream_t st, float i16_div) {
   dim3 grid((n_samples + 1023) / 1024 > 8 ? 8 : (n_samples + 1023) / 1024, n_streams);
-  stage_in_kernel<<<grid, 256, 0, st>>>(pcm, pcm_stride, in, in16, in_stride, n_streams, n_samples);
+  stage_in_kernel<<<grid, 256, 0, st>>>(pcm, pcm_stride, in, in16, in_stride, n_streams, n_samples, i16_div);
   return 1;
 }
 int launch_slide_history(float *pcm, size_t pcm_stride, int n_streams, int n_samples, cudaStream_t st) {

@@ -134,7 +134,11 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
   if (!out) return fail(PNB_ERR_ARG, "out is NULL");
   *out = nullptr;
   if (n_streams < 1 || max_frames < 1) return fail(PNB_ERR_ARG, "n_streams and max_frames_per_call must be >= 1");
-  int rc = check_model(model);
+  const bool train_mode = (flags & PNB_TRAIN_DATA) != 0;
+  if (train_mode && (n_streams & 1)) return fail(PNB_ERR_ARG, "PNB_TRAIN_DATA needs n_streams = 2 x pairs");
+  if (train_mode && (flags & (PNB_NN_TENSOR | PNB_POSTFILTER)))
+    return fail(PNB_ERR_ARG, "PNB_TRAIN_DATA runs no network: combine it only with PNB_KEEP_TAPS");
+  int rc = train_mode ? 0 : check_model(model);
   if (rc) return rc;
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -177,6 +181,7 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
     CKD(r);
   }
   // weights, in the reference's layout
+  if (!train_mode) {
   CKD(upload(&e->fc.W, model->fc->input_weights, 70 * 128));
   CKD(upload(&e->fc.b, model->fc->bias, 128));
   CKD(upload(&e->conv1.W, model->conv1->input_weights, 5 * 128 * 512));
@@ -201,6 +206,7 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
   e->act_conv2 = model->conv2->activation;
   e->act_gb = model->fc_gb->activation;
   e->act_rb = model->fc_rb->activation;
+  }
 
   // stream state
   e->pcm_stride = kKeep + F * kFrame;
@@ -213,13 +219,19 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
   e->ring = (int)F + 5;
   CKD(dalloc(&e->d_zring, (size_t)e->ring * S * kBins));
   CKD(dalloc(&e->d_ering, (size_t)e->ring * S * kBands));
-  CKD(dalloc(&e->d_P, F * S * kBins));
+  if (!train_mode) CKD(dalloc(&e->d_P, F * S * kBins));
   CKD(dalloc(&e->d_Ex, F * S * kBands));
   CKD(dalloc(&e->d_sil, F * S));
-  CKD(dalloc(&e->d_gr, F * S * 68));
+  if (!train_mode) CKD(dalloc(&e->d_gr, F * S * 68));
+  if (train_mode) CKD(dalloc(&e->d_raw, F * S * 68));
   if (flags & PNB_KEEP_TAPS) {
     CKD(dalloc(&e->d_tap_pitch, F * S * 4));
     CKD(dalloc(&e->d_tap_pitchf, F * S * 2));
+  }
+  if (train_mode) {
+    CKD(cudaDeviceSynchronize());
+    *out = e;
+    return PNB_OK;
   }
   // network state and scratch
   CKD(dalloc(&e->ring_fc, 5 * S * 128));
@@ -246,7 +258,8 @@ extern "C" void pnb_destroy(pnb_engine *e) {
   tc_release(e);
   float *fl[] = {e->fc.W, e->fc.b, e->conv1.W, e->conv1.b, e->conv2.W, e->conv2.b, e->fc_gb.W, e->fc_gb.b,
                  e->fc_rb.W, e->fc_rb.b, e->d_pcm, e->d_synth, e->d_last_gain, e->d_feat, e->d_Ex, e->d_gr,
-                 e->d_tap_pitchf, e->ring_fc, e->ring_c1, e->c2, e->zr, e->nx, e->nh, e->d_hin, e->d_hout};
+                 e->d_tap_pitchf, e->ring_fc, e->ring_c1, e->c2, e->zr, e->nx, e->nh, e->d_hin, e->d_hout,
+                 e->d_raw, e->d_records};
   for (float *p : fl) if (p) cudaFree(p);
   for (int i = 0; i < 5; i++) {
     if (e->gru[i].W) cudaFree(e->gru[i].W);
@@ -289,12 +302,16 @@ extern "C" int pnb_reset(pnb_engine *e) {
   CK(cudaMemset(e->d_ering, 0, (size_t)e->ring * S * kBands * sizeof(float)));
   CK(cudaMemset(e->d_last_period, 0, S * sizeof(int)));
   CK(cudaMemset(e->d_last_gain, 0, S * sizeof(float)));
+  e->hop = 0;
+  if (e->flags & PNB_TRAIN_DATA) {
+    CK(cudaDeviceSynchronize());
+    return PNB_OK;
+  }
   CK(cudaMemset(e->ring_fc, 0, 5 * S * 128 * sizeof(float)));
   CK(cudaMemset(e->ring_c1, 0, 3 * S * 512 * sizeof(float)));
   CK(cudaMemset(e->c2, 0, S * 512 * sizeof(float)));
   for (int i = 0; i < 5; i++)
     for (int p = 0; p < 2; p++) CK(cudaMemset(e->h[i][p], 0, S * e->gru[i].H * sizeof(float)));
-  e->hop = 0;
   for (int i = 0; i < 5; i++) e->par[i] = 0;
   int trc = tc_reset(e);
   if (trc) return trc;
@@ -348,7 +365,7 @@ extern "C" int pnb_profile_read(pnb_engine *e, double *ms, long long *counts) {
 }
 extern "C" const char *pnb_kernel_class_name(int cls) {
   static const char *names[PNB_NUM_KERNEL_CLASSES] = {"stage_in_kernel", "analysis_kernel", "fc_f32_kernel",
-      "gemm_f32_kernel", "gru_gates_kernel", "synthesis_kernel", "slide_history_kernel", "tc_gemm_kernel", "tc_aux_kernel"};
+      "gemm_f32_kernel", "gru_gates_kernel", "synthesis_kernel", "slide_history_kernel", "tc_gemm_kernel", "tc_aux_kernel", "train_labels_kernel"};
   return (cls >= 0 && cls < PNB_NUM_KERNEL_CLASSES) ? names[cls] : "?";
 }
 
@@ -440,6 +457,7 @@ static int nn_step_f32(pnb_engine *e, int t, cudaStream_t st) {
 static int process_device(pnb_engine *e, const float *d_in, const short *d_in16, size_t in_stride, float *d_out,
                           short *d_out16, size_t out_stride, int F, float *d_gr, cudaStream_t st) {
   if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  if (e->flags & PNB_TRAIN_DATA) return fail(PNB_ERR_ARG, "engine was created with PNB_TRAIN_DATA: use pnb_train_records_*");
   if (F < 1 || F > e->Fmax) return fail(PNB_ERR_ARG, "n_frames %d outside [1, %d]", F, e->Fmax);
   if ((!d_in && !d_in16) || (!d_out && !d_out16)) return fail(PNB_ERR_ARG, "input/output pointer is NULL");
   if (in_stride < (size_t)F * kFrame || out_stride < (size_t)F * kFrame)
@@ -451,7 +469,7 @@ static int process_device(pnb_engine *e, const float *d_in, const short *d_in16,
   AnalysisArgs a;
   a.pcm = e->d_pcm; a.pcm_stride = e->pcm_stride; a.n_streams = S; a.n_frames = F; a.tab = e->d_tab;
   a.feat = e->d_feat; a.zring = e->d_zring; a.ering = e->d_ering; a.ring = e->ring; a.hop0 = e->hop;
-  a.P = e->d_P; a.Ex = e->d_Ex; a.silence = e->d_sil;
+  a.P = e->d_P; a.Ex = e->d_Ex; a.raw = nullptr; a.silence = e->d_sil;
   a.last_period = e->d_last_period; a.last_gain = e->d_last_gain;
   a.tap_pitch = e->d_tap_pitch; a.tap_pitchf = e->d_tap_pitchf;
   { ProfScope ps(e, PNB_K_ANALYSIS, st); n += launch_analysis(a, st); }
@@ -497,6 +515,72 @@ extern "C" int pnb_process_device_i16(pnb_engine *e, const short *d_in, size_t i
                                       size_t out_stride, int n_frames, float *d_gr, void *cuda_stream) {
   return process_device(e, nullptr, d_in, in_stride, nullptr, d_out, out_stride, n_frames, d_gr,
                         (cudaStream_t)cuda_stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// training-data generator (row f1): stage both files of every pair, analysis over 2N streams, labels
+// ------------------------------------------------------------------------------------------
+extern "C" int pnb_train_records_device(pnb_engine *e, const short *d_speech, size_t speech_stride,
+                                        const short *d_noisy, size_t noisy_stride, int F, float *d_records,
+                                        size_t records_stride, void *cuda_stream) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  if (!(e->flags & PNB_TRAIN_DATA)) return fail(PNB_ERR_ARG, "engine was not created with PNB_TRAIN_DATA");
+  if (F < 1 || F > e->Fmax) return fail(PNB_ERR_ARG, "n_frames %d outside [1, %d]", F, e->Fmax);
+  if (!d_speech || !d_noisy || !d_records) return fail(PNB_ERR_ARG, "speech/noisy/records pointer is NULL");
+  if (speech_stride < (size_t)F * kFrame || noisy_stride < (size_t)F * kFrame)
+    return fail(PNB_ERR_ARG, "row stride smaller than n_frames*480");
+  if (records_stride < (size_t)F * PNB_RECORD_FLOATS) return fail(PNB_ERR_ARG, "records_stride smaller than n_frames*138");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int S = e->S, N = S / 2;
+  long long n = 0;
+  {
+    ProfScope ps(e, PNB_K_STAGE_IN, st);
+    n += launch_stage_in(e->d_pcm, e->pcm_stride, nullptr, d_noisy, noisy_stride, N, F * kFrame, st, 1.f);
+    n += launch_stage_in(e->d_pcm + (size_t)N * e->pcm_stride, e->pcm_stride, nullptr, d_speech, speech_stride, N, F * kFrame, st, 1.f);
+  }
+  AnalysisArgs a;
+  a.pcm = e->d_pcm; a.pcm_stride = e->pcm_stride; a.n_streams = S; a.n_frames = F; a.tab = e->d_tab;
+  a.feat = e->d_feat; a.zring = e->d_zring; a.ering = e->d_ering; a.ring = e->ring; a.hop0 = e->hop;
+  a.P = nullptr; a.Ex = e->d_Ex; a.raw = e->d_raw; a.silence = e->d_sil;
+  a.last_period = e->d_last_period; a.last_gain = e->d_last_gain;
+  a.tap_pitch = e->d_tap_pitch; a.tap_pitchf = e->d_tap_pitchf;
+  { ProfScope ps(e, PNB_K_ANALYSIS, st); n += launch_analysis(a, st); }
+  LabelArgs l;
+  l.feat = e->d_feat; l.raw = e->d_raw; l.Ex = e->d_Ex; l.tab = e->d_tab; l.n_pairs = N; l.n_frames = F;
+  l.records = d_records; l.pair_stride = records_stride;
+  { ProfScope ps(e, PNB_K_LABELS, st); n += launch_train_labels(l, st); }
+  { ProfScope ps(e, PNB_K_SLIDE, st); n += launch_slide_history(e->d_pcm, e->pcm_stride, S, F * kFrame, st); }
+  CK(cudaGetLastError());
+  e->hop += F;
+  e->last_frames = F;
+  e->launches += n;
+  return PNB_OK;
+}
+
+extern "C" int pnb_train_records_host(pnb_engine *e, const short *speech, size_t speech_stride, const short *noisy,
+                                      size_t noisy_stride, int F, float *records, size_t records_stride) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  if (!(e->flags & PNB_TRAIN_DATA)) return fail(PNB_ERR_ARG, "engine was not created with PNB_TRAIN_DATA");
+  if (!speech || !noisy || !records) return fail(PNB_ERR_ARG, "speech/noisy/records pointer is NULL");
+  if (F < 1 || F > e->Fmax) return fail(PNB_ERR_ARG, "n_frames %d outside [1, %d]", F, e->Fmax);
+  if (speech_stride < (size_t)F * kFrame || noisy_stride < (size_t)F * kFrame)
+    return fail(PNB_ERR_ARG, "row stride smaller than n_frames*480");
+  if (records_stride < (size_t)F * PNB_RECORD_FLOATS) return fail(PNB_ERR_ARG, "records_stride smaller than n_frames*138");
+  CK(cudaSetDevice(e->device));
+  const size_t N = e->S / 2, row = (size_t)e->Fmax * kFrame, rrow = (size_t)e->Fmax * PNB_RECORD_FLOATS;
+  if (!e->d_hin16) CK(cudaMalloc((void **)&e->d_hin16, 2 * N * row * sizeof(short)));
+  if (!e->d_records) CK(cudaMalloc((void **)&e->d_records, N * rrow * sizeof(float)));
+  const size_t w = (size_t)F * kFrame * sizeof(short);
+  short *d_noisy = e->d_hin16, *d_speech = e->d_hin16 + N * row;
+  CK(cudaMemcpy2DAsync(d_noisy, row * 2, noisy, noisy_stride * 2, w, N, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpy2DAsync(d_speech, row * 2, speech, speech_stride * 2, w, N, cudaMemcpyHostToDevice, e->stream));
+  int rc = pnb_train_records_device(e, d_speech, row, d_noisy, row, F, e->d_records, rrow, e->stream);
+  if (rc) return rc;
+  CK(cudaMemcpy2DAsync(records, records_stride * 4, e->d_records, rrow * 4, (size_t)F * PNB_RECORD_FLOATS * 4, N,
+                       cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return PNB_OK;
 }
 
 template <typename T>

@@ -33,6 +33,8 @@ struct pnb_engine {
   int ring = 0;
   float2 *d_P = nullptr;
   float *d_Ex = nullptr;
+  float *d_raw = nullptr;     // [F][S][68] training-data mode only
+  float *d_records = nullptr; // [S/2][Fmax][138] staging of pnb_train_records_host
   unsigned char *d_sil = nullptr;
   float *d_gr = nullptr;
   int *d_tap_pitch = nullptr;

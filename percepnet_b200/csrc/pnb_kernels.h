@@ -15,8 +15,9 @@ struct AnalysisArgs {
   float *ering;            // [ring][S][34] their band energies
   int ring;                // slots (>= n_frames + 5)
   long hop0;               // absolute index of the call's first hop
-  float2 *P;               // [F][S][400]
+  float2 *P;               // [F][S][400] or null (training-data mode has no synthesis)
   float *Ex;               // [F][S][34] or null
+  float *raw;              // [F][S][68] or null: look-ahead band energies and pitch coherence before the x30
   unsigned char *silence;  // [F][S]
   int *last_period;        // [S] carried state
   float *last_gain;        // [S]
@@ -41,11 +42,23 @@ struct SynthesisArgs {
   int postfilter;
 };
 
+// training-data records (train(), denoise.cpp:600-787): streams [0,N) are the noisy signals, [N,2N) the clean ones
+struct LabelArgs {
+  const float *feat;       // [F][2N][70]
+  const float *raw;        // [F][2N][68]
+  const float *Ex;         // [F][2N][34]
+  const Tables *tab;
+  int n_pairs, n_frames;
+  float *records;          // pair p, frame t at records + p*pair_stride + t*138
+  size_t pair_stride;
+};
+int launch_train_labels(const LabelArgs &a, cudaStream_t st);
+
 cudaError_t dsp_configure();
 int launch_analysis(const AnalysisArgs &a, cudaStream_t st);
 int launch_synthesis(const SynthesisArgs &a, cudaStream_t st);
 int launch_stage_in(float *pcm, size_t pcm_stride, const float *in, const short *in16, size_t in_stride,
-                    int n_streams, int n_samples, cudaStream_t st);
+                    int n_streams, int n_samples, cudaStream_t st, float i16_div = 32768.f);
 int launch_slide_history(float *pcm, size_t pcm_stride, int n_streams, int n_samples, cudaStream_t st);
 
 // ---- network, fp32 FMA path (pnb_nn_f32.cu) ---------------------------------------------

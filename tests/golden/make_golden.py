@@ -14,6 +14,8 @@ Writes (all small, committed):
                    scales (out, g/r) and through the CLI's int16 conversions (src/main.cpp:30-39),
                    with weights = percepnet_b200.weights.synth_model(0) (digest stored)
   stages.npz       per-stage outputs of the reference's non-static functions on the same audio
+  train.npz        two (speech, noisy) int16 pairs cut from /root/reference/sampledata and the 138-float records
+                   the reference's own train() (src/denoise.cpp:600) wrote for them
 """
 import os
 import re
@@ -40,8 +42,30 @@ def parse_arrays(path):
     return arrs
 
 
+def make_train(R):
+    import tempfile
+    n = 40
+    sp = np.fromfile(os.path.join(REF, "sampledata/speech/speech.pcm"), dtype=np.int16)
+    no = np.fromfile(os.path.join(REF, "sampledata/noise/noise.pcm"), dtype=np.int16)
+    speech, noisy, recs = [], [], []
+    with tempfile.TemporaryDirectory() as d:
+        for k, (off, shift) in enumerate(((480 * 100, 1), (480 * 260, 3))):
+            c = sp[off:off + 480 * n].copy()
+            y = np.clip(c.astype(np.int32) + (no[off:off + 480 * n].astype(np.int32) >> shift), -32768, 32767).astype(np.int16)
+            fc, fn, fo = (os.path.join(d, f"{nm}{k}") for nm in ("c", "n", "o"))
+            c.tofile(fc); y.tofile(fn)
+            assert R.train_files(fc, fn, n, fo) == 0
+            speech.append(c); noisy.append(y)
+            recs.append(np.fromfile(fo, np.float32).reshape(n, 138))
+    np.savez_compressed(os.path.join(OUT, "train.npz"), speech=np.stack(speech), noisy=np.stack(noisy),
+                        records=np.stack(recs))
+    print("train.npz", os.path.getsize(os.path.join(OUT, "train.npz")))
+
+
 def main():
     build()
+    if "--train-only" in sys.argv:
+        return make_train(Reference())
     R = Reference()
     np.savez_compressed(os.path.join(OUT, "toy_layers.npz"), **parse_arrays(os.path.join(REF, "tests/nnet_data_test.h")))
 
@@ -106,6 +130,7 @@ def main():
     st["rnn_out"] = np.stack(outs)
     st["borders"] = R.erb_borders()
     np.savez_compressed(os.path.join(OUT, "stages.npz"), **st)
+    make_train(R)
     for f in ("toy_layers.npz", "e2e.npz", "stages.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

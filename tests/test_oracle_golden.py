@@ -86,3 +86,13 @@ def test_post_filter_properties(oracle):
     G = np.sqrt(1.02 * q / (1 + 0.02 * q * q))
     assert np.allclose(out, G * gw, rtol=2e-6, atol=1e-7)
     assert np.allclose(oracle.post_filter(np.ones(34, np.float32), Ey), 1.0, atol=1e-5)   # g = 1 is a fixed point
+
+
+def test_golden_training_records(oracle):
+    """Row f1: the restated train() loop against the records the reference's train() wrote (tests/golden/train.npz)."""
+    g = np.load(os.path.join(GOLDEN, "train.npz"))
+    for k in range(g["speech"].shape[0]):
+        got = oracle.train_records(g["speech"][k], g["noisy"][k])
+        assert same_bits(got, g["records"][k])
+    rec = g["records"]
+    assert np.any(rec[..., 104:] == np.float32(0.99)) and np.any(rec[..., 104:] < 0.5)    # both label branches occur

@@ -156,3 +156,43 @@ def test_multi_stream_driver(oracle, reference, model0):
     reference.set_model(model0)
     x = synth_pcm(3, 6, seed=5)
     assert same_bits(oracle.process_streams(model0, x, 2), reference.process_streams(x, 2))
+
+
+def test_training_records_match_reference_train(oracle, reference, tmp_path):
+    """Row f1: the restated train() loop and label math (denoise.cpp:549-589, 600-787) against the reference's own
+    train() run on files: every 138-float record bit for bit, over speech-like pairs at several SNRs, an
+    all-zero clean file (g = 0) and identical clean/noisy files (g = 1 up to the .0001 bias)."""
+    from percepnet_b200.synth import synth_pairs
+    n_frames = 40
+    clean, noisy = synth_pairs(6, n_frames, seed=77)
+    cases = [(clean[k], noisy[k]) for k in range(6)]
+    cases.append((np.zeros_like(clean[0]), noisy[0]))
+    cases.append((noisy[1], noisy[1]))
+    cases.append((clean[2], (noisy[2] // 64).astype(np.int16)))      # noisy far below clean: g clipped at 1
+    saw_branch = 0
+    for k, (c, n) in enumerate(cases):
+        fc, fn, fo = (str(tmp_path / f"{nm}{k}") for nm in ("c", "n", "o"))
+        c.tofile(fc); n.tofile(fn)
+        assert reference.train_files(fc, fn, n_frames, fo) == 0
+        want = np.fromfile(fo, np.float32).reshape(n_frames, 138)
+        got = oracle.train_records(c, n)
+        assert same_bits(got, want), (k, np.abs(got - want).max())
+        saw_branch += int(np.any(want[:, 104:] == np.float32(0.99)))
+    assert saw_branch >= 3        # the Ephatp < Exp branch (r = 0.99, attenuated g) is exercised
+
+
+def test_training_file_wraparound_matches_reference(oracle, reference, tmp_path):
+    """train() re-reads a file from its start when a read hits EOF (denoise.cpp:676-679, 687-690); the CLI's
+    read_cyclic_frames restates that: files shorter than <count>, with and without a trailing partial frame."""
+    from percepnet_b200.gen_features import read_cyclic_frames
+    from percepnet_b200.synth import synth_pairs
+    clean, noisy = synth_pairs(1, 12, seed=5)
+    count = 30
+    for tail_c, tail_n, nc, nn in ((0, 0, 12, 12), (123, 0, 9, 12), (7, 479, 12, 7)):
+        fc, fn, fo = str(tmp_path / "c"), str(tmp_path / "n"), str(tmp_path / "o")
+        clean[0][:nc * 480 + tail_c].tofile(fc)
+        noisy[0][:nn * 480 + tail_n].tofile(fn)
+        assert reference.train_files(fc, fn, count, fo) == 0
+        want = np.fromfile(fo, np.float32).reshape(count, 138)
+        got = oracle.train_records(read_cyclic_frames(fc, count), read_cyclic_frames(fn, count))
+        assert same_bits(got, want), (tail_c, tail_n)
