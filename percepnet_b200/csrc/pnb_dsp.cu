@@ -799,6 +799,7 @@ __global__ void __launch_bounds__(kSynWarps * 32) synthesis_kernel(SynthesisArgs
         G = sqrtf(((1.f + 0.02f) * q) / (1.f + 0.02f * (q * q)));
       }
       G = __shfl_sync(0xffffffffu, G, 0);
+      __syncwarp();  // lane 0's reads of g are ordered before the overwrite (the shuffle alone is not a memory fence)
       for (int b = lane; b < kBands; b += 32) W.g[b] = G * W.gw[b];
       __syncwarp();
     }
