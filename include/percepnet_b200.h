@@ -115,6 +115,10 @@ int pnb_process_device_i16(pnb_engine *e, const short *d_in, size_t in_stride, s
 #define PNB_RECORD_FLOATS 138
 int pnb_train_records_host(pnb_engine *e, const short *speech, size_t speech_stride, const short *noisy,
                            size_t noisy_stride, int n_frames, float *records, size_t records_stride);
+/* Pipelined form (pair it with pnb_wait, like pnb_submit_host_*): the copies of neighbouring calls overlap the
+ * kernels; the buffers of a call must stay untouched until pnb_wait returns or two further calls were submitted. */
+int pnb_submit_train_records(pnb_engine *e, const short *speech, size_t speech_stride, const short *noisy,
+                             size_t noisy_stride, int n_frames, float *records, size_t records_stride);
 int pnb_train_records_device(pnb_engine *e, const short *d_speech, size_t speech_stride, const short *d_noisy,
                              size_t noisy_stride, int n_frames, float *d_records, size_t records_stride,
                              void *cuda_stream);

@@ -45,6 +45,7 @@ def load_library() -> C.CDLL:
     L.pnb_model_free.argtypes = [vp]
     L.pnb_model_free.restype = None
     L.pnb_train_records_host.argtypes = [vp, vp, sz, vp, sz, i, vp, sz]
+    L.pnb_submit_train_records.argtypes = [vp, vp, sz, vp, sz, i, vp, sz]
     L.pnb_train_records_device.argtypes = [vp, vp, sz, vp, sz, i, vp, sz, vp]
     L.pnb_destroy.argtypes = [vp]
     L.pnb_destroy.restype = None
@@ -73,7 +74,7 @@ def load_library() -> C.CDLL:
 
 
 EXPORTS = ("pnb_create", "pnb_destroy", "pnb_reset", "pnb_process_host_f32", "pnb_process_host_i16",
-           "pnb_model_load_blob", "pnb_model_free", "pnb_train_records_host", "pnb_train_records_device", "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_wait",
+           "pnb_model_load_blob", "pnb_model_free", "pnb_train_records_host", "pnb_train_records_device", "pnb_submit_train_records", "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_wait",
            "pnb_read_tap", "pnb_launch_count",
            "pnb_launches_per_call", "pnb_profile_enable", "pnb_profile_read", "pnb_kernel_class_name", "pnb_n_streams", "pnb_max_frames", "pnb_last_error", "pnb_version")
 

@@ -181,24 +181,46 @@ __device__ __forceinline__ void fft960_warp(float2 *f, const FftTw &T, int lane,
 // ERB band pooling (denoise.cpp:89-123 / 125-160): v[bin] is |X|^2 or Re(X conj P) for bins 0..399.
 // Accumulator b receives, in the reference's order, first the frac-weighted bins of band b-1 and then
 // the (1-frac)-weighted bins of band b; ends are doubled.
-template <int L>
+// kDual pools two quantities over the same bands at once (two independent add chains per lane).
+template <bool kDual>
+__device__ __forceinline__ void band_acc(int b, const float *vf, const float *vo, float *out, const float *vf2,
+                                         const float *vo2, float *out2, const short *border) {
+  float acc = 0.f, acc2 = 0.f;
+  if (b > 0) {
+    const int lo = border[b - 1], hi = border[b];
+#pragma unroll 4
+    for (int k = lo; k < hi; k++) {
+      acc = acc + vf[k];
+      if (kDual) acc2 = acc2 + vf2[k];
+    }
+  }
+  if (b < kBands - 1) {
+    const int lo = border[b], hi = border[b + 1];
+#pragma unroll 4
+    for (int k = lo; k < hi; k++) {
+      acc = acc + vo[k];
+      if (kDual) acc2 = acc2 + vo2[k];
+    }
+  }
+  if (b == 0 || b == kBands - 1) { acc *= 2; acc2 *= 2; }
+  out[b] = acc;
+  if (kDual) out2[b] = acc2;
+}
+template <int L, bool kDual = false>
 __device__ void band_pool_warp(const float *vf, const float *vo, float *out, const short *border, int lane,
-                               unsigned mask) {
+                               unsigned mask, const float *vf2 = nullptr, const float *vo2 = nullptr,
+                               float *out2 = nullptr) {
   // vf[k] = frac[k] * v[k] and vo[k] = (1 - frac[k]) * v[k] were formed by the caller (the very products the
-  // reference adds, denoise.cpp:102-103), so the serial part is one load and one add per bin
+  // reference adds, denoise.cpp:102-103), so the serial part is one load and one add per bin.
+  // Accumulators 32 and 33 are the longest chains (96 and 51 adds) and 0 and 1 the shortest (2 and 4): with a
+  // warp per stream, lane j takes accumulator j+2 and lanes 0/1 then add the two short ones, so the critical
+  // path is one long chain instead of two.
   __syncwarp(mask);
-  for (int b = lane; b < kBands; b += L) {
-    float acc = 0.f;
-    if (b > 0) {
-      int lo = border[b - 1], hi = border[b];
-      for (int k = lo; k < hi; k++) acc = acc + vf[k];
-    }
-    if (b < kBands - 1) {
-      int lo = border[b], hi = border[b + 1];
-      for (int k = lo; k < hi; k++) acc = acc + vo[k];
-    }
-    if (b == 0 || b == kBands - 1) acc *= 2;
-    out[b] = acc;
+  if (L == 32) {
+    band_acc<kDual>(lane + 2, vf, vo, out, vf2, vo2, out2, border);
+    if (lane < 2) band_acc<kDual>(lane, vf, vo, out, vf2, vo2, out2, border);
+  } else {
+    for (int b = lane; b < kBands; b += L) band_acc<kDual>(b, vf, vo, out, vf2, vo2, out2, border);
   }
   __syncwarp(mask);
 }
@@ -208,26 +230,40 @@ __device__ void band_pool_warp(const float *vf, const float *vo, float *out, con
 // dsyy[i] = y[i+len]^2 - y[i]^2 has been precomputed by the whole warp (same expression as the reference's
 // running update), so the serial part is one add and one max per lag.
 __device__ void best_two(const float *xcorr, const float *dsyy, int max_pitch, float syy, int &b0, int &b1) {
+  // Operands come four lags per 128-bit load (xcorr and dsyy are 16-byte aligned); the update rule is the
+  // reference's, one lag at a time.  On one lane the cost is the instruction count, so nothing is computed for a
+  // lag before its sign test.
   float num0 = -1.f, num1 = -1.f, den0 = 0.f, den1 = 0.f;
   b0 = 0;
   b1 = 1;
-  for (int i = 0; i < max_pitch; i++) {
-    float xc = xcorr[i];
-    if (xc > 0.f) {
-      float c = xc * 1e-12f;
-      float num = c * c;
-      if (num * den1 > num1 * syy) {
-        if (num * den0 > num0 * syy) {
-          num1 = num0; den1 = den0; b1 = b0;
-          num0 = num;  den0 = syy;  b0 = i;
-        } else {
-          num1 = num; den1 = syy; b1 = i;
-        }
-      }
-    }
-    syy = syy + dsyy[i];
-    syy = 1.f > syy ? 1.f : syy;
+#define PNB_BEST_STEP(XC, D, I)                              \
+  do {                                                       \
+    if ((XC) > 0.f) {                                        \
+      const float c_ = (XC) * 1e-12f;                        \
+      const float num_ = c_ * c_;                            \
+      if (num_ * den1 > num1 * syy) {                        \
+        if (num_ * den0 > num0 * syy) {                      \
+          num1 = num0; den1 = den0; b1 = b0;                 \
+          num0 = num_; den0 = syy; b0 = (I);                 \
+        } else {                                             \
+          num1 = num_; den1 = syy; b1 = (I);                 \
+        }                                                    \
+      }                                                      \
+    }                                                        \
+    syy = syy + (D);                                         \
+    syy = 1.f > syy ? 1.f : syy;                             \
+  } while (0)
+  int i = 0;
+  for (; i + 4 <= max_pitch; i += 4) {
+    const float4 x4 = *reinterpret_cast<const float4 *>(xcorr + i);
+    const float4 d4 = *reinterpret_cast<const float4 *>(dsyy + i);
+    PNB_BEST_STEP(x4.x, d4.x, i);
+    PNB_BEST_STEP(x4.y, d4.y, i + 1);
+    PNB_BEST_STEP(x4.z, d4.z, i + 2);
+    PNB_BEST_STEP(x4.w, d4.w, i + 3);
   }
+  for (; i < max_pitch; i++) PNB_BEST_STEP(xcorr[i], dsyy[i], i);
+#undef PNB_BEST_STEP
 }
 
 // Sequential dot product s + sum_j a[j] b[j] (ascending j, multiply then add -- the reference's order) with the
@@ -262,7 +298,19 @@ __device__ void best_two_sparse(const float *xcorr, const float *dsyy, int max_p
     int hi = (seg == 0 ? lo_a : lo_b) + 5;
     hi = hi < lo ? lo : hi;
     hi = hi > max_pitch ? max_pitch : hi;
-    for (; i < lo; i++) {  // no candidates here
+    // no candidates here: only the running energy advances (four steps per 128-bit load once aligned)
+    for (; i < lo && (i & 3); i++) {
+      syy = syy + dsyy[i];
+      syy = 1.f > syy ? 1.f : syy;
+    }
+    for (; i + 4 <= lo; i += 4) {
+      const float4 d4 = *reinterpret_cast<const float4 *>(dsyy + i);
+      syy = syy + d4.x; syy = 1.f > syy ? 1.f : syy;
+      syy = syy + d4.y; syy = 1.f > syy ? 1.f : syy;
+      syy = syy + d4.z; syy = 1.f > syy ? 1.f : syy;
+      syy = syy + d4.w; syy = 1.f > syy ? 1.f : syy;
+    }
+    for (; i < lo; i++) {
       syy = syy + dsyy[i];
       syy = 1.f > syy ? 1.f : syy;
     }
@@ -291,6 +339,7 @@ __device__ __forceinline__ float pitch_gain(float xy, float xx, float yy) {
   return xy / sqrtf(1.f + xx * yy);  // pitch.cpp:417-420 (float sqrt overload)
 }
 
+constexpr int kAcHops = 8;  // hops whose pitch_downsample autocorrelations are computed together
 struct PitchSmem {
   float lp[kLp];       // decimated, whitened pitch buffer
   float yy[392];       // yy_lookup of remove_doubling (385 used); before that the energy deltas of the lag scans
@@ -304,7 +353,10 @@ struct WarpSmem {
   float xc[400];       // xcorr (147 / 294) -- doubles as the per-bin scratch of band pooling (frac-weighted);
                        // the (1-frac)-weighted scratch lives in the tail of the FFT line (bins 0..399 end at slot 447)
   float Ex[kBands], Ep[kBands], Exp[kBands], Ey[kBands];
+  float ac_pre[kAcHops * 5];  // autocorrelations of pitch_downsample for a group of hops (see the pre-pass)
 };
+static_assert(offsetof(WarpSmem, xc) == sizeof(float2) * kFftLine, "the pre-pass treats fft[] + xc[] as one array");
+static_assert(kLp + 240 * (kAcHops - 1) + 4 <= 2 * kFftLine + 400, "decimated group does not fit the scratch");
 
 struct BlockSmem {
   FftTw ft;
@@ -326,6 +378,20 @@ struct AnaCfg {
   static constexpr int kLagsPerLane = (L == 32) ? 5 : 10;       // coarse search: adjacent lags per lane
   static constexpr int kLagLanes = (L == 32) ? 30 : 15;         // lanes that own lags; the next lane accumulates Syy
 };
+
+// Per-section cycle accounting of the analysis kernel (debug builds only: -DPNB_ANA_TIMING).  Lane 0 of every
+// warp samples clock64() at the section boundaries and the deltas are summed into g_ana_cycles.
+#ifdef PNB_ANA_TIMING
+__device__ unsigned long long g_ana_cycles[16];
+#define ANA_TICK(k)                                      \
+  do {                                                   \
+    long long _now = clock64();                          \
+    if (lane == 0) ana_acc[k] += (unsigned long long)(_now - ana_t0); \
+    ana_t0 = _now;                                       \
+  } while (0)
+#else
+#define ANA_TICK(k) do { } while (0)
+#endif
 
 template <int L>
 __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(AnalysisArgs A) {
@@ -354,9 +420,56 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
   int last_period = A.last_period[s];
   float last_gain = A.last_gain[s];
 
+#ifdef PNB_ANA_TIMING
+  unsigned long long ana_acc[16];
+  for (int i = 0; i < 16; i++) ana_acc[i] = 0;
+  long long ana_t0 = clock64();
+#endif
   for (int t = 0; t < A.n_frames; t++) {
     const float *line = row + (size_t)t * kFrame;  // line[j] == reference comb_buf[j] at this hop
     const size_t fs = (size_t)t * A.n_streams + s;
+
+    // ---- pre-pass, once per group of kAcHops hops: the five autocorrelations pitch_downsample needs
+    // (pitch.cpp:182 -> celt_lpc.cpp:198-279).  Inside a hop only five lanes can work on them (one strictly
+    // sequential 864-term sum per lag); but the 2:1 decimated signal of hop t+1 is that of hop t advanced by 240
+    // samples (only element 0 of each hop's buffer has its own formula, pitch.cpp:165), so the decimated signal
+    // of the whole group is laid out once in the scratch line and ONE LANE PER HOP runs the five sums of its hop,
+    // sharing every loaded sample between the lags.  Same products, same order of additions as the reference.
+    if (t % kAcHops == 0) {
+      const int G = (A.n_frames - t < kAcHops) ? A.n_frames - t : kAcHops;
+      float *D = reinterpret_cast<float *>(W.fft);
+      const float *src = line + kOffPitch;
+      const int nD = kLp + 240 * (G - 1);
+      for (int i = lane; i < nD; i += L) D[i] = .5f * (.5f * (src[2 * i - 1] + src[2 * i + 1]) + src[2 * i]);
+      __syncwarp(mask);
+      if (lane < G) {
+        const float *Dh = D + 240 * lane, *sh = src + kFrame * lane;
+        float4 c = *reinterpret_cast<const float4 *>(Dh), n = *reinterpret_cast<const float4 *>(Dh + 4);
+        c.x = .5f * (.5f * sh[1] + sh[0]);  // lp[0] of this hop (pitch.cpp:165)
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#define PNB_AC_STEP(X, P1, P2, P3, P4) \
+  a0 = a0 + (X) * (X); a1 = a1 + (X) * (P1); a2 = a2 + (X) * (P2); a3 = a3 + (X) * (P3); a4 = a4 + (X) * (P4)
+#pragma unroll 1
+        for (int m = 0; m < 215; m++) {  // j = 4m .. 4m+3 < 860 (celt_lpc.cpp:250-252: fastN = n - lag)
+          PNB_AC_STEP(c.x, c.y, c.z, c.w, n.x);
+          PNB_AC_STEP(c.y, c.z, c.w, n.x, n.y);
+          PNB_AC_STEP(c.z, c.w, n.x, n.y, n.z);
+          PNB_AC_STEP(c.w, n.x, n.y, n.z, n.w);
+          c = n;
+          if (m < 214) n = *reinterpret_cast<const float4 *>(Dh + 4 * (m + 2));  // up to lp[860..863]
+        }
+#undef PNB_AC_STEP
+        // the tail i = k+860 .. 863 is summed on its own and then added (celt_lpc.cpp:253-256); c = lp[860..863]
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        d0 = d0 + c.x * c.x; d0 = d0 + c.y * c.y; d0 = d0 + c.z * c.z; d0 = d0 + c.w * c.w;
+        d1 = d1 + c.y * c.x; d1 = d1 + c.z * c.y; d1 = d1 + c.w * c.z;
+        d2 = d2 + c.z * c.x; d2 = d2 + c.w * c.y;
+        d3 = d3 + c.w * c.x;
+        float *o = W.ac_pre + 5 * lane;
+        o[0] = a0 + d0; o[1] = a1 + d1; o[2] = a2 + d2; o[3] = a3 + d3; o[4] = a4 + 0.f;
+      }
+      __syncwarp(mask);
+    }
 
     // ---- one transform per hop.  The look-ahead window of hop c (denoise.cpp:498-506: the newest 960
     // samples) is the very block whose spectrum is the analysis spectrum X five hops later (:402, :333-346:
@@ -374,6 +487,7 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
         return make_float2((1.f / kWin) * v, 0.f);
       });
     }
+    ANA_TICK(0);
     {
       float2 *Zg = A.zring + ((size_t)slot_new * A.n_streams + s) * kBins;
       for (int k = lane; k < kBins; k += L) {
@@ -394,6 +508,7 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
     }
     const float2 *Xg = A.zring + ((size_t)slot_x * A.n_streams + s) * kBins;
     __syncwarp(mask);
+    ANA_TICK(1);
 
     // ---- pitch_downsample (pitch.cpp:148-216) ----
     {
@@ -405,17 +520,12 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
         W.p.lp[i] = v;
       }
       __syncwarp(mask);
-      // autocorrelation, 5 lags: bulk over 860 samples then the 4-sample tail (celt_lpc.cpp:250-256)
-      float ac = 0.f;
-      if (lane < 5) {
-        ac = seq_dot4(W.p.lp, W.p.lp + lane, 860, 0.f);
-        float d = 0.f;
-        for (int i = lane + 860; i < kLp; i++) d = d + W.p.lp[i] * W.p.lp[i - lane];
-        ac += d;
-      }
-      float ac0 = __shfl_sync(mask, ac, 0, L), ac1 = __shfl_sync(mask, ac, 1, L), ac2 = __shfl_sync(mask, ac, 2, L),
-            ac3 = __shfl_sync(mask, ac, 3, L), ac4 = __shfl_sync(mask, ac, 4, L);
+      ANA_TICK(2);
+      // autocorrelation, 5 lags: computed for the whole group of hops by the pre-pass above
+      const float *acp = W.ac_pre + 5 * (t % kAcHops);
+      const float ac0 = acp[0], ac1 = acp[1], ac2 = acp[2], ac3 = acp[3], ac4 = acp[4];
       float fir0 = 0, fir1 = 0, fir2 = 0, fir3 = 0, fir4 = 0;
+      ANA_TICK(3);
       if (lane == 0) {
         float a[5] = {ac0, ac1, ac2, ac3, ac4};
         a[0] *= 1.0001f;                                                        // pitch.cpp:190
@@ -451,6 +561,7 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
       fir2 = __shfl_sync(mask, fir2, 0, L);
       fir3 = __shfl_sync(mask, fir3, 0, L);
       fir4 = __shfl_sync(mask, fir4, 0, L);
+      ANA_TICK(4);
       // 5-tap FIR in place with zero history (pitch.cpp:106-145,154), walked from the end so the taps
       // still see unfiltered samples
       for (int base = kLp - L; base >= 0; base -= L) {
@@ -470,6 +581,7 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
       }
     }
 
+    ANA_TICK(5);
     // ---- pitch_search (pitch.cpp:283-386): x = lp+384, y = lp, len 960, max_pitch 588 ----
     int pitch_lag, T;
     float pitch_corr, gain;
@@ -510,11 +622,13 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
         }
         float syy_c = __shfl_sync(mask, acc[0], CF::kLagLanes, L);
         __syncwarp(mask);
+        ANA_TICK(6);
         b0 = 0; b1 = 0;
         if (lane == 0) best_two(W.xc, W.p.yy, 147, syy_c, b0, b1);
         b0 = __shfl_sync(mask, b0, 0, L);
         b1 = __shfl_sync(mask, b1, 0, L);
         __syncwarp(mask);
+        ANA_TICK(7);
       }
       // fine: at most ten lags around 2*b0 and 2*b1 (pitch.cpp:344-361); lane 10 accumulates Syy of the
       // second find_best_pitch, lane 11 the xx of remove_doubling (pitch.cpp:448)
@@ -542,6 +656,7 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
       float syy_f = __shfl_sync(mask, sacc, 10, L);
       float xx = __shfl_sync(mask, sacc, 11, L);
       __syncwarp(mask);
+      ANA_TICK(8);
       int off = 0;
       float corr = 0.f;
       pitch_lag = 0;
@@ -559,6 +674,7 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
       pitch_lag = __shfl_sync(mask, pitch_lag, 0, L);
       pitch_corr = __shfl_sync(mask, corr, 0, L);
       __syncwarp(mask);  // the scan's energy deltas in W.p.yy are dead; the yy table is built next
+      ANA_TICK(9);
 
       // ---- remove_doubling (pitch.cpp:423-527) with maxperiod 384, minperiod 30, N 480 ----
       const int second_check[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};
@@ -566,12 +682,16 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
       int T0 = (kMaxPeriod - pitch_lag) / 2;
       if (T0 >= 384) T0 = 383;
       const int prev_period = last_period / 2;
-      // 30 roles: 0: xy at T0; 1: the yy_lookup recurrence; 2..29: candidate (k, which) = (2 + (role-2)/2, (role-2)&1)
+      // 32 roles: 0: xy at T0; 1: the yy_lookup recurrence; 2..29: candidate (k, which) = (2 + (role-2)/2, (role-2)&1);
+      // 30, 31: xy at T0-1 and T0+1, the neighbours the final refinement needs when no sub-harmonic replaces T0
+      // (the usual outcome) -- they ride along in lanes that would idle, and the extra pass below is skipped
 #pragma unroll 1
-      for (int rbase = 0; rbase < 30; rbase += L) {
+      for (int rbase = 0; rbase < 32; rbase += L) {
         const int role = rbase + lane;
         int lag = -1;
         if (role == 0) lag = T0;
+        else if (role == 30) lag = T0 - 1;
+        else if (role == 31) lag = T0 + 1;
         else if (role >= 2 && role < 30) {
           int k = 2 + ((role - 2) >> 1);
           int T1 = (2 * T0 + k) / (2 * k);
@@ -581,6 +701,9 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
             else lag = (2 * second_check[k] * T0 + k) / (2 * k);
           }
         }
+        // all lanes meet here before the 480-step loops: without it the lanes whose lag needed no division run the
+        // dot loop ahead of the candidate lanes and the loop is executed once per group
+        __syncwarp(mask);
         if (role == 1) {
           // yy_lookup recurrence (pitch.cpp:449-455), strictly sequential; operands fetched four at a time.
           // Table entry i is stored at W.p.yy[i + 3] so that groups of four are 16-byte aligned.
@@ -596,13 +719,14 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
             yy = yy + a.x * a.x - b.x * b.x; o.w = 0.f > yy ? 0.f : yy;
             *reinterpret_cast<float4 *>(&W.p.yy[i + 3]) = o;
           }
-        } else if (role < 30) {
+        } else {
           float d = 0.f;
           if (lag >= 0) d = seq_dot4(x, x - lag, 480, 0.f);
           W.p.cand_xy[role] = d;
         }
       }
       __syncwarp(mask);
+      ANA_TICK(10);
       int Tsel = T0;
       float g = 0.f, best_xy = 0.f, best_yy = 0.f;
       if (lane == 0) {
@@ -638,11 +762,17 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
         }
       }
       Tsel = __shfl_sync(mask, Tsel, 0, L);
+      ANA_TICK(11);
       // final +-1 refinement: three dot products around the selected period (pitch.cpp:512-513)
       {
-        float d = 0.f;
-        if (lane < 3) d = seq_dot4(x, x - (Tsel + lane - 1), 480, 0.f);
-        float x0 = __shfl_sync(mask, d, 0, L), x1 = __shfl_sync(mask, d, 1, L), x2 = __shfl_sync(mask, d, 2, L);
+        float x0, x1, x2;
+        if (Tsel == T0) {  // warp-uniform
+          x0 = W.p.cand_xy[30]; x1 = W.p.cand_xy[0]; x2 = W.p.cand_xy[31];
+        } else {
+          float d = 0.f;
+          if (lane < 3) d = seq_dot4(x, x - (Tsel + lane - 1), 480, 0.f);
+          x0 = __shfl_sync(mask, d, 0, L); x1 = __shfl_sync(mask, d, 1, L); x2 = __shfl_sync(mask, d, 2, L);
+        }
         int Tout = 0;
         float pg = 0.f;
         if (lane == 0) {
@@ -662,6 +792,7 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
       }
       last_period = T;
       last_gain = gain;
+      ANA_TICK(12);
     }
 
     // ---- comb-filtered block, its spectrum P and the band statistics (denoise.cpp:416-427) ----
@@ -678,26 +809,25 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
         float v = p * w;
         return make_float2((1.f / kWin) * v, 0.f);
       });
+      ANA_TICK(13);
       float2 *Pg = A.P ? A.P + fs * kBins : nullptr;
       for (int k = lane; k < kBins; k += L) {
-        float2 p = W.fft[fpos(k)];
+        float2 p = W.fft[fpos(k)], x = Xg[k];
         if (Pg) Pg[k] = p;
         float e = p.x * p.x;
         e += p.y * p.y;
-        W.xc[k] = B.frac[k] * e;
-        xo[k] = B.omf[k] * e;
+        const float fr = B.frac[k], om = B.omf[k];
+        W.xc[k] = fr * e;
+        xo[k] = om * e;
+        float c = x.x * p.x;
+        c += x.y * p.y;
+        xo[kBins + k] = fr * c;       // the line's tail (fft[448..1080)) holds three 400-float arrays
+        xo[2 * kBins + k] = om * c;
       }
-      band_pool_warp<L>(W.xc, xo, W.Ep, B.border, lane, mask);
-      for (int k = lane; k < kBins; k += L) {
-        float2 p = W.fft[fpos(k)], x = Xg[k];
-        float e = x.x * p.x;
-        e += x.y * p.y;
-        W.xc[k] = B.frac[k] * e;
-        xo[k] = B.omf[k] * e;
-      }
-      band_pool_warp<L>(W.xc, xo, W.Exp, B.border, lane, mask);
+      band_pool_warp<L, true>(W.xc, xo, W.Ep, B.border, lane, mask, xo + kBins, xo + 2 * kBins, W.Exp);
     }
 
+    ANA_TICK(14);
     // ---- features (denoise.cpp:427-433, 487-496, 528-530) ----
     {
       float *F = A.feat + fs * kFeat;
@@ -730,7 +860,12 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
       if (A.Ex) for (int b = lane; b < kBands; b += L) A.Ex[fs * kBands + b] = W.Ex[b];
     }
     __syncwarp(mask);
+    ANA_TICK(15);
   }
+#ifdef PNB_ANA_TIMING
+  if (lane == 0)
+    for (int i = 0; i < 16; i++) atomicAdd(&g_ana_cycles[i], ana_acc[i]);
+#endif
   if (lane == 0) {
     A.last_period[s] = last_period;
     A.last_gain[s] = last_gain;
@@ -987,6 +1122,18 @@ __global__ void __launch_bounds__(256) train_labels_kernel(LabelArgs A) {
   G = __shfl_sync(0xffffffffu, G, 0);
   for (int b = lane; b < kBands; b += 32) rec[70 + b] = G * sh_gw[wib][b];
 }
+
+#ifdef PNB_ANA_TIMING
+extern "C" int pnb_debug_analysis_cycles(unsigned long long *out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, g_ana_cycles, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_ana_cycles, z, sizeof z);
+  }
+  return 0;
+}
+#endif
 
 int launch_train_labels(const LabelArgs &a, cudaStream_t st) {
   const long total = (long)a.n_frames * a.n_pairs;

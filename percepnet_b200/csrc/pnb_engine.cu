@@ -677,6 +677,53 @@ extern "C" int pnb_submit_host_i16(pnb_engine *e, const short *in, size_t in_str
                                    int n_frames) {
   return submit_host<short>(e, in, in_stride, out, out_stride, n_frames);
 }
+// pipelined twin of pnb_train_records_host: same slots, streams and events as submit_host
+extern "C" int pnb_submit_train_records(pnb_engine *e, const short *speech, size_t speech_stride, const short *noisy,
+                                        size_t noisy_stride, int F, float *records, size_t records_stride) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  if (!(e->flags & PNB_TRAIN_DATA)) return fail(PNB_ERR_ARG, "engine was not created with PNB_TRAIN_DATA");
+  if (!speech || !noisy || !records) return fail(PNB_ERR_ARG, "speech/noisy/records pointer is NULL");
+  if (F < 1 || F > e->Fmax) return fail(PNB_ERR_ARG, "n_frames %d outside [1, %d]", F, e->Fmax);
+  if (speech_stride < (size_t)F * kFrame || noisy_stride < (size_t)F * kFrame)
+    return fail(PNB_ERR_ARG, "row stride smaller than n_frames*480");
+  if (records_stride < (size_t)F * PNB_RECORD_FLOATS) return fail(PNB_ERR_ARG, "records_stride smaller than n_frames*138");
+  CK(cudaSetDevice(e->device));
+  const size_t N = e->S / 2, row = (size_t)e->Fmax * kFrame, rrow = (size_t)e->Fmax * PNB_RECORD_FLOATS;
+  if (!e->s_in) {
+    CK(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      CK(cudaEventCreateWithFlags(&e->ev_in[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&e->ev_cmp[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&e->ev_out[k], cudaEventDisableTiming));
+    }
+  }
+  if (!e->pipe_in[0]) {
+    for (int k = 0; k < 2; k++) {
+      CK(cudaMalloc(&e->pipe_in[k], 2 * N * row * sizeof(short)));
+      CK(cudaMalloc(&e->pipe_out[k], N * rrow * sizeof(float)));
+    }
+    e->submitted = 0;
+  }
+  const int k = (int)(e->submitted & 1);
+  if (e->submitted >= 2) CK(cudaEventSynchronize(e->ev_out[k]));  // the slot's previous round trip is complete
+  short *d_noisy = (short *)e->pipe_in[k], *d_speech = d_noisy + N * row;
+  const size_t w = (size_t)F * kFrame * sizeof(short);
+  CK(cudaMemcpy2DAsync(d_noisy, row * 2, noisy, noisy_stride * 2, w, N, cudaMemcpyHostToDevice, e->s_in));
+  CK(cudaMemcpy2DAsync(d_speech, row * 2, speech, speech_stride * 2, w, N, cudaMemcpyHostToDevice, e->s_in));
+  CK(cudaEventRecord(e->ev_in[k], e->s_in));
+  CK(cudaStreamWaitEvent(e->stream, e->ev_in[k], 0));
+  int rc = pnb_train_records_device(e, d_speech, row, d_noisy, row, F, (float *)e->pipe_out[k], rrow, e->stream);
+  if (rc) return rc;
+  CK(cudaEventRecord(e->ev_cmp[k], e->stream));
+  CK(cudaStreamWaitEvent(e->s_out, e->ev_cmp[k], 0));
+  CK(cudaMemcpy2DAsync(records, records_stride * 4, e->pipe_out[k], rrow * 4, (size_t)F * PNB_RECORD_FLOATS * 4, N,
+                       cudaMemcpyDeviceToHost, e->s_out));
+  CK(cudaEventRecord(e->ev_out[k], e->s_out));
+  e->submitted++;
+  return PNB_OK;
+}
+
 extern "C" int pnb_wait(pnb_engine *e) {
   if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
   CK(cudaSetDevice(e->device));

@@ -66,6 +66,15 @@ def test_records_match_oracle_chunked(api, oracle):
     assert t0 == F
     got = np.concatenate(parts, axis=1)
     _check(got, want)
+    # the pipelined entry gives the same records (three calls in flight over two slots)
+    eng.reset()
+    outs = [np.empty((N, n, 138), np.float32) for n in (12, 12, 12)]
+    ins = [(np.ascontiguousarray(clean[:, k * 12 * 480:(k + 1) * 12 * 480]), np.ascontiguousarray(noisy[:, k * 12 * 480:(k + 1) * 12 * 480])) for k in range(3)]
+    for (c, y), o in zip(ins, outs):
+        rc = eng.L.pnb_submit_train_records(eng.h, c.ctypes.data, c.shape[1], y.ctypes.data, y.shape[1], 12, o.ctypes.data, 12 * 138)
+        assert rc == 0, eng.L.pnb_last_error()
+    assert eng.L.pnb_wait(eng.h) == 0
+    assert same_bits(np.concatenate(outs, axis=1), got)
     # reset gives the same records again
     eng.reset()
     again = eng.train_records(clean[:, :16 * 480], noisy[:, :16 * 480])
