@@ -225,47 +225,6 @@ __device__ void band_pool_warp(const float *vf, const float *vo, float *out, con
   __syncwarp(mask);
 }
 
-// pitch.cpp:46-104 (float build): best two lags by xcorr^2/Syy with the reference's update rule.
-// y has element stride `ys` in shared memory.  Runs on one lane.
-// dsyy[i] = y[i+len]^2 - y[i]^2 has been precomputed by the whole warp (same expression as the reference's
-// running update), so the serial part is one add and one max per lag.
-__device__ void best_two(const float *xcorr, const float *dsyy, int max_pitch, float syy, int &b0, int &b1) {
-  // Operands come four lags per 128-bit load (xcorr and dsyy are 16-byte aligned); the update rule is the
-  // reference's, one lag at a time.  On one lane the cost is the instruction count, so nothing is computed for a
-  // lag before its sign test.
-  float num0 = -1.f, num1 = -1.f, den0 = 0.f, den1 = 0.f;
-  b0 = 0;
-  b1 = 1;
-#define PNB_BEST_STEP(XC, D, I)                              \
-  do {                                                       \
-    if ((XC) > 0.f) {                                        \
-      const float c_ = (XC) * 1e-12f;                        \
-      const float num_ = c_ * c_;                            \
-      if (num_ * den1 > num1 * syy) {                        \
-        if (num_ * den0 > num0 * syy) {                      \
-          num1 = num0; den1 = den0; b1 = b0;                 \
-          num0 = num_; den0 = syy; b0 = (I);                 \
-        } else {                                             \
-          num1 = num_; den1 = syy; b1 = (I);                 \
-        }                                                    \
-      }                                                      \
-    }                                                        \
-    syy = syy + (D);                                         \
-    syy = 1.f > syy ? 1.f : syy;                             \
-  } while (0)
-  int i = 0;
-  for (; i + 4 <= max_pitch; i += 4) {
-    const float4 x4 = *reinterpret_cast<const float4 *>(xcorr + i);
-    const float4 d4 = *reinterpret_cast<const float4 *>(dsyy + i);
-    PNB_BEST_STEP(x4.x, d4.x, i);
-    PNB_BEST_STEP(x4.y, d4.y, i + 1);
-    PNB_BEST_STEP(x4.z, d4.z, i + 2);
-    PNB_BEST_STEP(x4.w, d4.w, i + 3);
-  }
-  for (; i < max_pitch; i++) PNB_BEST_STEP(xcorr[i], dsyy[i], i);
-#undef PNB_BEST_STEP
-}
-
 // Sequential dot product s + sum_j a[j] b[j] (ascending j, multiply then add -- the reference's order) with the
 // `a` operand fetched four at a time: `a` is the operand that is common to (almost) all lanes, so its 128-bit load
 // is a single shared-memory wavefront per four steps.  a must be 16-byte aligned, n a multiple of 4.
@@ -281,58 +240,51 @@ __device__ __forceinline__ float seq_dot4(const float *a, const float *b, int n,
   return s;
 }
 
-// The fine search leaves xcorr at zero except within +-2 of 2*b0 and 2*b1 (pitch.cpp:344-361); zero entries can
-// never become candidates (pitch.cpp:73), so between the two windows only the running energy is advanced.
-__device__ void best_two_sparse(const float *xcorr, const float *dsyy, int max_pitch, float syy, int w0, int w1,
-                                int &b0, int &b1) {
-  float num0 = -1.f, num1 = -1.f, den0 = 0.f, den1 = 0.f;
-  b0 = 0;
-  b1 = 1;
-  int lo_a = w0 < w1 ? w0 : w1, lo_b = w0 < w1 ? w1 : w0;
-  int i = 0;
-#pragma unroll 1
-  for (int seg = 0; seg < 2; seg++) {
-    int lo = seg == 0 ? lo_a : lo_b;
-    lo = lo < i ? i : lo;
-    lo = lo > max_pitch ? max_pitch : lo;
-    int hi = (seg == 0 ? lo_a : lo_b) + 5;
-    hi = hi < lo ? lo : hi;
-    hi = hi > max_pitch ? max_pitch : hi;
-    // no candidates here: only the running energy advances (four steps per 128-bit load once aligned)
-    for (; i < lo && (i & 3); i++) {
-      syy = syy + dsyy[i];
-      syy = 1.f > syy ? 1.f : syy;
-    }
-    for (; i + 4 <= lo; i += 4) {
-      const float4 d4 = *reinterpret_cast<const float4 *>(dsyy + i);
-      syy = syy + d4.x; syy = 1.f > syy ? 1.f : syy;
-      syy = syy + d4.y; syy = 1.f > syy ? 1.f : syy;
-      syy = syy + d4.z; syy = 1.f > syy ? 1.f : syy;
-      syy = syy + d4.w; syy = 1.f > syy ? 1.f : syy;
-    }
-    for (; i < lo; i++) {
-      syy = syy + dsyy[i];
-      syy = 1.f > syy ? 1.f : syy;
-    }
-    for (; i < hi; i++) {
-      float xc = xcorr[i];
-      if (xc > 0.f) {
-        float c = xc * 1e-12f;
-        float num = c * c;
-        if (num * den1 > num1 * syy) {
-          if (num * den0 > num0 * syy) {
-            num1 = num0; den1 = den0; b1 = b0;
-            num0 = num;  den0 = syy;  b0 = i;
-          } else {
-            num1 = num; den1 = syy; b1 = i;
-          }
-        }
-      }
-      syy = syy + dsyy[i];
-      syy = 1.f > syy ? 1.f : syy;
-    }
+// ---- find_best_pitch (pitch.cpp:46-104) with the lags spread over the lanes -------------------------------
+// The reference walks the lags in order, keeping the best two by xcorr^2/Syy under a cross-multiplied test whose
+// outcome depends on the state left by the earlier lags.  The running energy Syy of every lag does NOT depend on
+// that state, so (1) one lane runs the energy recurrence and leaves the energy each lag is tested with in place of
+// the deltas, (2) every lane forms its lag's numerator, (3) all lanes test their lag against the current state at
+// once; the lowest passing lag is exactly the next lag the sequential walk would have accepted (all lower ones
+// fail against the very state they would have met), its update is applied, the higher lags are tested again, and
+// so on until none passes.  Same comparisons on the same operands as the reference, a handful of rounds instead
+// of one dependent step per lag.
+struct Best2 {
+  float num0, num1, den0, den1;
+  int b0, b1;
+};
+__device__ __forceinline__ Best2 best2_init() { return Best2{-1.f, -1.f, 0.f, 0.f, 0, 1}; }
+
+// in place: d[i] (energy delta of lag i) -> energy lag i is tested with; n4 = number of lags rounded up to 4
+__device__ __forceinline__ void energy_chain(float *d, int n4, float syy) {
+  for (int i = 0; i < n4; i += 4) {
+    const float4 d4 = *reinterpret_cast<const float4 *>(d + i);
+    float4 e;
+    e.x = syy; syy = syy + d4.x; syy = 1.f > syy ? 1.f : syy;
+    e.y = syy; syy = syy + d4.y; syy = 1.f > syy ? 1.f : syy;
+    e.z = syy; syy = syy + d4.z; syy = 1.f > syy ? 1.f : syy;
+    e.w = syy; syy = syy + d4.w; syy = 1.f > syy ? 1.f : syy;
+    *reinterpret_cast<float4 *>(d + i) = e;
   }
-  // the energy after the last window is never used again
+}
+
+// lanes hold candidates in ascending lag order (lane order); wlane = lane id within the warp
+__device__ __forceinline__ void best2_rounds(Best2 &S, bool alive, float num, float e, int idx, unsigned mask, int wlane) {
+  while (true) {
+    const bool pass = alive && (num * S.den1 > S.num1 * e);
+    const unsigned m = __ballot_sync(mask, pass);
+    if (!m) break;
+    const int f = __ffs(m) - 1;
+    const float nf = __shfl_sync(mask, num, f), ef = __shfl_sync(mask, e, f);
+    const int jf = __shfl_sync(mask, idx, f);
+    if (nf * S.den0 > S.num0 * ef) {
+      S.num1 = S.num0; S.den1 = S.den0; S.b1 = S.b0;
+      S.num0 = nf; S.den0 = ef; S.b0 = jf;
+    } else {
+      S.num1 = nf; S.den1 = ef; S.b1 = jf;
+    }
+    alive = alive && (wlane > f);
+  }
 }
 
 __device__ __forceinline__ float pitch_gain(float xy, float xx, float yy) {
@@ -623,10 +575,19 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
         float syy_c = __shfl_sync(mask, acc[0], CF::kLagLanes, L);
         __syncwarp(mask);
         ANA_TICK(6);
-        b0 = 0; b1 = 0;
-        if (lane == 0) best_two(W.xc, W.p.yy, 147, syy_c, b0, b1);
-        b0 = __shfl_sync(mask, b0, 0, L);
-        b1 = __shfl_sync(mask, b1, 0, L);
+        if (lane == 0) energy_chain(W.p.yy, 148, syy_c);
+        __syncwarp(mask);
+        {
+          Best2 S = best2_init();
+          for (int base = 0; base < 147; base += L) {
+            const int i = base + lane;
+            const bool valid = i < 147;
+            const float xv = valid ? W.xc[i] : 0.f, ev = valid ? W.p.yy[i] : 1.f;
+            const float c = xv * 1e-12f;
+            best2_rounds(S, valid && xv > 0.f, c * c, ev, i, mask, wlane);
+          }
+          b0 = S.b0; b1 = S.b1;
+        }
         __syncwarp(mask);
         ANA_TICK(7);
       }
@@ -660,9 +621,34 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
       int off = 0;
       float corr = 0.f;
       pitch_lag = 0;
+      // second find_best_pitch (pitch.cpp:362): xcorr is zero outside the two windows and zero entries are never
+      // candidates (pitch.cpp:73), so only the (at most ten) window lags are tested; the energy recurrence still
+      // runs from lag 0 up to the end of the later window
+      int c0;
+      {
+        const int w0 = 2 * b0 - 2, w1 = 2 * b1 - 2;
+        const int lo_a = w0 < w1 ? w0 : w1, lo_b = w0 < w1 ? w1 : w0;
+        int loA = lo_a < 0 ? 0 : lo_a;
+        loA = loA > 294 ? 294 : loA;
+        int hiA = lo_a + 5;
+        hiA = hiA < loA ? loA : hiA;
+        hiA = hiA > 294 ? 294 : hiA;
+        int loB = lo_b < hiA ? hiA : lo_b;
+        loB = loB > 294 ? 294 : loB;
+        int hiB = lo_b + 5;
+        hiB = hiB < loB ? loB : hiB;
+        hiB = hiB > 294 ? 294 : hiB;
+        if (lane == 0) energy_chain(W.p.yy, (hiB + 3) & ~3, syy_f);
+        __syncwarp(mask);
+        const int idx = lane < 5 ? loA + lane : loB + (lane - 5);
+        const bool valid = lane < 5 ? idx < hiA : (lane < 10 && idx < hiB);
+        const float xv = valid ? W.xc[idx] : 0.f, ev = valid ? W.p.yy[idx] : 1.f;
+        const float c = xv * 1e-12f;
+        Best2 S = best2_init();
+        best2_rounds(S, valid && xv > 0.f, c * c, ev, idx, mask, wlane);
+        c0 = S.b0;
+      }
       if (lane == 0) {
-        int c0, c1;
-        best_two_sparse(W.xc, W.p.yy, 294, syy_f, 2 * b0 - 2, 2 * b1 - 2, c0, c1);
         if (c0 > 0 && c0 < 293) {
           float a = W.xc[c0 - 1], b = W.xc[c0], cc = W.xc[c0 + 1];
           if ((cc - a) > .7f * (b - a)) off = 1;
