@@ -249,6 +249,14 @@ __device__ __forceinline__ float seq_dot4(const float *a, const float *b, int n,
 // fail against the very state they would have met), its update is applied, the higher lags are tested again, and
 // so on until none passes.  Same comparisons on the same operands as the reference, a handful of rounds instead
 // of one dependent step per lag.
+// max(a, b) that returns NaN when a is NaN, like the reference's MAX32(b, a) = (b > a ? b : a) with a constant b:
+// one FMNMX instead of a compare and a select
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
 struct Best2 {
   float num0, num1, den0, den1;
   int b0, b1;
@@ -260,10 +268,10 @@ __device__ __forceinline__ void energy_chain(float *d, int n4, float syy) {
   for (int i = 0; i < n4; i += 4) {
     const float4 d4 = *reinterpret_cast<const float4 *>(d + i);
     float4 e;
-    e.x = syy; syy = syy + d4.x; syy = 1.f > syy ? 1.f : syy;
-    e.y = syy; syy = syy + d4.y; syy = 1.f > syy ? 1.f : syy;
-    e.z = syy; syy = syy + d4.z; syy = 1.f > syy ? 1.f : syy;
-    e.w = syy; syy = syy + d4.w; syy = 1.f > syy ? 1.f : syy;
+    e.x = syy; syy = max_nan(syy + d4.x, 1.f);
+    e.y = syy; syy = max_nan(syy + d4.y, 1.f);
+    e.z = syy; syy = max_nan(syy + d4.z, 1.f);
+    e.w = syy; syy = max_nan(syy + d4.w, 1.f);
     *reinterpret_cast<float4 *>(d + i) = e;
   }
 }
@@ -294,6 +302,7 @@ __device__ __forceinline__ float pitch_gain(float xy, float xx, float yy) {
 constexpr int kAcHops = 8;  // hops whose pitch_downsample autocorrelations are computed together
 struct PitchSmem {
   float lp[kLp];       // decimated, whitened pitch buffer
+  float sq[kLp];       // lp[i]^2: the terms of every running energy (find_best_pitch, yy_lookup)
   float yy[392];       // yy_lookup of remove_doubling (385 used); before that the energy deltas of the lag scans
   float cand_xy[32];   // per-candidate cross products of remove_doubling
 };
@@ -529,6 +538,7 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
         sum = sum + fir4 * m4;
         __syncwarp(mask);
         W.p.lp[i] = sum;
+        W.p.sq[i] = sum * sum;
         __syncwarp(mask);
       }
     }
@@ -569,8 +579,7 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
         }
         // energy deltas of the coarse scan: y4[i+240]^2 - y4[i]^2 (pitch.cpp:101)
         for (int i = lane; i < 147; i += L) {
-          float yn = W.p.lp[2 * (i + 240)], yo = W.p.lp[2 * i];
-          W.p.yy[i] = yn * yn - yo * yo;
+          W.p.yy[i] = W.p.sq[2 * (i + 240)] - W.p.sq[2 * i];
         }
         float syy_c = __shfl_sync(mask, acc[0], CF::kLagLanes, L);
         __syncwarp(mask);
@@ -595,8 +604,7 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
       // second find_best_pitch, lane 11 the xx of remove_doubling (pitch.cpp:448)
       for (int i = lane; i < 294; i += L) {
         W.xc[i] = 0.f;
-        float yn = W.p.lp[i + 480], yo = W.p.lp[i];  // energy deltas of the fine scan
-        W.p.yy[i] = yn * yn - yo * yo;
+        W.p.yy[i] = W.p.sq[i + 480] - W.p.sq[i];  // energy deltas of the fine scan
       }
       __syncwarp(mask);
       int fl = -1;
@@ -690,19 +698,21 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
         // all lanes meet here before the 480-step loops: without it the lanes whose lag needed no division run the
         // dot loop ahead of the candidate lanes and the loop is executed once per group
         __syncwarp(mask);
+        // the energy table is read only at the lags of roles 0 and 2..29 (T0, T1, T1b): the recurrence stops there
+        const int max_lag = (L == 32) ? __reduce_max_sync(mask, role < 30 ? lag : -1) : 384;  // (all roles in one pass)
         if (role == 1) {
           // yy_lookup recurrence (pitch.cpp:449-455), strictly sequential; operands fetched four at a time.
           // Table entry i is stored at W.p.yy[i + 3] so that groups of four are 16-byte aligned.
           float yy = xx;
           W.p.yy[3] = xx;
-          for (int i = 1; i <= 384; i += 4) {
-            const float4 a = *reinterpret_cast<const float4 *>(x - i - 3);        // x[-i-3 .. -i]
-            const float4 b = *reinterpret_cast<const float4 *>(x + 480 - i - 3);  // x[480-i-3 .. 480-i]
+          for (int i = 1; i <= max_lag; i += 4) {
+            const float4 a = *reinterpret_cast<const float4 *>(W.p.sq + 384 - i - 3);  // x[-i-3 .. -i]^2
+            const float4 b = *reinterpret_cast<const float4 *>(W.p.sq + 864 - i - 3);  // x[480-i-3 .. 480-i]^2
             float4 o;
-            yy = yy + a.w * a.w - b.w * b.w; o.x = 0.f > yy ? 0.f : yy;
-            yy = yy + a.z * a.z - b.z * b.z; o.y = 0.f > yy ? 0.f : yy;
-            yy = yy + a.y * a.y - b.y * b.y; o.z = 0.f > yy ? 0.f : yy;
-            yy = yy + a.x * a.x - b.x * b.x; o.w = 0.f > yy ? 0.f : yy;
+            yy = yy + a.w - b.w; o.x = max_nan(yy, 0.f);
+            yy = yy + a.z - b.z; o.y = max_nan(yy, 0.f);
+            yy = yy + a.y - b.y; o.z = max_nan(yy, 0.f);
+            yy = yy + a.x - b.x; o.w = max_nan(yy, 0.f);
             *reinterpret_cast<float4 *>(&W.p.yy[i + 3]) = o;
           }
         } else {
