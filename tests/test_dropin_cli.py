@@ -41,8 +41,13 @@ def test_dropin_cli_on_gpu(tmp_path):
     from percepnet_b200.synth import synth_pcm, to_int16
     x16 = to_int16(synth_pcm(1, 60, seed=2024)[0])
     ref_out, ref_gr = _run(REF_BIN, x16, str(tmp_path / "ref"))
-    out, gr = _run(B200_BIN, x16, str(tmp_path / "b200"))
-    assert out.shape == ref_out.shape == ((60 - 1) * 480,)          # first hop dropped, src/main.cpp:37-38
-    assert np.abs(out.astype(np.int32) - ref_out.astype(np.int32)).max() <= 1
-    rel = np.abs(gr - ref_gr) / np.maximum(np.abs(ref_gr), 1e-6)
-    assert rel.max() < 1e-4
+    for nn in ("fp32", "tensor"):                                    # PNB_SHIM_NN selects the shim's network path
+        os.environ["PNB_SHIM_NN"] = nn
+        try:
+            out, gr = _run(B200_BIN, x16, str(tmp_path / f"b200_{nn}"))
+        finally:
+            del os.environ["PNB_SHIM_NN"]
+        assert out.shape == ref_out.shape == ((60 - 1) * 480,)      # first hop dropped, src/main.cpp:37-38
+        assert np.abs(out.astype(np.int32) - ref_out.astype(np.int32)).max() <= 1, nn
+        rel = np.abs(gr - ref_gr) / np.maximum(np.abs(ref_gr), 1e-6)
+        assert rel.max() < 1e-4, nn
