@@ -83,5 +83,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_timing() -> str:
+    """libpercepnet_b200_timing.so: the same library with -DPNB_ANA_TIMING in pnb_dsp.cu (per-section cycle
+    accounting of analysis_kernel, read by tools/analysis_sections.py).  Debug aid, not loaded by the product."""
+    build()
+    nvcc = _nvcc()
+    obj = os.path.join(OBJ, "pnb_dsp_timing.o")
+    out = os.path.join(HERE, "libpercepnet_b200_timing.so")
+    subprocess.run([nvcc, *ARCH, *COMMON, *SOURCES["pnb_dsp.cu"], "-DPNB_ANA_TIMING", "-c", os.path.join(CSRC, "pnb_dsp.cu"),
+                    "-o", obj], check=True, capture_output=True)
+    others = [os.path.join(OBJ, f.replace(".cu", ".o")) for f in SOURCES if f != "pnb_dsp.cu"]
+    subprocess.run([nvcc, *ARCH, "-shared", "-cudart", "static", "-o", out, obj, *others], check=True, capture_output=True)
+    return out
+
+
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    if "--timing" in sys.argv:
+        print(build_timing())
+    else:
+        build(force="--force" in sys.argv, verbose=True)

@@ -938,7 +938,6 @@ __global__ void __launch_bounds__(kSynWarps * 32) synthesis_kernel(SynthesisArgs
     const long c = A.hop0 + t;
     const int slot_x = (int)(((c - 5) % A.ring + A.ring) % A.ring);
     const float2 *Xg = A.zring + ((size_t)slot_x * A.n_streams + s) * kBins, *Pg = A.P + fs * kBins;
-    const float scale = 1.f / kWin;
     // bins 0..399 and their mirror images; everything from 400 to 560 is zero
     {
       const float *frac = B.frac, *omf = B.omf;

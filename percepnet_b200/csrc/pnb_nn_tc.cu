@@ -63,13 +63,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
-      : "memory");
-}
 // ---- CTA-pair (cta_group::2) forms: the two CTAs of a cluster act as one M = 256 tensor-core unit ----
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> the leader's copy
 __device__ __forceinline__ uint32_t cluster_ctarank() {

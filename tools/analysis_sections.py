@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-section cycle shares of analysis_kernel, from a -DPNB_ANA_TIMING build of pnb_dsp.cu
-(percepnet_b200/libpercepnet_b200_timing.so; see the commands at the top of profiles/r1_analysis_sections.md)."""
+(percepnet_b200/libpercepnet_b200_timing.so, built by `python percepnet_b200/build.py --timing`)."""
 import ctypes as C
 import json
 import os
