@@ -153,7 +153,8 @@ const char *pnb_kernel_class_name(int cls);
 
 /* Number of kernels this library has launched on behalf of e since creation. */
 long long pnb_launch_count(const pnb_engine *e);
-/* Kernel launches one pnb_process_* call with n_frames hops issues. */
+/* Kernel launches one pnb_process_* call with n_frames hops issues (one more on the calls that also move the
+ * streams' history back to the start of their rows, at most every call, typically every eighth). */
 int pnb_launches_per_call(const pnb_engine *e, int n_frames);
 
 int pnb_n_streams(const pnb_engine *e);

@@ -16,6 +16,7 @@ constexpr int kBins = 400;         // bins below the last ERB border; bins 400..
 constexpr int kOffAnalysis = 2400; // analysis window   = line[2400 .. 3360)   
 constexpr int kOffPitch = 1632;    // pitch buffer      = line[1632 .. 3360)
 constexpr int kOffLook = 4800;     // look-ahead window = line[4800 .. 5760)
+constexpr int kLineCalls = 8;      // at most this many calls between two moves of the history to the start of its row
 constexpr int kLp = 864;           // decimated pitch buffer length
 constexpr int kMaxPeriod = 768, kMinPeriod = 60;
 

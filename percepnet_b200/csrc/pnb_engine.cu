@@ -209,7 +209,10 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
   }
 
   // stream state
-  e->pcm_stride = kKeep + F * kFrame;
+  // room for several calls' hops behind the history (advance_line): eight calls when calls are short, fewer
+  // when one call already carries many hops (the move is then amortised over those hops anyway)
+  const size_t line_calls = F >= 128 ? 1 : (128 / F > (size_t)kLineCalls ? (size_t)kLineCalls : 128 / F);
+  e->pcm_stride = kKeep + line_calls * F * kFrame;
   CKD(dalloc(&e->d_pcm, S * e->pcm_stride));
   CKD(dalloc(&e->d_synth, S * kFrame));
   CKD(dalloc(&e->d_last_period, S));
@@ -297,6 +300,7 @@ extern "C" int pnb_reset(pnb_engine *e) {
   CK(cudaDeviceSynchronize());
   const size_t S = e->S;
   CK(cudaMemset(e->d_pcm, 0, S * e->pcm_stride * sizeof(float)));
+  e->line_off = 0;
   CK(cudaMemset(e->d_synth, 0, S * kFrame * sizeof(float)));
   CK(cudaMemset(e->d_zring, 0, (size_t)e->ring * S * kBins * sizeof(float2)));
   CK(cudaMemset(e->d_ering, 0, (size_t)e->ring * S * kBands * sizeof(float)));
@@ -454,6 +458,17 @@ static int nn_step_f32(pnb_engine *e, int t, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
+// The next call's window starts n_frames*480 samples further on; when it would not fit any more, the last 5280
+// samples are moved back to the start of the rows.  Returns the number of launches.
+static int advance_line(pnb_engine *e, int F, cudaStream_t st) {
+  e->line_off += (size_t)F * kFrame;
+  if (e->line_off + kKeep + (size_t)e->Fmax * kFrame <= e->pcm_stride) return 0;
+  ProfScope ps(e, PNB_K_SLIDE, st);
+  int n = launch_slide_history(e->d_pcm, e->pcm_stride, e->S, (int)e->line_off, st);
+  e->line_off = 0;
+  return n;
+}
+
 static int process_device(pnb_engine *e, const float *d_in, const short *d_in16, size_t in_stride, float *d_out,
                           short *d_out16, size_t out_stride, int F, float *d_gr, cudaStream_t st) {
   if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
@@ -465,9 +480,10 @@ static int process_device(pnb_engine *e, const float *d_in, const short *d_in16,
   CK(cudaSetDevice(e->device));
   const int S = e->S;
   long long n = 0;
-  { ProfScope ps(e, PNB_K_STAGE_IN, st); n += launch_stage_in(e->d_pcm, e->pcm_stride, d_in, d_in16, in_stride, S, F * kFrame, st); }
+  float *line = e->d_pcm + e->line_off;  // this call's [history | new hops] window of every row
+  { ProfScope ps(e, PNB_K_STAGE_IN, st); n += launch_stage_in(line, e->pcm_stride, d_in, d_in16, in_stride, S, F * kFrame, st); }
   AnalysisArgs a;
-  a.pcm = e->d_pcm; a.pcm_stride = e->pcm_stride; a.n_streams = S; a.n_frames = F; a.tab = e->d_tab;
+  a.pcm = line; a.pcm_stride = e->pcm_stride; a.n_streams = S; a.n_frames = F; a.tab = e->d_tab;
   a.feat = e->d_feat; a.zring = e->d_zring; a.ering = e->d_ering; a.ring = e->ring; a.hop0 = e->hop;
   a.P = e->d_P; a.Ex = e->d_Ex; a.raw = nullptr; a.silence = e->d_sil;
   a.last_period = e->d_last_period; a.last_gain = e->d_last_gain;
@@ -497,7 +513,7 @@ static int process_device(pnb_engine *e, const float *d_in, const short *d_in16,
   s.tab = e->d_tab; s.synth_mem = e->d_synth; s.out = d_out; s.out16 = d_out16; s.out_stride = out_stride;
   s.postfilter = (e->flags & PNB_POSTFILTER) ? 1 : 0;
   { ProfScope ps(e, PNB_K_SYNTHESIS, st); n += launch_synthesis(s, st); }
-  { ProfScope ps(e, PNB_K_SLIDE, st); n += launch_slide_history(e->d_pcm, e->pcm_stride, S, F * kFrame, st); }
+  n += advance_line(e, F, st);
   if (d_gr) CK(cudaMemcpyAsync(d_gr, e->d_gr, (size_t)F * S * 68 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   CK(cudaGetLastError());
   e->hop += F;
@@ -534,13 +550,14 @@ extern "C" int pnb_train_records_device(pnb_engine *e, const short *d_speech, si
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int S = e->S, N = S / 2;
   long long n = 0;
+  float *line = e->d_pcm + e->line_off;
   {
     ProfScope ps(e, PNB_K_STAGE_IN, st);
-    n += launch_stage_in(e->d_pcm, e->pcm_stride, nullptr, d_noisy, noisy_stride, N, F * kFrame, st, 1.f);
-    n += launch_stage_in(e->d_pcm + (size_t)N * e->pcm_stride, e->pcm_stride, nullptr, d_speech, speech_stride, N, F * kFrame, st, 1.f);
+    n += launch_stage_in(line, e->pcm_stride, nullptr, d_noisy, noisy_stride, N, F * kFrame, st, 1.f);
+    n += launch_stage_in(line + (size_t)N * e->pcm_stride, e->pcm_stride, nullptr, d_speech, speech_stride, N, F * kFrame, st, 1.f);
   }
   AnalysisArgs a;
-  a.pcm = e->d_pcm; a.pcm_stride = e->pcm_stride; a.n_streams = S; a.n_frames = F; a.tab = e->d_tab;
+  a.pcm = line; a.pcm_stride = e->pcm_stride; a.n_streams = S; a.n_frames = F; a.tab = e->d_tab;
   a.feat = e->d_feat; a.zring = e->d_zring; a.ering = e->d_ering; a.ring = e->ring; a.hop0 = e->hop;
   a.P = nullptr; a.Ex = e->d_Ex; a.raw = e->d_raw; a.silence = e->d_sil;
   a.last_period = e->d_last_period; a.last_gain = e->d_last_gain;
@@ -550,7 +567,7 @@ extern "C" int pnb_train_records_device(pnb_engine *e, const short *d_speech, si
   l.feat = e->d_feat; l.raw = e->d_raw; l.Ex = e->d_Ex; l.tab = e->d_tab; l.n_pairs = N; l.n_frames = F;
   l.records = d_records; l.pair_stride = records_stride;
   { ProfScope ps(e, PNB_K_LABELS, st); n += launch_train_labels(l, st); }
-  { ProfScope ps(e, PNB_K_SLIDE, st); n += launch_slide_history(e->d_pcm, e->pcm_stride, S, F * kFrame, st); }
+  n += advance_line(e, F, st);
   CK(cudaGetLastError());
   e->hop += F;
   e->last_frames = F;
@@ -841,8 +858,9 @@ extern "C" void pnb_model_free(pnb_model *m) {
 extern "C" long long pnb_launch_count(const pnb_engine *e) { return e ? e->launches : 0; }
 extern "C" int pnb_launches_per_call(const pnb_engine *e, int n_frames) {
   if (!e) return 0;
-  if (e->flags & PNB_NN_TENSOR) return 4 + tc_launches_per_call(e) + tc_launches_per_step(e) * n_frames;
-  return 4 + 25 * n_frames;
+  // without the history move of advance_line (at most one more launch per call)
+  if (e->flags & PNB_NN_TENSOR) return 3 + tc_launches_per_call(e) + tc_launches_per_step(e) * n_frames;
+  return 3 + 25 * n_frames;
 }
 extern "C" int pnb_n_streams(const pnb_engine *e) { return e ? e->S : 0; }
 extern "C" int pnb_max_frames(const pnb_engine *e) { return e ? e->Fmax : 0; }

@@ -20,8 +20,12 @@ struct pnb_engine {
   int act_fc = 0, act_conv1 = 0, act_conv2 = 0, act_gb = 0, act_rb = 0;
 
   // per-stream signal state
-  float *d_pcm = nullptr;  // [S][5280 + Fmax*480]: history then the call's hops
+  // [S][5280 + c*Fmax*480], c <= kLineCalls: each stream's history line.  A call appends its hops behind the history and
+  // the next call simply starts F*480 samples further on (line_off); only when the row is used up are the last
+  // 5280 samples moved back to its start, once every c calls instead of after every call.
+  float *d_pcm = nullptr;
   size_t pcm_stride = 0;
+  size_t line_off = 0;
   float *d_synth = nullptr;
   int *d_last_period = nullptr;
   float *d_last_gain = nullptr;

@@ -101,7 +101,8 @@ def test_dsp_taps_bit_exact_and_outputs(api, oracle, model0, scale):
     assert np.abs(out - ref_out).max() < 0.25 * lsb
     if scale != 1.0:
         assert sum(1 for s in range(S) for t in taps[s] if not t.silence) > 20   # comb-filter branch exercised
-    assert eng.launches == sum(eng.launches_per_call(n) for n in (8, 8, 4))
+    base = sum(eng.launches_per_call(n) for n in (8, 8, 4))
+    assert base <= eng.launches <= base + 3          # + the occasional move of the history lines
     eng.close()
 
 
