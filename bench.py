@@ -383,7 +383,7 @@ def main():
         step(W + i)
     ev1.record(stream)
     barrier()
-    launches = eng.launches - launches0                     # kernels launched inside the timed region (library counter)
+    launches = (eng.launches - launches0) * world           # kernels launched inside the timed region (library counter; every rank issues the same schedule)
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     from percepnet_b200.sharding import aggregate_throughput
