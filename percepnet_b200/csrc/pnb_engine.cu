@@ -604,6 +604,7 @@ template <typename T>
 static int process_host(pnb_engine *e, const T *in, size_t in_stride, T *out, size_t out_stride, int F, float *gr,
                         T **d_in_p, T **d_out_p) {
   if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  if (e->flags & PNB_TRAIN_DATA) return fail(PNB_ERR_ARG, "engine was created with PNB_TRAIN_DATA: use pnb_train_records_*");
   if (!in || !out) return fail(PNB_ERR_ARG, "input/output pointer is NULL");
   if (F < 1 || F > e->Fmax) return fail(PNB_ERR_ARG, "n_frames %d outside [1, %d]", F, e->Fmax);
   if (in_stride < (size_t)F * kFrame || out_stride < (size_t)F * kFrame)
@@ -641,6 +642,7 @@ extern "C" int pnb_process_host_i16(pnb_engine *e, const short *in, size_t in_st
 template <typename T>
 static int submit_host(pnb_engine *e, const T *in, size_t in_stride, T *out, size_t out_stride, int F) {
   if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  if (e->flags & PNB_TRAIN_DATA) return fail(PNB_ERR_ARG, "engine was created with PNB_TRAIN_DATA: use pnb_submit_train_records");
   if (!in || !out) return fail(PNB_ERR_ARG, "input/output pointer is NULL");
   if (F < 1 || F > e->Fmax) return fail(PNB_ERR_ARG, "n_frames %d outside [1, %d]", F, e->Fmax);
   if (in_stride < (size_t)F * kFrame || out_stride < (size_t)F * kFrame)

@@ -92,6 +92,8 @@ def test_train_mode_argument_checks(api, model0):
     eng = api.Engine(4, 4, None, api.TRAIN_DATA)
     with pytest.raises(api.PnbError):
         eng.process(np.zeros((4, 480), np.float32))                 # enhancement entry refused
+    z16 = np.zeros((4, 480), np.int16)
+    assert eng.L.pnb_submit_host_i16(eng.h, z16.ctypes.data, 480, z16.ctypes.data, 480, 1) != 0   # and its pipelined form
     with pytest.raises(api.PnbError):
         eng.train_records(np.zeros((2, 5 * 480), np.int16), np.zeros((2, 5 * 480), np.int16))   # > max_frames
     eng.close()
