@@ -265,3 +265,24 @@ def test_sixteen_lane_analysis_variant_matches(api, model0, tmp_path):
     for k in res["32"]:
         a, b = res["32"][k], res["16"][k]
         assert a.shape == b.shape and (np.array_equal(a, b) if a.dtype.kind == "i" else same_bits(a, b)), k
+
+
+def test_random_mixtures_batch(api, oracle, model0):
+    """48 seeded random streams (harmonics, noise, DC, silent gaps, clicks; amplitudes 1e-4 .. 1) in one batch:
+    DSP taps bit-exact, g/r and PCM within the bars."""
+    from util import random_mixtures
+    F = 18
+    x = random_mixtures(48, F)
+    eng = api.Engine(48, F, model0, api.NN_FP32 | api.KEEP_TAPS)
+    out, gr = eng.process(x, want_gr=True)
+    feats, pitch, ex = eng.read_tap("features", F), eng.read_tap("pitch", F), eng.read_tap("Ex", F)
+    eng.close()
+    ref_out, ref_gr, taps = _oracle_run(oracle, model0, x)
+    for s in range(48):
+        assert same_bits(feats[:, s], np.stack([t.np("features") for t in taps[s]])), s
+        assert same_bits(ex[:, s], np.stack([t.np("Ex") for t in taps[s]])), s
+        assert np.array_equal(pitch[:, s, 1], np.array([t.pitch_index for t in taps[s]])), s
+        assert np.array_equal(pitch[:, s, 2], np.array([t.silence for t in taps[s]])), s
+    rel = np.abs(gr - ref_gr) / np.maximum(np.abs(ref_gr), 1e-6)
+    assert rel.max() < GR_RTOL
+    assert _lsb_diff(out, ref_out, True) <= PCM_LSB
