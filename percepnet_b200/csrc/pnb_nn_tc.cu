@@ -41,6 +41,10 @@ constexpr int TM = 128;   // streams per tile (UMMA M)
 constexpr int BK = 32;    // k per pipeline stage: 64-byte rows, SWIZZLE_64B
 constexpr int HT = 64;    // hidden units per GRU tile
 constexpr int GRU_BN = 3 * HT;  // weight rows per GRU tile (z|r|n)
+// Epilogue warps per CTA: warp 4 + q + 4 k reads TMEM lane quadrant q; the kEpiSets warps of a quadrant share its
+// rows' columns 16 at a time.  The epilogue (gate math, splits, stores) is what a tile costs most, see DESIGN.md 3.2.
+constexpr int kEpiSets = 2;
+constexpr int kTcThreads = 32 * (4 + 4 * kEpiSets);
 constexpr int DENSE_BN = 256;   // output columns per dense (conv) tile: the widest MMA, least operand traffic per MAC
 constexpr int kConvTerms = 2;         // bf16 terms per operand on the conv layers (2: 16-bit operands, 3 products)
 constexpr float kActScale = 1024.f;  // fp16 activations are stored x 2^10 (keeps the low term normal)
@@ -175,6 +179,7 @@ struct TcArgs {
   int tiles_m, tiles_n; // tile grid; a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
   int b_term_rows;      // row distance between the split terms inside a packed weight matrix
   int fmt;              // 0 fp16, 1 bf16
+  int debug;            // timing diagnostics (PNB_TC_DEBUG): 1 = issue no MMA (operand streaming only), 2 = issue no TMA load
   float out_scale;      // 2^-(activation scale + weight scale)
   const float *tansig;  // 201-entry table (global)
   const float *bias;
@@ -236,7 +241,7 @@ __host__ __device__ constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 
 // the B operand traffic (global->shared and shared->tensor core), which is what bounds this kernel.
 // The accumulators are zeroed by the epilogue warps (tcgen05.st) so that every MMA accumulates.
 template <int NA, int NB, int BN, int STAGES, bool GRU>
-__global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__ TcArgs args) {
+__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_constant__ TcArgs args) {
   using SL = StageLayout<NA, NB, BN>;
   using PR = Products<NA, NB>;
   constexpr int kAccCols = GRU ? 4 * HT : pow2_cols(BN);  // TMEM columns per accumulator buffer
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }  // both CTAs' epilogues
+    for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * 128 * kEpiSets); }  // every epilogue thread of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
@@ -291,6 +296,10 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
           for (int kb = 0; kb < sg.k_blocks; kb++, it++) {
             const int st = it % STAGES;
             mbar_wait(&empty_bar[st], ((it / STAGES) & 1) ^ 1);  // fresh barrier: passes immediately
+            if (args.debug & 2) {  // diagnostic: the MMAs run on whatever the stage holds
+              if (crank == 0) mbar_expect_tx(&full_bar[st], 0);
+              continue;
+            }
             if (crank == 0) mbar_expect_tx(&full_bar[st], 2 * SL::kPairBytes);
             uint8_t *sp = stage_base + st * SL::kBytes;
 #pragma unroll
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
               for (int p = 0; p < PR::n; p++) {
                 const uint64_t ad = smem_desc_sw64(sa + PR::a(p) * SL::kABytes) + (uint64_t)(ks * 2);
                 const uint64_t bd = smem_desc_sw64(sb + PR::b(p) * SL::kBBytes) + (uint64_t)(ks * 2);
-                umma_f16(dcol, ad, bd, id_main, 1u);
+                if (!(args.debug & 1)) umma_f16(dcol, ad, bd, id_main, 1u);
               }
             }
             umma_commit(&empty_bar[st]);  // frees the stage in both CTAs once these MMAs have read it
@@ -342,7 +351,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
     }
   } else if (warp >= 4) {
     // ===== epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31, one stream per thread =====
-    const int wq = warp & 3;
+    const int wq = warp & 3, eset = (warp - 4) >> 2;
     const float sc = args.out_scale;
     int j = 0;
     for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta, j++) {
@@ -356,7 +365,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
       if (GRU) {
         const int H = args.H;
         const float *b = args.bias;
-        for (int c = 0; c < HT; c += 16) {
+        for (int c = 16 * eset; c < HT; c += 16 * kEpiSets) {
           float zs[16], rs[16], nx[16], nh[16];
           tmem_ld16(tlane + HT + c, zs);      // accumulator columns: [nx | z | r | nh]
           tmem_ld16(tlane + 2 * HT + c, rs);
@@ -398,7 +407,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
         }
       } else {
         const int N = args.N;
-        for (int c = 0; c < BN; c += 16) {
+        for (int c = 16 * eset; c < BN; c += 16 * kEpiSets) {
           float d[16];
           tmem_ld16(tlane + c, d);
           const int j0 = n_tile * BN + c;
@@ -451,7 +460,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const __grid_constant__
         }
       }
       // zero the buffer for its next tile and hand it back to the leader's MMA thread
-      for (int c = 0; c < kAccCols; c += 16) tmem_st16_zero(tlane + c);
+      for (int c = 16 * eset; c < kAccCols; c += 16 * kEpiSets) tmem_st16_zero(tlane + c);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive_leader(&acc_empty[buf]);
@@ -735,6 +744,8 @@ int tc_launches_per_call(const pnb_engine *) { return 3 + 2; }  // kernels only;
 
 template <int NA, int NB, int BN, int STAGES, bool GRU>
 static void tc_launch(pnb_engine *e, TcArgs &a, int rows, int tiles_n, cudaStream_t st) {
+  static const int dbg = getenv("PNB_TC_DEBUG") ? atoi(getenv("PNB_TC_DEBUG")) : 0;  // results are garbage when set
+  a.debug = dbg;
   a.M = rows;
   a.tiles_m = (rows + TM - 1) / TM;
   a.tiles_n = tiles_n;
@@ -743,7 +754,7 @@ static void tc_launch(pnb_engine *e, TcArgs &a, int rows, int tiles_n, cudaStrea
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = tc_smem_bytes<NA, NB, BN, STAGES>();
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
