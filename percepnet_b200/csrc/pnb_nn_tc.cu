@@ -744,7 +744,13 @@ int tc_launches_per_call(const pnb_engine *) { return 3 + 2; }  // kernels only;
 
 template <int NA, int NB, int BN, int STAGES, bool GRU>
 static void tc_launch(pnb_engine *e, TcArgs &a, int rows, int tiles_n, cudaStream_t st) {
-  static const int dbg = getenv("PNB_TC_DEBUG") ? atoi(getenv("PNB_TC_DEBUG")) : 0;  // results are garbage when set
+  // timing diagnostics only (profiles/README.md): with PNB_TC_DEBUG set the network's results are garbage
+  static const int dbg = [] {
+    const char *v = getenv("PNB_TC_DEBUG");
+    const int d = v ? atoi(v) : 0;
+    if (d) fprintf(stderr, "percepnet_b200: PNB_TC_DEBUG=%d -- network outputs are INVALID (timing diagnostics)\n", d);
+    return d;
+  }();
   a.debug = dbg;
   a.M = rows;
   a.tiles_m = (rows + TM - 1) / TM;
