@@ -111,3 +111,17 @@ def test_weight_blob_roundtrip(built, model0, tmp_path):
         api.BlobModel(path)
     out = subprocess.run(["nm", "-D", "--defined-only", built.SHIM], capture_output=True, text=True, check=True).stdout
     assert "_Z23rnnoise_model_from_fileP8_IO_FILE" in out and "_Z18rnnoise_model_freeP8RNNModel" in out
+
+
+def test_public_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: both headers must compile as strict C99 and as C++11 (no torch, no CUDA types)."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "percepnet_b200.h"\n#include "pnb_nnet_layout.h"\n'
+                   "int main(void) { pnb_engine *e = 0; (void)e; return (int)sizeof(pnb_model) > 0 ? 0 : 1; }\n")
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    subprocess.run([cxx, "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True)
+    hdr = open(os.path.join(inc, "percepnet_b200.h")).read()
+    assert "torch" not in hdr and "cuda_runtime" not in hdr
