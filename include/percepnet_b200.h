@@ -49,7 +49,12 @@ enum {
   PNB_ERR_ARG = -1,
   PNB_ERR_CUDA = -2,
   PNB_ERR_NO_DEVICE = -3,
-  PNB_ERR_ALLOC = -4
+  PNB_ERR_ALLOC = -4,
+  PNB_ERR_DOMAIN = -5  /* PNB_NN_TENSOR only: a pre-activation reached |x| >= 8.5e7, where the reference's tansig_approx
+                          (src/vec.h:63) overflows its float->int conversion (undefined behaviour; on x86 "tanh" returns
+                          its argument).  The tensor path does not reproduce that: outputs since the last pnb_reset are not
+                          the reference's.  Reported by the synchronising entry points (pnb_process_host_*, pnb_wait,
+                          pnb_check); sticky until pnb_reset.  The fp32 path (PNB_NN_FP32) follows the reference there too. */
 };
 
 /* pnb_create flags */
@@ -96,6 +101,9 @@ int pnb_process_host_i16(pnb_engine *e, const short *in, size_t in_stride, short
 int pnb_submit_host_f32(pnb_engine *e, const float *in, size_t in_stride, float *out, size_t out_stride, int n_frames);
 int pnb_submit_host_i16(pnb_engine *e, const short *in, size_t in_stride, short *out, size_t out_stride, int n_frames);
 int pnb_wait(pnb_engine *e);
+/* Waits for everything enqueued on the engine's internal streams and on `cuda_stream` (the stream the caller passed to
+ * pnb_process_device_*), then reports the engine's status: PNB_OK, PNB_ERR_DOMAIN, or PNB_ERR_CUDA. */
+int pnb_check(pnb_engine *e, void *cuda_stream);
 
 /* Device buffers on the engine's device; asynchronous on cuda_stream (a cudaStream_t, NULL = default
  * stream).  d_gr (NULL ok) as above, in device memory. */
@@ -123,6 +131,30 @@ int pnb_train_records_device(pnb_engine *e, const short *d_speech, size_t speech
                              size_t noisy_stride, int n_frames, float *d_records, size_t records_stride,
                              void *cuda_stream);
 
+/* Per-stream state for migration between engines / GPUs (the live part of the reference's DenoiseState + RNNState,
+ * src/denoise.cpp:71-85, src/nnet_data.h:28-38): input history, overlap-add memory, pitch continuity, the spectra the
+ * next five hops will analyse, conv histories and GRU states -- pnb_state_size() bytes, a flat host blob.
+ * Both calls wait for the engine to be idle.  A state taken from stream a of one engine and set on stream b of another
+ * (any batch size, either network mode, same model) continues the stream exactly where it left off: bit for bit between
+ * engines of the same mode.  PNB_TRAIN_DATA engines carry the signal part only. */
+size_t pnb_state_size(void);
+int pnb_get_state(pnb_engine *e, int stream, void *dst, size_t dst_bytes);
+int pnb_set_state(pnb_engine *e, int stream, const void *src, size_t src_bytes);
+
+/* The pitch analysis alone (BASELINE.json config 5; needs no engine): for each of n_units pitch buffers of 1728
+ * float samples (unit u at d_pitch_buf + u*stride; the reference's st->pitch_buf, src/denoise.cpp:80,405-411) runs
+ * pitch_downsample, pitch_search and remove_doubling (src/pitch.cpp:148-216, 283-386, 423-527) exactly as the hot path
+ * does, and writes the final period T in [60, 767], the raw pitch correlation (feature 69) and the pitch gain.
+ * d_prev_period / d_prev_gain (NULL = 0) are the previous frame's values remove_doubling's continuity test uses;
+ * d_lag (NULL ok) receives pitch_search's lag before the doubling check.  Asynchronous on cuda_stream, current device. */
+int pnb_pitch_only_device(const float *d_pitch_buf, size_t stride, long long n_units, const int *d_prev_period,
+                          const float *d_prev_gain, int *d_period, float *d_corr, float *d_gain, int *d_lag,
+                          void *cuda_stream);
+
+/* Host-buffer form (blocking): copies the buffers to the current device, runs the kernel, copies the results back. */
+int pnb_pitch_only_host(const float *pitch_buf, size_t stride, long long n_units, const int *prev_period,
+                        const float *prev_gain, int *period, float *corr, float *gain, int *lag);
+
 /* Per-frame intermediates of the LAST call (requires PNB_KEEP_TAPS); copies to host memory.
  * Layouts are [n_frames][n_streams][...]:                                                   */
 enum {
@@ -135,7 +167,8 @@ enum {
   PNB_TAP_GR = 6,       /* float[68]  g, r                                                    */
   /* network state after the last hop of the call, layout [n_streams][width] (no PNB_KEEP_TAPS needed): */
   PNB_TAP_NN_C2 = 7,    /* float[512] conv2 output                                            */
-  PNB_TAP_NN_H0 = 8     /* +0..4: float[512|128] states of gru1, gru2, gru3, gru_gb, gru_rb   */
+  PNB_TAP_NN_H0 = 8,    /* +0..4: float[512|128] states of gru1, gru2, gru3, gru_gb, gru_rb   */
+  PNB_TAP_G_USED = 13   /* float[34]  band gains as applied: g, post-filtered under PNB_POSTFILTER (PNB_KEEP_TAPS) */
 };
 int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes);
 

@@ -252,6 +252,32 @@ class Oracle:
         return g, r
 
 
+    def pitch_batch(self, bufs, n_threads=1):
+        """[n, 1728] pitch buffers -> (T int32 [n], corr [n], gain [n]) with zero previous period / gain"""
+        b, bp = _f(bufs)
+        n = b.shape[0]
+        T, corr, gain = np.empty(n, np.int32), np.empty(n, np.float32), np.empty(n, np.float32)
+        self.lib.pn_oracle_pitch_batch.argtypes = [F32P, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, I32P, F32P, F32P, C.c_int]
+        self.lib.pn_oracle_pitch_batch(bp, b.shape[1], n, None, None, T.ctypes.data_as(I32P), corr.ctypes.data_as(F32P),
+                                       gain.ctypes.data_as(F32P), n_threads)
+        return T, corr, gain
+
+    def rnn_f64(self, model, features):
+        """features [F, 70] of one stream -> (g [F, 34], r [F, 34] in float64, max |pre-activation| per frame):
+        the network in double precision from a zero state (pn_oracle_compute_rnn_f64)."""
+        feats = np.ascontiguousarray(features, dtype=np.float32)
+        F = feats.shape[0]
+        st = np.zeros(512 + 1024 + 4 * 512 + 128, np.float64)
+        g, r, mp = np.empty((F, 34), np.float64), np.empty((F, 34), np.float64), np.empty(F, np.float64)
+        D = C.POINTER(C.c_double)
+        self.lib.pn_oracle_compute_rnn_f64.restype = C.c_double
+        cm = model.as_c_model()
+        for t in range(F):
+            mp[t] = self.lib.pn_oracle_compute_rnn_f64(C.byref(cm), st.ctypes.data_as(D), g[t].ctypes.data_as(D),
+                                                       r[t].ctypes.data_as(D), feats[t].ctypes.data_as(F32P))
+        return g, r, mp
+
+
 class Reference:
     """The compiled, unmodified reference behind oracle/ref_harness.cpp."""
 

@@ -625,6 +625,125 @@ void pn_oracle_compute_rnn(const pnb_model *m, float *st, float *gains, float *s
   pn_oracle_dense_layer(m->fc_rb, strengths, hr);
 }
 
+/* the pitch analysis of n independent 1728-sample pitch buffers (denoise.cpp:404-414), OpenMP over units */
+void pn_oracle_pitch_batch(const float *bufs, size_t stride, int n, const int *prev_period, const float *prev_gain,
+                           int *T_out, float *corr_out, float *gain_out, int n_threads) {
+  int u;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(n_threads > 0 ? n_threads : 1) schedule(static)
+#endif
+  for (u = 0; u < n; u++) {
+    float lp[864], corr;
+    int pitch, T;
+    pn_oracle_pitch_downsample(bufs + (size_t)u * stride, lp);
+    pn_oracle_pitch_search(lp, &pitch, &corr, NULL, NULL);
+    T = 768 - pitch;
+    gain_out[u] = pn_oracle_remove_doubling(lp, &T, prev_period ? prev_period[u] : 0, prev_gain ? prev_gain[u] : 0.f);
+    T_out[u] = T;
+    corr_out[u] = corr;
+  }
+  (void)n_threads;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/*  The same network in double precision: the arbiter between two single-precision         */
+/*  evaluations (the reference's sequential fp32 sums and the GPU's split-operand tensor    */
+/*  products).  Same wiring (rnn.cpp:42-81), same tansig table and correction formula       */
+/*  (vec.h:53-71) evaluated in double.  Returns through *max_pre the largest |x| handed to  */
+/*  tansig_approx, so that a test can tell whether a frame stayed inside the domain in      */
+/*  which the reference's float->int conversion is defined (|x| < 8.6e7, vec.h:63).         */
+/* ------------------------------------------------------------------------------------ */
+static double tansig_d(double x, double *max_pre) {
+  double y, dy, sign = 1, fi;
+  int i;
+  build_tables();
+  if (x < 0) { x = -x; sign = -1; }
+  if (x > *max_pre) *max_pre = x;
+  fi = floor(.5 + 25 * x);
+  i = fi < 200 ? (int)fi : 200;
+  i = i > 0 ? i : 0;
+  x -= .04 * i;
+  y = (double)K.tansig[i];
+  dy = 1 - y * y;
+  y = y + x * dy * (1 - y * x);
+  return sign * y;
+}
+static void activate_d(double *v, int n, int act, double *mp) {
+  int i;
+  if (act == PNB_ACT_SIGMOID) for (i = 0; i < n; i++) v[i] = .5 + .5 * tansig_d(.5 * v[i], mp);
+  else if (act == PNB_ACT_TANH) for (i = 0; i < n; i++) v[i] = tansig_d(v[i], mp);
+  else if (act == PNB_ACT_RELU) for (i = 0; i < n; i++) v[i] = v[i] < 0 ? 0 : v[i];
+}
+static void gemv_acc_d(double *out, const float *W, int rows, int cols, int stride, const double *x) {
+  int i, j;
+  for (j = 0; j < cols; j++) {
+    double xj = x[j];
+    const float *w = W + (size_t)j * stride;
+    for (i = 0; i < rows; i++) out[i] += (double)w[i] * xj;
+  }
+}
+static void dense_d(const pnb_dense_layer *l, double *out, const double *in, double *mp) {
+  int N = l->nb_neurons, i;
+  for (i = 0; i < N; i++) out[i] = l->bias[i];
+  gemv_acc_d(out, l->input_weights, N, l->nb_inputs, N, in);
+  activate_d(out, N, l->activation, mp);
+}
+static void conv1d_d(const pnb_conv1d_layer *l, double *out, double *mem, const double *in, double *mp) {
+  int C = l->nb_inputs, Kt = l->kernel_size, N = l->nb_neurons, i;
+  double *cat = (double *)malloc((size_t)C * Kt * sizeof(double));
+  memcpy(cat, mem, (size_t)C * (Kt - 1) * sizeof(double));
+  memcpy(cat + C * (Kt - 1), in, C * sizeof(double));
+  for (i = 0; i < N; i++) out[i] = l->bias[i];
+  gemv_acc_d(out, l->input_weights, N, C * Kt, N, cat);
+  activate_d(out, N, l->activation, mp);
+  memcpy(mem, cat + C, (size_t)C * (Kt - 1) * sizeof(double));
+  free(cat);
+}
+static void gru_d(const pnb_gru_layer *l, double *h, const double *in, double *mp) {
+  int N = l->nb_neurons, M = l->nb_inputs, S = 3 * N, i;
+  double *z = (double *)malloc(4 * (size_t)N * sizeof(double)), *r = z + N, *c = r + N, *t = c + N;
+  const float *b = l->bias, *W = l->input_weights, *U = l->recurrent_weights;
+  for (i = 0; i < N; i++) z[i] = (double)b[i] + (double)b[3 * N + i];
+  gemv_acc_d(z, W, N, M, S, in);
+  gemv_acc_d(z, U, N, N, S, h);
+  activate_d(z, N, PNB_ACT_SIGMOID, mp);
+  for (i = 0; i < N; i++) r[i] = (double)b[N + i] + (double)b[4 * N + i];
+  gemv_acc_d(r, W + N, N, M, S, in);
+  gemv_acc_d(r, U + N, N, N, S, h);
+  activate_d(r, N, PNB_ACT_SIGMOID, mp);
+  for (i = 0; i < N; i++) { c[i] = b[2 * N + i]; t[i] = b[5 * N + i]; }
+  gemv_acc_d(t, U + 2 * N, N, N, S, h);
+  for (i = 0; i < N; i++) c[i] += t[i] * r[i];
+  gemv_acc_d(c, W + 2 * N, N, M, S, in);
+  activate_d(c, N, l->activation, mp);
+  for (i = 0; i < N; i++) h[i] = z[i] * h[i] + (1 - z[i]) * c[i];
+  free(z);
+}
+double pn_oracle_compute_rnn_f64(const pnb_model *m, double *st, double *gains, double *strengths, const float *feat) {
+  double f[PNO_FEATURES], d0[128], c1[512], c2[512], rb_in[1024], gb_in[2560], mp = 0.0;
+  double *m1 = st, *m2 = st + 512, *h1 = st + 1536, *h2 = h1 + 512, *h3 = h2 + 512, *hg = h3 + 512, *hr = hg + 512;
+  int i;
+  for (i = 0; i < PNO_FEATURES; i++) f[i] = feat[i];
+  dense_d(m->fc, d0, f, &mp);
+  conv1d_d(m->conv1, c1, m1, d0, &mp);
+  conv1d_d(m->conv2, c2, m2, c1, &mp);
+  gru_d(m->gru1, h1, c2, &mp);
+  gru_d(m->gru2, h2, h1, &mp);
+  gru_d(m->gru3, h3, h2, &mp);
+  gru_d(m->gru_gb, hg, h3, &mp);
+  memcpy(rb_in, h3, 512 * sizeof(double));
+  memcpy(rb_in + 512, c2, 512 * sizeof(double));
+  gru_d(m->gru_rb, hr, rb_in, &mp);
+  memcpy(gb_in, c2, 512 * sizeof(double));
+  memcpy(gb_in + 512, h1, 512 * sizeof(double));
+  memcpy(gb_in + 1024, h2, 512 * sizeof(double));
+  memcpy(gb_in + 1536, h3, 512 * sizeof(double));
+  memcpy(gb_in + 2048, hg, 512 * sizeof(double));
+  dense_d(m->fc_gb, gains, gb_in, &mp);
+  dense_d(m->fc_rb, strengths, hr, &mp);
+  return mp;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /*  Per-stream engine.  hist[] is the reference's comb_buf (denoise.cpp:77,388-389); its   */
 /*  pitch_buf and analysis_mem are windows of it:                     */

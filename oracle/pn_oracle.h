@@ -18,6 +18,7 @@
 #ifndef PN_ORACLE_H
 #define PN_ORACLE_H
 
+#include <stddef.h>
 #include "../include/pnb_nnet_layout.h"
 
 #ifdef __cplusplus
@@ -99,6 +100,16 @@ void pn_oracle_gru_layer(const pnb_gru_layer *l, float *state, const float *in);
 /* state block: [conv1 mem 512][conv2 mem 1024][gru1 512][gru2 512][gru3 512][gru_gb 512][gru_rb 128] */
 void pn_oracle_compute_rnn(const pnb_model *m, float *state, float *gains, float *strengths,
                            const float *features);                                               /* rnn.cpp:42 */
+
+/* pitch_downsample + pitch_search + remove_doubling on n independent pitch buffers (unit u at bufs + u*stride),
+ * OpenMP over units; prev_* NULL = 0 */
+void pn_oracle_pitch_batch(const float *bufs, size_t stride, int n, const int *prev_period, const float *prev_gain,
+                           int *T_out, float *corr_out, float *gain_out, int n_threads);
+/* The same network evaluated in double precision (same wiring, table and correction formula): the arbiter between
+ * two single-precision evaluations.  state: PNO_NN_STATE doubles, laid out like the float state block.  Returns the
+ * largest |x| handed to the tanh approximation in this frame (the reference's is defined for |x| < 8.6e7 only). */
+double pn_oracle_compute_rnn_f64(const pnb_model *m, double *state, double *gains, double *strengths,
+                                 const float *features);
 
 #ifdef __cplusplus
 }

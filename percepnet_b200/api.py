@@ -21,7 +21,8 @@ FRAME = 480
 NN_FP32, NN_TENSOR, POSTFILTER, KEEP_TAPS, TRAIN_DATA = 0, 1, 2, 4, 8
 RECORD = 138
 TAPS = {"features": (0, np.float32, 70), "pitch": (1, np.int32, 4), "pitchf": (2, np.float32, 2),
-        "X": (3, np.float32, 800), "P": (4, np.float32, 800), "Ex": (5, np.float32, 34), "gr": (6, np.float32, 68)}
+        "X": (3, np.float32, 800), "P": (4, np.float32, 800), "Ex": (5, np.float32, 34), "gr": (6, np.float32, 68),
+        "g_used": (13, np.float32, 34)}
 
 _lib = None
 
@@ -57,7 +58,13 @@ def load_library() -> C.CDLL:
     L.pnb_submit_host_f32.argtypes = [vp, vp, sz, vp, sz, i]
     L.pnb_submit_host_i16.argtypes = [vp, vp, sz, vp, sz, i]
     L.pnb_wait.argtypes = [vp]
+    L.pnb_check.argtypes = [vp, vp]
     L.pnb_read_tap.argtypes = [vp, i, vp, sz]
+    L.pnb_state_size.restype = sz
+    L.pnb_get_state.argtypes = [vp, i, vp, sz]
+    L.pnb_set_state.argtypes = [vp, i, vp, sz]
+    L.pnb_pitch_only_device.argtypes = [vp, sz, C.c_longlong, vp, vp, vp, vp, vp, vp, vp]
+    L.pnb_pitch_only_host.argtypes = [vp, sz, C.c_longlong, vp, vp, vp, vp, vp, vp]
     L.pnb_launch_count.argtypes = [vp]
     L.pnb_launch_count.restype = C.c_longlong
     L.pnb_launches_per_call.argtypes = [vp, i]
@@ -74,9 +81,36 @@ def load_library() -> C.CDLL:
 
 
 EXPORTS = ("pnb_create", "pnb_destroy", "pnb_reset", "pnb_process_host_f32", "pnb_process_host_i16",
-           "pnb_model_load_blob", "pnb_model_free", "pnb_train_records_host", "pnb_train_records_device", "pnb_submit_train_records", "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_wait",
-           "pnb_read_tap", "pnb_launch_count",
+           "pnb_model_load_blob", "pnb_model_free", "pnb_train_records_host", "pnb_train_records_device", "pnb_submit_train_records", "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_wait", "pnb_check",
+           "pnb_read_tap", "pnb_state_size", "pnb_get_state", "pnb_set_state", "pnb_pitch_only_device", "pnb_pitch_only_host", "pnb_launch_count",
            "pnb_launches_per_call", "pnb_profile_enable", "pnb_profile_read", "pnb_kernel_class_name", "pnb_n_streams", "pnb_max_frames", "pnb_last_error", "pnb_version")
+
+
+def pitch_only_device(d_buf: int, stride: int, n_units: int, d_period: int, d_corr: int, d_gain: int, d_lag: int = 0,
+                      d_prev_period: int = 0, d_prev_gain: int = 0, stream: int = 0):
+    """pnb_pitch_only_device on raw device pointers (BASELINE.json config 5: the pitch analysis alone)."""
+    L = load_library()
+    rc = L.pnb_pitch_only_device(d_buf, stride, n_units, d_prev_period or None, d_prev_gain or None, d_period, d_corr,
+                                 d_gain, d_lag or None, stream or None)
+    if rc != 0:
+        raise PnbError(f"pnb_pitch_only_device failed ({rc}): {L.pnb_last_error().decode()}")
+
+
+def pitch_only(bufs: np.ndarray, prev_period=None, prev_gain=None):
+    """pnb_pitch_only_host: [n, 1728] float32 pitch buffers -> (period int32 [n], corr [n], gain [n], lag int32 [n])"""
+    L = load_library()
+    b = np.ascontiguousarray(bufs, np.float32)
+    n = b.shape[0]
+    T, lag = np.empty(n, np.int32), np.empty(n, np.int32)
+    corr, gain = np.empty(n, np.float32), np.empty(n, np.float32)
+    pp = None if prev_period is None else np.ascontiguousarray(prev_period, np.int32)
+    pg = None if prev_gain is None else np.ascontiguousarray(prev_gain, np.float32)
+    rc = L.pnb_pitch_only_host(b.ctypes.data, b.shape[1], n, None if pp is None else pp.ctypes.data,
+                               None if pg is None else pg.ctypes.data, T.ctypes.data, corr.ctypes.data, gain.ctypes.data,
+                               lag.ctypes.data)
+    if rc != 0:
+        raise PnbError(f"pnb_pitch_only_host failed ({rc}): {L.pnb_last_error().decode()}")
+    return T, corr, gain, lag
 
 
 class BlobModel:
@@ -172,11 +206,23 @@ class Engine:
     def wait(self):
         self._ck(self.L.pnb_wait(self.h), "pnb_wait")
 
+    def check(self, stream: int = 0):
+        """pnb_check: waits for the engine's work (and `stream`) and raises on PNB_ERR_DOMAIN / PNB_ERR_CUDA."""
+        self._ck(self.L.pnb_check(self.h, stream or None), "pnb_check")
+
     def read_tap(self, name: str, n_frames: int) -> np.ndarray:
         code, dt, width = TAPS[name]
         a = np.empty((n_frames, self.n_streams, width), dt)
         self._ck(self.L.pnb_read_tap(self.h, code, a.ctypes.data, a.nbytes), f"pnb_read_tap({name})")
         return a
+
+    def get_state(self, stream: int) -> bytes:
+        buf = C.create_string_buffer(self.L.pnb_state_size())
+        self._ck(self.L.pnb_get_state(self.h, stream, buf, len(buf)), "pnb_get_state")
+        return buf.raw
+
+    def set_state(self, stream: int, blob: bytes):
+        self._ck(self.L.pnb_set_state(self.h, stream, blob, len(blob)), "pnb_set_state")
 
     def read_nn_state(self) -> dict:
         """fp32 network state after the last hop: conv2 output and the five GRU states, [S, width]."""

@@ -354,6 +354,359 @@ __device__ unsigned long long g_ana_cycles[16];
 #define ANA_TICK(k) do { } while (0)
 #endif
 
+// ------------------------------------------------------------------------------------------
+// The pitch stage of one hop: pitch_downsample (pitch.cpp:148-216) on the 1728-sample pitch buffer `src`,
+// pitch_search (pitch.cpp:283-386) and remove_doubling (pitch.cpp:423-527).  `acp` holds the five autocorrelations of
+// the decimated signal (celt_lpc.cpp:198-279), computed by the caller.  Shared by the analysis kernel and the
+// pitch-only kernel of BASELINE.json config 5.
+// ------------------------------------------------------------------------------------------
+struct PitchResult {
+  int pitch_lag, T;          // lag returned by pitch_search; period after remove_doubling
+  float pitch_corr, gain;    // pitch.cpp:385; pitch gain of remove_doubling
+};
+#ifdef PNB_ANA_TIMING
+#define ANA_TIMER_PARAMS , unsigned long long *ana_acc, long long &ana_t0
+#define ANA_TIMER_ARGS , ana_acc, ana_t0
+#else
+#define ANA_TIMER_PARAMS
+#define ANA_TIMER_ARGS
+#endif
+template <int L, bool kInlineAc = false>
+__device__ __forceinline__ PitchResult pitch_stage(WarpSmem &W, const float *src, const float *acp, int last_period,
+                                                   float last_gain, int lane, int wlane, unsigned mask ANA_TIMER_PARAMS) {
+  using CF = AnaCfg<L>;
+  // ---- pitch_downsample (pitch.cpp:148-216) ----
+  {
+    for (int i = lane; i < kLp; i += L) {
+      float v;
+      if (i == 0) v = .5f * (.5f * src[1] + src[0]);
+      else v = .5f * (.5f * (src[2 * i - 1] + src[2 * i + 1]) + src[2 * i]);
+      W.p.lp[i] = v;
+    }
+    __syncwarp(mask);
+    ANA_TICK(2);
+    // autocorrelation, 5 lags (celt_lpc.cpp:198-279): the analysis kernel computes them for a whole group of hops in
+    // its pre-pass; a caller without one (kInlineAc) has lane k run the strictly sequential sum of lag k here
+    if (kInlineAc) {
+      if (lane < 5) {
+        const float *lp = W.p.lp;
+        float a = 0.f, d = 0.f;
+        for (int j = 0; j < 860; j++) a = a + lp[j] * lp[j + lane];          // fastN = n - lag (celt_lpc.cpp:250-252)
+        for (int i = lane + 860; i < kLp; i++) d = d + lp[i] * lp[i - lane];  // the tail, summed apart (:253-256)
+        W.ac_pre[lane] = a + d;
+      }
+      __syncwarp(mask);
+      acp = W.ac_pre;
+    }
+    const float ac0 = acp[0], ac1 = acp[1], ac2 = acp[2], ac3 = acp[3], ac4 = acp[4];
+    float fir0 = 0, fir1 = 0, fir2 = 0, fir3 = 0, fir4 = 0;
+    ANA_TICK(3);
+    if (lane == 0) {
+      float a[5] = {ac0, ac1, ac2, ac3, ac4};
+      a[0] *= 1.0001f;                                                        // pitch.cpp:190
+      for (int i = 1; i <= 4; i++) a[i] -= a[i] * (.008f * i) * (.008f * i);  // :199
+      float lpc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a[0] != 0.f) {  // Levinson, celt_lpc.cpp:53-83, the divide in double (:61)
+        float err = a[0];
+        for (int i = 0; i < 4; i++) {
+          float rr = 0.f;
+          for (int j = 0; j < i; j++) rr += lpc[j] * a[i - j];
+          rr += a[i + 1];
+          float r = (float)(-(double)rr / ((double)err + 0.00001));
+          lpc[i] = r;
+          for (int j = 0; j < (i + 1) >> 1; j++) {
+            float t1 = lpc[j], t2 = lpc[i - 1 - j];
+            lpc[j] = t1 + r * t2;
+            lpc[i - 1 - j] = t2 + r * t1;
+          }
+          err = err - (r * r) * err;
+          if (err < .001f * a[0]) break;
+        }
+      }
+      float tmp = 1.f;
+      for (int i = 0; i < 4; i++) { tmp = .9f * tmp; lpc[i] = lpc[i] * tmp; }  // :204-208
+      fir0 = lpc[0] + .8f;                                                     // :210-214
+      fir1 = lpc[1] + .8f * lpc[0];
+      fir2 = lpc[2] + .8f * lpc[1];
+      fir3 = lpc[3] + .8f * lpc[2];
+      fir4 = .8f * lpc[3];
+    }
+    fir0 = __shfl_sync(mask, fir0, 0, L);
+    fir1 = __shfl_sync(mask, fir1, 0, L);
+    fir2 = __shfl_sync(mask, fir2, 0, L);
+    fir3 = __shfl_sync(mask, fir3, 0, L);
+    fir4 = __shfl_sync(mask, fir4, 0, L);
+    ANA_TICK(4);
+    // 5-tap FIR in place with zero history (pitch.cpp:106-145,154), walked from the end so the taps
+    // still see unfiltered samples
+    for (int base = kLp - L; base >= 0; base -= L) {
+      int i = base + lane;
+      float x0 = W.p.lp[i];
+      float m0 = i >= 1 ? W.p.lp[i - 1] : 0.f, m1 = i >= 2 ? W.p.lp[i - 2] : 0.f, m2 = i >= 3 ? W.p.lp[i - 3] : 0.f,
+            m3 = i >= 4 ? W.p.lp[i - 4] : 0.f, m4 = i >= 5 ? W.p.lp[i - 5] : 0.f;
+      float sum = x0;
+      sum = sum + fir0 * m0;
+      sum = sum + fir1 * m1;
+      sum = sum + fir2 * m2;
+      sum = sum + fir3 * m3;
+      sum = sum + fir4 * m4;
+      __syncwarp(mask);
+      W.p.lp[i] = sum;
+      W.p.sq[i] = sum * sum;
+      __syncwarp(mask);
+    }
+  }
+
+  ANA_TICK(5);
+  // ---- pitch_search (pitch.cpp:283-386): x = lp+384, y = lp, len 960, max_pitch 588 ----
+  int pitch_lag, T;
+  float pitch_corr, gain;
+  {
+    int b0, b1;
+    // coarse: the 4x-decimated signals are stride-2 views of lp.  A lag lane owns kLagsPerLane adjacent lags and
+    // slides a window of y along, so each step costs one new y load; every lag still accumulates in ascending
+    // j exactly like the reference (pitch.cpp:218-281).  The lane after the lag lanes accumulates the energy
+    // Syy = 1 + sum y4[j]^2 of find_best_pitch (pitch.cpp:54,69-70) through the same code shape (lag 0 of y on y).
+    {
+      constexpr int NL = CF::kLagsPerLane;
+      const bool syy_lane = (lane == CF::kLagLanes);
+      const float *xb = syy_lane ? W.p.lp : W.p.lp + 384;
+      const int L0 = (lane < CF::kLagLanes) ? NL * lane : 0;
+      const float *yb = W.p.lp + 2 * L0;
+      float acc[NL], w[NL];
+#pragma unroll
+      for (int q = 0; q < NL; q++) { acc[q] = 0.f; w[q] = yb[2 * q]; }
+      if (syy_lane) acc[0] = 1.f;
+      for (int j = 0; j < 240; j += NL) {
+#pragma unroll
+        for (int u = 0; u < NL; u++) {
+          const float xj = xb[2 * (j + u)];
+#pragma unroll
+          for (int q = 0; q < NL; q++) acc[q] = acc[q] + xj * w[(u + q) % NL];
+          w[u] = yb[2 * (j + u + NL)];
+        }
+      }
+      if (lane < CF::kLagLanes) {
+#pragma unroll
+        for (int q = 0; q < NL; q++)
+          if (L0 + q < 147) W.xc[L0 + q] = acc[q];
+      }
+      // energy deltas of the coarse scan: y4[i+240]^2 - y4[i]^2 (pitch.cpp:101)
+      for (int i = lane; i < 147; i += L) {
+        W.p.yy[i] = W.p.sq[2 * (i + 240)] - W.p.sq[2 * i];
+      }
+      float syy_c = __shfl_sync(mask, acc[0], CF::kLagLanes, L);
+      __syncwarp(mask);
+      ANA_TICK(6);
+      if (lane == 0) energy_chain(W.p.yy, 148, syy_c);
+      __syncwarp(mask);
+      {
+        Best2 S = best2_init();
+        for (int base = 0; base < 147; base += L) {
+          const int i = base + lane;
+          const bool valid = i < 147;
+          const float xv = valid ? W.xc[i] : 0.f, ev = valid ? W.p.yy[i] : 1.f;
+          const float c = xv * 1e-12f;
+          best2_rounds(S, valid && xv > 0.f, c * c, ev, i, mask, wlane);
+        }
+        b0 = S.b0; b1 = S.b1;
+      }
+      __syncwarp(mask);
+      ANA_TICK(7);
+    }
+    // fine: at most ten lags around 2*b0 and 2*b1 (pitch.cpp:344-361); lane 10 accumulates Syy of the
+    // second find_best_pitch, lane 11 the xx of remove_doubling (pitch.cpp:448)
+    for (int i = lane; i < 294; i += L) {
+      W.xc[i] = 0.f;
+      W.p.yy[i] = W.p.sq[i + 480] - W.p.sq[i];  // energy deltas of the fine scan
+    }
+    __syncwarp(mask);
+    int fl = -1;
+    if (lane < 5) fl = 2 * b0 - 2 + lane;
+    else if (lane < 10) fl = 2 * b1 - 2 + (lane - 5);
+    const bool fine_ok = (fl >= 0 && fl < 294);
+    float sacc = (lane == 10) ? 1.f : 0.f;
+    {
+      const float *a, *b;
+      int n = 480;
+      if (lane < 10) { a = W.p.lp + 384; b = W.p.lp + (fine_ok ? fl : 0); if (!fine_ok) n = 0; }
+      else if (lane == 10) { a = W.p.lp; b = W.p.lp; }
+      else if (lane == 11) { a = W.p.lp + 384; b = W.p.lp + 384; }
+      else { a = W.p.lp; b = W.p.lp; n = 0; }
+      if (n) sacc = seq_dot4(a, b, 480, sacc);
+    }
+    if (fine_ok) W.xc[fl] = (-1.f > sacc) ? -1.f : sacc;
+    float syy_f = __shfl_sync(mask, sacc, 10, L);
+    float xx = __shfl_sync(mask, sacc, 11, L);
+    __syncwarp(mask);
+    ANA_TICK(8);
+    int off = 0;
+    float corr = 0.f;
+    pitch_lag = 0;
+    // second find_best_pitch (pitch.cpp:362): xcorr is zero outside the two windows and zero entries are never
+    // candidates (pitch.cpp:73), so only the (at most ten) window lags are tested; the energy recurrence still
+    // runs from lag 0 up to the end of the later window
+    int c0;
+    {
+      const int w0 = 2 * b0 - 2, w1 = 2 * b1 - 2;
+      const int lo_a = w0 < w1 ? w0 : w1, lo_b = w0 < w1 ? w1 : w0;
+      int loA = lo_a < 0 ? 0 : lo_a;
+      loA = loA > 294 ? 294 : loA;
+      int hiA = lo_a + 5;
+      hiA = hiA < loA ? loA : hiA;
+      hiA = hiA > 294 ? 294 : hiA;
+      int loB = lo_b < hiA ? hiA : lo_b;
+      loB = loB > 294 ? 294 : loB;
+      int hiB = lo_b + 5;
+      hiB = hiB < loB ? loB : hiB;
+      hiB = hiB > 294 ? 294 : hiB;
+      if (lane == 0) energy_chain(W.p.yy, (hiB + 3) & ~3, syy_f);
+      __syncwarp(mask);
+      const int idx = lane < 5 ? loA + lane : loB + (lane - 5);
+      const bool valid = lane < 5 ? idx < hiA : (lane < 10 && idx < hiB);
+      const float xv = valid ? W.xc[idx] : 0.f, ev = valid ? W.p.yy[idx] : 1.f;
+      const float c = xv * 1e-12f;
+      Best2 S = best2_init();
+      best2_rounds(S, valid && xv > 0.f, c * c, ev, idx, mask, wlane);
+      c0 = S.b0;
+    }
+    if (lane == 0) {
+      if (c0 > 0 && c0 < 293) {
+        float a = W.xc[c0 - 1], b = W.xc[c0], cc = W.xc[c0 + 1];
+        if ((cc - a) > .7f * (b - a)) off = 1;
+        else if ((a - cc) > .7f * (b - cc)) off = -1;
+      }
+      pitch_lag = 2 * c0 - off;
+      corr = W.xc[c0];
+    }
+    pitch_lag = __shfl_sync(mask, pitch_lag, 0, L);
+    pitch_corr = __shfl_sync(mask, corr, 0, L);
+    __syncwarp(mask);  // the scan's energy deltas in W.p.yy are dead; the yy table is built next
+    ANA_TICK(9);
+
+    // ---- remove_doubling (pitch.cpp:423-527) with maxperiod 384, minperiod 30, N 480 ----
+    const int second_check[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};
+    const float *x = W.p.lp + 384;
+    int T0 = (kMaxPeriod - pitch_lag) / 2;
+    if (T0 >= 384) T0 = 383;
+    const int prev_period = last_period / 2;
+    // 32 roles: 0: xy at T0; 1: the yy_lookup recurrence; 2..29: candidate (k, which) = (2 + (role-2)/2, (role-2)&1);
+    // 30, 31: xy at T0-1 and T0+1, the neighbours the final refinement needs when no sub-harmonic replaces T0
+    // (the usual outcome) -- they ride along in lanes that would idle, and the extra pass below is skipped
+#pragma unroll 1
+    for (int rbase = 0; rbase < 32; rbase += L) {
+      const int role = rbase + lane;
+      int lag = -1;
+      if (role == 0) lag = T0;
+      else if (role == 30) lag = T0 - 1;
+      else if (role == 31) lag = T0 + 1;
+      else if (role >= 2 && role < 30) {
+        int k = 2 + ((role - 2) >> 1);
+        int T1 = (2 * T0 + k) / (2 * k);
+        if (T1 >= 30) {
+          if ((role & 1) == 0) lag = T1;
+          else if (k == 2) lag = (T1 + T0 > 384) ? T0 : T0 + T1;
+          else lag = (2 * second_check[k] * T0 + k) / (2 * k);
+        }
+      }
+      // all lanes meet here before the 480-step loops: without it the lanes whose lag needed no division run the
+      // dot loop ahead of the candidate lanes and the loop is executed once per group
+      __syncwarp(mask);
+      // the energy table is read only at the lags of roles 0 and 2..29 (T0, T1, T1b): the recurrence stops there
+      const int max_lag = (L == 32) ? __reduce_max_sync(mask, role < 30 ? lag : -1) : 384;  // (all roles in one pass)
+      if (role == 1) {
+        // yy_lookup recurrence (pitch.cpp:449-455), strictly sequential; operands fetched four at a time.
+        // Table entry i is stored at W.p.yy[i + 3] so that groups of four are 16-byte aligned.
+        float yy = xx;
+        W.p.yy[3] = xx;
+        for (int i = 1; i <= max_lag; i += 4) {
+          const float4 a = *reinterpret_cast<const float4 *>(W.p.sq + 384 - i - 3);  // x[-i-3 .. -i]^2
+          const float4 b = *reinterpret_cast<const float4 *>(W.p.sq + 864 - i - 3);  // x[480-i-3 .. 480-i]^2
+          float4 o;
+          yy = yy + a.w - b.w; o.x = max_nan(yy, 0.f);
+          yy = yy + a.z - b.z; o.y = max_nan(yy, 0.f);
+          yy = yy + a.y - b.y; o.z = max_nan(yy, 0.f);
+          yy = yy + a.x - b.x; o.w = max_nan(yy, 0.f);
+          *reinterpret_cast<float4 *>(&W.p.yy[i + 3]) = o;
+        }
+      } else {
+        float d = 0.f;
+        if (lag >= 0) d = seq_dot4(x, x - lag, 480, 0.f);
+        W.p.cand_xy[role] = d;
+      }
+    }
+    __syncwarp(mask);
+    ANA_TICK(10);
+    int Tsel = T0;
+    float g = 0.f, best_xy = 0.f, best_yy = 0.f;
+    if (lane == 0) {
+      float xy = W.p.cand_xy[0];
+      float yy = W.p.yy[T0 + 3];
+      best_xy = xy;
+      best_yy = yy;
+      float g0 = pitch_gain(xy, xx, yy);
+      g = g0;
+      for (int k = 2; k <= 15; k++) {
+        int T1 = (2 * T0 + k) / (2 * k);
+        if (T1 < 30) break;
+        int T1b;
+        if (k == 2) T1b = (T1 + T0 > 384) ? T0 : T0 + T1;
+        else T1b = (2 * second_check[k] * T0 + k) / (2 * k);
+        float xy1 = W.p.cand_xy[2 + 2 * (k - 2)], xy2 = W.p.cand_xy[3 + 2 * (k - 2)];
+        xy = .5f * (xy1 + xy2);
+        yy = .5f * (W.p.yy[T1 + 3] + W.p.yy[T1b + 3]);
+        float g1 = pitch_gain(xy, xx, yy);
+        float cont;
+        int dT = T1 - prev_period;
+        dT = dT < 0 ? -dT : dT;
+        if (dT <= 1) cont = last_gain;
+        else if (dT <= 2 && 5 * k * k < T0) cont = .5f * last_gain;
+        else cont = 0.f;
+        float th = .7f * g0 - cont;
+        float thresh = .3f > th ? .3f : th;
+        if (T1 < 90) {
+          th = .85f * g0 - cont;
+          thresh = .4f > th ? .4f : th;
+        }  // the T1 < 2*minperiod branch of the reference is unreachable
+        if (g1 > thresh) { best_xy = xy; best_yy = yy; Tsel = T1; g = g1; }
+      }
+    }
+    Tsel = __shfl_sync(mask, Tsel, 0, L);
+    ANA_TICK(11);
+    // final +-1 refinement: three dot products around the selected period (pitch.cpp:512-513)
+    {
+      float x0, x1, x2;
+      if (Tsel == T0) {  // warp-uniform
+        x0 = W.p.cand_xy[30]; x1 = W.p.cand_xy[0]; x2 = W.p.cand_xy[31];
+      } else {
+        float d = 0.f;
+        if (lane < 3) d = seq_dot4(x, x - (Tsel + lane - 1), 480, 0.f);
+        x0 = __shfl_sync(mask, d, 0, L); x1 = __shfl_sync(mask, d, 1, L); x2 = __shfl_sync(mask, d, 2, L);
+      }
+      int Tout = 0;
+      float pg = 0.f;
+      if (lane == 0) {
+        best_xy = 0.f > best_xy ? 0.f : best_xy;
+        if (best_yy <= best_xy) pg = 1.f;
+        else pg = best_xy / (best_yy + 1.f);
+        int o2;
+        if ((x2 - x0) > .7f * (x1 - x0)) o2 = 1;
+        else if ((x0 - x2) > .7f * (x1 - x2)) o2 = -1;
+        else o2 = 0;
+        if (pg > g) pg = g;
+        Tout = 2 * Tsel + o2;
+        if (Tout < kMinPeriod) Tout = kMinPeriod;
+      }
+      T = __shfl_sync(mask, Tout, 0, L);
+      gain = __shfl_sync(mask, pg, 0, L);
+    }
+    ANA_TICK(12);
+  }
+  PitchResult res;
+  res.pitch_lag = pitch_lag; res.T = T; res.pitch_corr = pitch_corr; res.gain = gain;
+  return res;
+}
+
 template <int L>
 __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(AnalysisArgs A) {
   using CF = AnaCfg<L>;
@@ -471,325 +824,13 @@ __global__ void __launch_bounds__(AnaCfg<L>::kWarps * 32) analysis_kernel(Analys
     __syncwarp(mask);
     ANA_TICK(1);
 
-    // ---- pitch_downsample (pitch.cpp:148-216) ----
-    {
-      const float *src = line + kOffPitch;
-      for (int i = lane; i < kLp; i += L) {
-        float v;
-        if (i == 0) v = .5f * (.5f * src[1] + src[0]);
-        else v = .5f * (.5f * (src[2 * i - 1] + src[2 * i + 1]) + src[2 * i]);
-        W.p.lp[i] = v;
-      }
-      __syncwarp(mask);
-      ANA_TICK(2);
-      // autocorrelation, 5 lags: computed for the whole group of hops by the pre-pass above
-      const float *acp = W.ac_pre + 5 * (t % kAcHops);
-      const float ac0 = acp[0], ac1 = acp[1], ac2 = acp[2], ac3 = acp[3], ac4 = acp[4];
-      float fir0 = 0, fir1 = 0, fir2 = 0, fir3 = 0, fir4 = 0;
-      ANA_TICK(3);
-      if (lane == 0) {
-        float a[5] = {ac0, ac1, ac2, ac3, ac4};
-        a[0] *= 1.0001f;                                                        // pitch.cpp:190
-        for (int i = 1; i <= 4; i++) a[i] -= a[i] * (.008f * i) * (.008f * i);  // :199
-        float lpc[4] = {0.f, 0.f, 0.f, 0.f};
-        if (a[0] != 0.f) {  // Levinson, celt_lpc.cpp:53-83, the divide in double (:61)
-          float err = a[0];
-          for (int i = 0; i < 4; i++) {
-            float rr = 0.f;
-            for (int j = 0; j < i; j++) rr += lpc[j] * a[i - j];
-            rr += a[i + 1];
-            float r = (float)(-(double)rr / ((double)err + 0.00001));
-            lpc[i] = r;
-            for (int j = 0; j < (i + 1) >> 1; j++) {
-              float t1 = lpc[j], t2 = lpc[i - 1 - j];
-              lpc[j] = t1 + r * t2;
-              lpc[i - 1 - j] = t2 + r * t1;
-            }
-            err = err - (r * r) * err;
-            if (err < .001f * a[0]) break;
-          }
-        }
-        float tmp = 1.f;
-        for (int i = 0; i < 4; i++) { tmp = .9f * tmp; lpc[i] = lpc[i] * tmp; }  // :204-208
-        fir0 = lpc[0] + .8f;                                                     // :210-214
-        fir1 = lpc[1] + .8f * lpc[0];
-        fir2 = lpc[2] + .8f * lpc[1];
-        fir3 = lpc[3] + .8f * lpc[2];
-        fir4 = .8f * lpc[3];
-      }
-      fir0 = __shfl_sync(mask, fir0, 0, L);
-      fir1 = __shfl_sync(mask, fir1, 0, L);
-      fir2 = __shfl_sync(mask, fir2, 0, L);
-      fir3 = __shfl_sync(mask, fir3, 0, L);
-      fir4 = __shfl_sync(mask, fir4, 0, L);
-      ANA_TICK(4);
-      // 5-tap FIR in place with zero history (pitch.cpp:106-145,154), walked from the end so the taps
-      // still see unfiltered samples
-      for (int base = kLp - L; base >= 0; base -= L) {
-        int i = base + lane;
-        float x0 = W.p.lp[i];
-        float m0 = i >= 1 ? W.p.lp[i - 1] : 0.f, m1 = i >= 2 ? W.p.lp[i - 2] : 0.f, m2 = i >= 3 ? W.p.lp[i - 3] : 0.f,
-              m3 = i >= 4 ? W.p.lp[i - 4] : 0.f, m4 = i >= 5 ? W.p.lp[i - 5] : 0.f;
-        float sum = x0;
-        sum = sum + fir0 * m0;
-        sum = sum + fir1 * m1;
-        sum = sum + fir2 * m2;
-        sum = sum + fir3 * m3;
-        sum = sum + fir4 * m4;
-        __syncwarp(mask);
-        W.p.lp[i] = sum;
-        W.p.sq[i] = sum * sum;
-        __syncwarp(mask);
-      }
-    }
-
-    ANA_TICK(5);
-    // ---- pitch_search (pitch.cpp:283-386): x = lp+384, y = lp, len 960, max_pitch 588 ----
-    int pitch_lag, T;
-    float pitch_corr, gain;
-    {
-      int b0, b1;
-      // coarse: the 4x-decimated signals are stride-2 views of lp.  A lag lane owns kLagsPerLane adjacent lags and
-      // slides a window of y along, so each step costs one new y load; every lag still accumulates in ascending
-      // j exactly like the reference (pitch.cpp:218-281).  The lane after the lag lanes accumulates the energy
-      // Syy = 1 + sum y4[j]^2 of find_best_pitch (pitch.cpp:54,69-70) through the same code shape (lag 0 of y on y).
-      {
-        constexpr int NL = CF::kLagsPerLane;
-        const bool syy_lane = (lane == CF::kLagLanes);
-        const float *xb = syy_lane ? W.p.lp : W.p.lp + 384;
-        const int L0 = (lane < CF::kLagLanes) ? NL * lane : 0;
-        const float *yb = W.p.lp + 2 * L0;
-        float acc[NL], w[NL];
-#pragma unroll
-        for (int q = 0; q < NL; q++) { acc[q] = 0.f; w[q] = yb[2 * q]; }
-        if (syy_lane) acc[0] = 1.f;
-        for (int j = 0; j < 240; j += NL) {
-#pragma unroll
-          for (int u = 0; u < NL; u++) {
-            const float xj = xb[2 * (j + u)];
-#pragma unroll
-            for (int q = 0; q < NL; q++) acc[q] = acc[q] + xj * w[(u + q) % NL];
-            w[u] = yb[2 * (j + u + NL)];
-          }
-        }
-        if (lane < CF::kLagLanes) {
-#pragma unroll
-          for (int q = 0; q < NL; q++)
-            if (L0 + q < 147) W.xc[L0 + q] = acc[q];
-        }
-        // energy deltas of the coarse scan: y4[i+240]^2 - y4[i]^2 (pitch.cpp:101)
-        for (int i = lane; i < 147; i += L) {
-          W.p.yy[i] = W.p.sq[2 * (i + 240)] - W.p.sq[2 * i];
-        }
-        float syy_c = __shfl_sync(mask, acc[0], CF::kLagLanes, L);
-        __syncwarp(mask);
-        ANA_TICK(6);
-        if (lane == 0) energy_chain(W.p.yy, 148, syy_c);
-        __syncwarp(mask);
-        {
-          Best2 S = best2_init();
-          for (int base = 0; base < 147; base += L) {
-            const int i = base + lane;
-            const bool valid = i < 147;
-            const float xv = valid ? W.xc[i] : 0.f, ev = valid ? W.p.yy[i] : 1.f;
-            const float c = xv * 1e-12f;
-            best2_rounds(S, valid && xv > 0.f, c * c, ev, i, mask, wlane);
-          }
-          b0 = S.b0; b1 = S.b1;
-        }
-        __syncwarp(mask);
-        ANA_TICK(7);
-      }
-      // fine: at most ten lags around 2*b0 and 2*b1 (pitch.cpp:344-361); lane 10 accumulates Syy of the
-      // second find_best_pitch, lane 11 the xx of remove_doubling (pitch.cpp:448)
-      for (int i = lane; i < 294; i += L) {
-        W.xc[i] = 0.f;
-        W.p.yy[i] = W.p.sq[i + 480] - W.p.sq[i];  // energy deltas of the fine scan
-      }
-      __syncwarp(mask);
-      int fl = -1;
-      if (lane < 5) fl = 2 * b0 - 2 + lane;
-      else if (lane < 10) fl = 2 * b1 - 2 + (lane - 5);
-      const bool fine_ok = (fl >= 0 && fl < 294);
-      float sacc = (lane == 10) ? 1.f : 0.f;
-      {
-        const float *a, *b;
-        int n = 480;
-        if (lane < 10) { a = W.p.lp + 384; b = W.p.lp + (fine_ok ? fl : 0); if (!fine_ok) n = 0; }
-        else if (lane == 10) { a = W.p.lp; b = W.p.lp; }
-        else if (lane == 11) { a = W.p.lp + 384; b = W.p.lp + 384; }
-        else { a = W.p.lp; b = W.p.lp; n = 0; }
-        if (n) sacc = seq_dot4(a, b, 480, sacc);
-      }
-      if (fine_ok) W.xc[fl] = (-1.f > sacc) ? -1.f : sacc;
-      float syy_f = __shfl_sync(mask, sacc, 10, L);
-      float xx = __shfl_sync(mask, sacc, 11, L);
-      __syncwarp(mask);
-      ANA_TICK(8);
-      int off = 0;
-      float corr = 0.f;
-      pitch_lag = 0;
-      // second find_best_pitch (pitch.cpp:362): xcorr is zero outside the two windows and zero entries are never
-      // candidates (pitch.cpp:73), so only the (at most ten) window lags are tested; the energy recurrence still
-      // runs from lag 0 up to the end of the later window
-      int c0;
-      {
-        const int w0 = 2 * b0 - 2, w1 = 2 * b1 - 2;
-        const int lo_a = w0 < w1 ? w0 : w1, lo_b = w0 < w1 ? w1 : w0;
-        int loA = lo_a < 0 ? 0 : lo_a;
-        loA = loA > 294 ? 294 : loA;
-        int hiA = lo_a + 5;
-        hiA = hiA < loA ? loA : hiA;
-        hiA = hiA > 294 ? 294 : hiA;
-        int loB = lo_b < hiA ? hiA : lo_b;
-        loB = loB > 294 ? 294 : loB;
-        int hiB = lo_b + 5;
-        hiB = hiB < loB ? loB : hiB;
-        hiB = hiB > 294 ? 294 : hiB;
-        if (lane == 0) energy_chain(W.p.yy, (hiB + 3) & ~3, syy_f);
-        __syncwarp(mask);
-        const int idx = lane < 5 ? loA + lane : loB + (lane - 5);
-        const bool valid = lane < 5 ? idx < hiA : (lane < 10 && idx < hiB);
-        const float xv = valid ? W.xc[idx] : 0.f, ev = valid ? W.p.yy[idx] : 1.f;
-        const float c = xv * 1e-12f;
-        Best2 S = best2_init();
-        best2_rounds(S, valid && xv > 0.f, c * c, ev, idx, mask, wlane);
-        c0 = S.b0;
-      }
-      if (lane == 0) {
-        if (c0 > 0 && c0 < 293) {
-          float a = W.xc[c0 - 1], b = W.xc[c0], cc = W.xc[c0 + 1];
-          if ((cc - a) > .7f * (b - a)) off = 1;
-          else if ((a - cc) > .7f * (b - cc)) off = -1;
-        }
-        pitch_lag = 2 * c0 - off;
-        corr = W.xc[c0];
-      }
-      pitch_lag = __shfl_sync(mask, pitch_lag, 0, L);
-      pitch_corr = __shfl_sync(mask, corr, 0, L);
-      __syncwarp(mask);  // the scan's energy deltas in W.p.yy are dead; the yy table is built next
-      ANA_TICK(9);
-
-      // ---- remove_doubling (pitch.cpp:423-527) with maxperiod 384, minperiod 30, N 480 ----
-      const int second_check[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};
-      const float *x = W.p.lp + 384;
-      int T0 = (kMaxPeriod - pitch_lag) / 2;
-      if (T0 >= 384) T0 = 383;
-      const int prev_period = last_period / 2;
-      // 32 roles: 0: xy at T0; 1: the yy_lookup recurrence; 2..29: candidate (k, which) = (2 + (role-2)/2, (role-2)&1);
-      // 30, 31: xy at T0-1 and T0+1, the neighbours the final refinement needs when no sub-harmonic replaces T0
-      // (the usual outcome) -- they ride along in lanes that would idle, and the extra pass below is skipped
-#pragma unroll 1
-      for (int rbase = 0; rbase < 32; rbase += L) {
-        const int role = rbase + lane;
-        int lag = -1;
-        if (role == 0) lag = T0;
-        else if (role == 30) lag = T0 - 1;
-        else if (role == 31) lag = T0 + 1;
-        else if (role >= 2 && role < 30) {
-          int k = 2 + ((role - 2) >> 1);
-          int T1 = (2 * T0 + k) / (2 * k);
-          if (T1 >= 30) {
-            if ((role & 1) == 0) lag = T1;
-            else if (k == 2) lag = (T1 + T0 > 384) ? T0 : T0 + T1;
-            else lag = (2 * second_check[k] * T0 + k) / (2 * k);
-          }
-        }
-        // all lanes meet here before the 480-step loops: without it the lanes whose lag needed no division run the
-        // dot loop ahead of the candidate lanes and the loop is executed once per group
-        __syncwarp(mask);
-        // the energy table is read only at the lags of roles 0 and 2..29 (T0, T1, T1b): the recurrence stops there
-        const int max_lag = (L == 32) ? __reduce_max_sync(mask, role < 30 ? lag : -1) : 384;  // (all roles in one pass)
-        if (role == 1) {
-          // yy_lookup recurrence (pitch.cpp:449-455), strictly sequential; operands fetched four at a time.
-          // Table entry i is stored at W.p.yy[i + 3] so that groups of four are 16-byte aligned.
-          float yy = xx;
-          W.p.yy[3] = xx;
-          for (int i = 1; i <= max_lag; i += 4) {
-            const float4 a = *reinterpret_cast<const float4 *>(W.p.sq + 384 - i - 3);  // x[-i-3 .. -i]^2
-            const float4 b = *reinterpret_cast<const float4 *>(W.p.sq + 864 - i - 3);  // x[480-i-3 .. 480-i]^2
-            float4 o;
-            yy = yy + a.w - b.w; o.x = max_nan(yy, 0.f);
-            yy = yy + a.z - b.z; o.y = max_nan(yy, 0.f);
-            yy = yy + a.y - b.y; o.z = max_nan(yy, 0.f);
-            yy = yy + a.x - b.x; o.w = max_nan(yy, 0.f);
-            *reinterpret_cast<float4 *>(&W.p.yy[i + 3]) = o;
-          }
-        } else {
-          float d = 0.f;
-          if (lag >= 0) d = seq_dot4(x, x - lag, 480, 0.f);
-          W.p.cand_xy[role] = d;
-        }
-      }
-      __syncwarp(mask);
-      ANA_TICK(10);
-      int Tsel = T0;
-      float g = 0.f, best_xy = 0.f, best_yy = 0.f;
-      if (lane == 0) {
-        float xy = W.p.cand_xy[0];
-        float yy = W.p.yy[T0 + 3];
-        best_xy = xy;
-        best_yy = yy;
-        float g0 = pitch_gain(xy, xx, yy);
-        g = g0;
-        for (int k = 2; k <= 15; k++) {
-          int T1 = (2 * T0 + k) / (2 * k);
-          if (T1 < 30) break;
-          int T1b;
-          if (k == 2) T1b = (T1 + T0 > 384) ? T0 : T0 + T1;
-          else T1b = (2 * second_check[k] * T0 + k) / (2 * k);
-          float xy1 = W.p.cand_xy[2 + 2 * (k - 2)], xy2 = W.p.cand_xy[3 + 2 * (k - 2)];
-          xy = .5f * (xy1 + xy2);
-          yy = .5f * (W.p.yy[T1 + 3] + W.p.yy[T1b + 3]);
-          float g1 = pitch_gain(xy, xx, yy);
-          float cont;
-          int dT = T1 - prev_period;
-          dT = dT < 0 ? -dT : dT;
-          if (dT <= 1) cont = last_gain;
-          else if (dT <= 2 && 5 * k * k < T0) cont = .5f * last_gain;
-          else cont = 0.f;
-          float th = .7f * g0 - cont;
-          float thresh = .3f > th ? .3f : th;
-          if (T1 < 90) {
-            th = .85f * g0 - cont;
-            thresh = .4f > th ? .4f : th;
-          }  // the T1 < 2*minperiod branch of the reference is unreachable
-          if (g1 > thresh) { best_xy = xy; best_yy = yy; Tsel = T1; g = g1; }
-        }
-      }
-      Tsel = __shfl_sync(mask, Tsel, 0, L);
-      ANA_TICK(11);
-      // final +-1 refinement: three dot products around the selected period (pitch.cpp:512-513)
-      {
-        float x0, x1, x2;
-        if (Tsel == T0) {  // warp-uniform
-          x0 = W.p.cand_xy[30]; x1 = W.p.cand_xy[0]; x2 = W.p.cand_xy[31];
-        } else {
-          float d = 0.f;
-          if (lane < 3) d = seq_dot4(x, x - (Tsel + lane - 1), 480, 0.f);
-          x0 = __shfl_sync(mask, d, 0, L); x1 = __shfl_sync(mask, d, 1, L); x2 = __shfl_sync(mask, d, 2, L);
-        }
-        int Tout = 0;
-        float pg = 0.f;
-        if (lane == 0) {
-          best_xy = 0.f > best_xy ? 0.f : best_xy;
-          if (best_yy <= best_xy) pg = 1.f;
-          else pg = best_xy / (best_yy + 1.f);
-          int o2;
-          if ((x2 - x0) > .7f * (x1 - x0)) o2 = 1;
-          else if ((x0 - x2) > .7f * (x1 - x2)) o2 = -1;
-          else o2 = 0;
-          if (pg > g) pg = g;
-          Tout = 2 * Tsel + o2;
-          if (Tout < kMinPeriod) Tout = kMinPeriod;
-        }
-        T = __shfl_sync(mask, Tout, 0, L);
-        gain = __shfl_sync(mask, pg, 0, L);
-      }
-      last_period = T;
-      last_gain = gain;
-      ANA_TICK(12);
-    }
+    // ---- pitch_downsample, pitch_search, remove_doubling (pitch.cpp:148-216, 283-386, 423-527) ----
+    const PitchResult pr = pitch_stage<L>(W, line + kOffPitch, W.ac_pre + 5 * (t % kAcHops), last_period, last_gain, lane,
+                                          wlane, mask ANA_TIMER_ARGS);
+    const int pitch_lag = pr.pitch_lag, T = pr.T;
+    const float pitch_corr = pr.pitch_corr, gain = pr.gain;
+    last_period = T;
+    last_gain = gain;
 
     // ---- comb-filtered block, its spectrum P and the band statistics (denoise.cpp:416-427) ----
     __syncwarp(mask);  // the pitch scratch is dead from here on; its storage becomes the FFT line again
@@ -919,7 +960,8 @@ __global__ void __launch_bounds__(kSynWarps * 32) synthesis_kernel(SynthesisArgs
     __syncwarp();
     if (A.postfilter) {  // denoise.cpp:216-250 applied to g (envelope post-filter, beta = 0.02)
       const float *Ey = A.Ex + fs * kBands;
-      for (int b = lane; b < kBands; b += 32) W.gw[b] = W.g[b] * sinf((float)(M_PI / 2 * (double)W.g[b]));
+      // sinf of the reference's libm is correctly rounded in all but rare cases; so is the rounded double sine
+      for (int b = lane; b < kBands; b += 32) W.gw[b] = W.g[b] * (float)sin((double)(float)(M_PI / 2 * (double)W.g[b]));
       __syncwarp();
       float G = 0.f;
       if (lane == 0) {
@@ -934,6 +976,8 @@ __global__ void __launch_bounds__(kSynWarps * 32) synthesis_kernel(SynthesisArgs
       for (int b = lane; b < kBands; b += 32) W.g[b] = G * W.gw[b];
       __syncwarp();
     }
+    if (A.tap_g)
+      for (int b = lane; b < kBands; b += 32) A.tap_g[fs * kBands + b] = W.g[b];
     const bool silence = A.silence[fs] != 0;
     const long c = A.hop0 + t;
     const int slot_x = (int)(((c - 5) % A.ring + A.ring) % A.ring);
@@ -993,9 +1037,9 @@ __global__ void __launch_bounds__(kSynWarps * 32) synthesis_kernel(SynthesisArgs
 // ------------------------------------------------------------------------------------------
 __global__ void stage_in_kernel(float *pcm, size_t pcm_stride, const float *in, const short *in16, size_t in_stride,
                                 int n_streams, int n_samples, float i16_div) {
-  const int s = blockIdx.y;
+  const int s = blockIdx.x;  // streams on grid.x (no 65535 limit), chunks of the row on grid.y
   float *dst = pcm + (size_t)s * pcm_stride + kKeep;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_samples; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n_samples; i += gridDim.y * blockDim.x) {
     float v;
     if (in) v = in[(size_t)s * in_stride + i];
     else v = ((float)in16[(size_t)s * in_stride + i]) / i16_div;  // main.cpp:34 (32768) / denoise.cpp:681 (NORM_RATIO 1)
@@ -1019,6 +1063,32 @@ __global__ void __launch_bounds__(512) slide_history_kernel(float *pcm, size_t p
   for (int i = 0; i < kPer; i++) {
     int j = threadIdx.x + 512 * i;
     if (j < kKeep) row[j] = keep[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// BASELINE.json config 5: the pitch analysis alone.  One warp per stream-frame: pitch_downsample + pitch_search +
+// remove_doubling on a 1728-sample pitch buffer (6 912 B in, 16 B out), the same device code the analysis kernel runs.
+// ------------------------------------------------------------------------------------------
+constexpr int kPitchWarps = 8;
+__global__ void __launch_bounds__(kPitchWarps * 32) pitch_only_kernel(PitchOnlyArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpSmem *Wall = reinterpret_cast<WarpSmem *>(smem_raw);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long s = (long)blockIdx.x * kPitchWarps + wib;
+  if (s >= A.n_units) return;
+  WarpSmem &W = Wall[wib];
+#ifdef PNB_ANA_TIMING
+  unsigned long long ana_acc[16];
+  long long ana_t0 = clock64();
+#endif
+  const PitchResult r = pitch_stage<32, true>(W, A.buf + (size_t)s * A.stride, nullptr, A.prev_period ? A.prev_period[s] : 0,
+                                              A.prev_gain ? A.prev_gain[s] : 0.f, lane, lane, 0xffffffffu ANA_TIMER_ARGS);
+  if (lane == 0) {
+    A.T[s] = r.T;
+    A.gain[s] = r.gain;
+    A.corr[s] = r.pitch_corr;
+    if (A.lag) A.lag[s] = r.pitch_lag;
   }
 }
 
@@ -1130,6 +1200,17 @@ extern "C" int pnb_debug_analysis_cycles(unsigned long long *out16, int reset) {
 }
 #endif
 
+int launch_pitch_only(const PitchOnlyArgs &a, cudaStream_t st) {
+  const size_t smem = kPitchWarps * sizeof(WarpSmem);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(pitch_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = true;
+  }
+  pitch_only_kernel<<<(unsigned)((a.n_units + kPitchWarps - 1) / kPitchWarps), kPitchWarps * 32, smem, st>>>(a);
+  return 1;
+}
+
 int launch_train_labels(const LabelArgs &a, cudaStream_t st) {
   const long total = (long)a.n_frames * a.n_pairs;
   train_labels_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(a);
@@ -1143,7 +1224,7 @@ int launch_synthesis(const SynthesisArgs &a, cudaStream_t st) {
 }
 int launch_stage_in(float *pcm, size_t pcm_stride, const float *in, const short *in16, size_t in_stride,
                     int n_streams, int n_samples, cudaStream_t st, float i16_div) {
-  dim3 grid((n_samples + 1023) / 1024 > 8 ? 8 : (n_samples + 1023) / 1024, n_streams);
+  dim3 grid(n_streams, (n_samples + 1023) / 1024 > 8 ? 8 : (n_samples + 1023) / 1024);
   stage_in_kernel<<<grid, 256, 0, st>>>(pcm, pcm_stride, in, in16, in_stride, n_streams, n_samples, i16_div);
   return 1;
 }

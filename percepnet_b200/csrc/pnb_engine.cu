@@ -126,6 +126,11 @@ static int check_model(const pnb_model *m) {
   const pnb_gru_layer *g5[5] = {m->gru1, m->gru2, m->gru3, m->gru_gb, m->gru_rb};
   for (int i = 0; i < 5; i++) ok = ok && g5[i]->reset_after == 1 && g5[i]->activation == PNB_ACT_TANH;
   if (!ok) return fail(PNB_ERR_ARG, "model dimensions are not PercepNet's (70-128-conv5x512-conv3x512-4xGRU512-GRU128-34/34)");
+  // the kernels fuse each layer's activation (rnn_train.py:111-121 / dump_percepnet.py); a model that asks for
+  // anything else would silently compute something the reference does not
+  if (m->fc->activation != PNB_ACT_RELU || m->conv1->activation != PNB_ACT_RELU || m->conv2->activation != PNB_ACT_TANH ||
+      m->fc_gb->activation != PNB_ACT_SIGMOID || m->fc_rb->activation != PNB_ACT_SIGMOID)
+    return fail(PNB_ERR_ARG, "model activations are not PercepNet's (fc relu, conv1 relu, conv2 tanh, fc_gb / fc_rb sigmoid)");
   return PNB_OK;
 }
 
@@ -134,6 +139,8 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
   if (!out) return fail(PNB_ERR_ARG, "out is NULL");
   *out = nullptr;
   if (n_streams < 1 || max_frames < 1) return fail(PNB_ERR_ARG, "n_streams and max_frames_per_call must be >= 1");
+  if ((long long)n_streams * max_frames > (1ll << 24))
+    return fail(PNB_ERR_ARG, "n_streams x max_frames_per_call above 2^24 rows per call: split the batch across engines");
   const bool train_mode = (flags & PNB_TRAIN_DATA) != 0;
   if (train_mode && (n_streams & 1)) return fail(PNB_ERR_ARG, "PNB_TRAIN_DATA needs n_streams = 2 x pairs");
   if (train_mode && (flags & (PNB_NN_TENSOR | PNB_POSTFILTER)))
@@ -215,6 +222,9 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
   e->pcm_stride = kKeep + line_calls * F * kFrame;
   CKD(dalloc(&e->d_pcm, S * e->pcm_stride));
   CKD(dalloc(&e->d_synth, S * kFrame));
+  CKD(dalloc(&e->d_status, 1));
+  CKD(cudaHostAlloc((void **)&e->h_status, sizeof(int), cudaHostAllocDefault));
+  *e->h_status = 0;
   CKD(dalloc(&e->d_last_period, S));
   CKD(dalloc(&e->d_last_gain, S));
   // per-call buffers
@@ -230,21 +240,24 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
   if (flags & PNB_KEEP_TAPS) {
     CKD(dalloc(&e->d_tap_pitch, F * S * 4));
     CKD(dalloc(&e->d_tap_pitchf, F * S * 2));
+    if (!train_mode) CKD(dalloc(&e->d_tap_g, F * S * kBands));
   }
   if (train_mode) {
     CKD(cudaDeviceSynchronize());
     *out = e;
     return PNB_OK;
   }
-  // network state and scratch
-  CKD(dalloc(&e->ring_fc, 5 * S * 128));
-  CKD(dalloc(&e->ring_c1, 3 * S * 512));
+  // network state; the conv rings and gate sums are scratch of the fp32 path only
   CKD(dalloc(&e->c2, S * 512));
   for (int i = 0; i < 5; i++)
     for (int p = 0; p < 2; p++) CKD(dalloc(&e->h[i][p], S * e->gru[i].H));
-  CKD(dalloc(&e->zr, S * 1024));
-  CKD(dalloc(&e->nx, S * 512));
-  CKD(dalloc(&e->nh, S * 512));
+  if (!(flags & PNB_NN_TENSOR)) {
+    CKD(dalloc(&e->ring_fc, 5 * S * 128));
+    CKD(dalloc(&e->ring_c1, 3 * S * 512));
+    CKD(dalloc(&e->zr, S * 1024));
+    CKD(dalloc(&e->nx, S * 512));
+    CKD(dalloc(&e->nh, S * 512));
+  }
   if (flags & PNB_NN_TENSOR) {
     int trc = tc_prepare(e, model);
     if (trc) { pnb_destroy(e); return trc; }
@@ -261,7 +274,7 @@ extern "C" void pnb_destroy(pnb_engine *e) {
   tc_release(e);
   float *fl[] = {e->fc.W, e->fc.b, e->conv1.W, e->conv1.b, e->conv2.W, e->conv2.b, e->fc_gb.W, e->fc_gb.b,
                  e->fc_rb.W, e->fc_rb.b, e->d_pcm, e->d_synth, e->d_last_gain, e->d_feat, e->d_Ex, e->d_gr,
-                 e->d_tap_pitchf, e->ring_fc, e->ring_c1, e->c2, e->zr, e->nx, e->nh, e->d_hin, e->d_hout,
+                 e->d_tap_pitchf, e->d_tap_g, e->ring_fc, e->ring_c1, e->c2, e->zr, e->nx, e->nh, e->d_hin, e->d_hout,
                  e->d_raw, e->d_records};
   for (float *p : fl) if (p) cudaFree(p);
   for (int i = 0; i < 5; i++) {
@@ -275,6 +288,8 @@ extern "C" void pnb_destroy(pnb_engine *e) {
   if (e->d_P) cudaFree(e->d_P);
   if (e->d_sil) cudaFree(e->d_sil);
   if (e->d_last_period) cudaFree(e->d_last_period);
+  if (e->d_status) cudaFree(e->d_status);
+  if (e->h_status) cudaFreeHost(e->h_status);
   if (e->d_tap_pitch) cudaFree(e->d_tap_pitch);
   if (e->d_tab) cudaFree(e->d_tab);
   if (e->d_hin16) cudaFree(e->d_hin16);
@@ -297,7 +312,8 @@ extern "C" void pnb_destroy(pnb_engine *e) {
 extern "C" int pnb_reset(pnb_engine *e) {
   if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
   CK(cudaSetDevice(e->device));
-  CK(cudaDeviceSynchronize());
+  cudaDeviceSynchronize();  // a poisoned engine may carry a sticky launch error of its own; the memsets below report a dead context
+  cudaGetLastError();
   const size_t S = e->S;
   CK(cudaMemset(e->d_pcm, 0, S * e->pcm_stride * sizeof(float)));
   e->line_off = 0;
@@ -306,13 +322,16 @@ extern "C" int pnb_reset(pnb_engine *e) {
   CK(cudaMemset(e->d_ering, 0, (size_t)e->ring * S * kBands * sizeof(float)));
   CK(cudaMemset(e->d_last_period, 0, S * sizeof(int)));
   CK(cudaMemset(e->d_last_gain, 0, S * sizeof(float)));
+  CK(cudaMemset(e->d_status, 0, sizeof(int)));
+  *e->h_status = 0;
   e->hop = 0;
+  e->poisoned = false;
   if (e->flags & PNB_TRAIN_DATA) {
     CK(cudaDeviceSynchronize());
     return PNB_OK;
   }
-  CK(cudaMemset(e->ring_fc, 0, 5 * S * 128 * sizeof(float)));
-  CK(cudaMemset(e->ring_c1, 0, 3 * S * 512 * sizeof(float)));
+  if (e->ring_fc) CK(cudaMemset(e->ring_fc, 0, 5 * S * 128 * sizeof(float)));
+  if (e->ring_c1) CK(cudaMemset(e->ring_c1, 0, 3 * S * 512 * sizeof(float)));
   CK(cudaMemset(e->c2, 0, S * 512 * sizeof(float)));
   for (int i = 0; i < 5; i++)
     for (int p = 0; p < 2; p++) CK(cudaMemset(e->h[i][p], 0, S * e->gru[i].H * sizeof(float)));
@@ -469,15 +488,10 @@ static int advance_line(pnb_engine *e, int F, cudaStream_t st) {
   return n;
 }
 
-static int process_device(pnb_engine *e, const float *d_in, const short *d_in16, size_t in_stride, float *d_out,
-                          short *d_out16, size_t out_stride, int F, float *d_gr, cudaStream_t st) {
-  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
-  if (e->flags & PNB_TRAIN_DATA) return fail(PNB_ERR_ARG, "engine was created with PNB_TRAIN_DATA: use pnb_train_records_*");
-  if (F < 1 || F > e->Fmax) return fail(PNB_ERR_ARG, "n_frames %d outside [1, %d]", F, e->Fmax);
-  if ((!d_in && !d_in16) || (!d_out && !d_out16)) return fail(PNB_ERR_ARG, "input/output pointer is NULL");
-  if (in_stride < (size_t)F * kFrame || out_stride < (size_t)F * kFrame)
-    return fail(PNB_ERR_ARG, "row stride smaller than n_frames*480");
-  CK(cudaSetDevice(e->device));
+// Enqueues one call.  Host-side stream state (hop counter, line offset, GRU buffer parity) is committed only after
+// every launch was accepted; a failure in between leaves work half-enqueued, so the engine is poisoned until pnb_reset.
+static int process_device_enqueue(pnb_engine *e, const float *d_in, const short *d_in16, size_t in_stride, float *d_out,
+                                  short *d_out16, size_t out_stride, int F, float *d_gr, cudaStream_t st, long long *n_out) {
   const int S = e->S;
   long long n = 0;
   float *line = e->d_pcm + e->line_off;  // this call's [history | new hops] window of every row
@@ -489,33 +503,47 @@ static int process_device(pnb_engine *e, const float *d_in, const short *d_in16,
   a.last_period = e->d_last_period; a.last_gain = e->d_last_gain;
   a.tap_pitch = e->d_tap_pitch; a.tap_pitchf = e->d_tap_pitchf;
   { ProfScope ps(e, PNB_K_ANALYSIS, st); n += launch_analysis(a, st); }
+  CK(cudaGetLastError());
   if (e->flags & PNB_NN_TENSOR) {
     int k = tc_begin_call(e, F, st);
     if (k < 0) return k;
     n += k;
-  }
-  for (int t = 0; t < F; t++) {
-    if (e->flags & PNB_NN_TENSOR) {
-      int k = tc_step(e, t, st);
-      if (k < 0) return k;
-      n += k;
-    } else {
-      n += nn_step_f32(e, t, st);
-    }
-  }
-  if (e->flags & PNB_NN_TENSOR) {
-    int k = tc_end_call(e, F, st);
-    if (k < 0) return k;
+    if ((k = tc_gru_chain(e, F, st)) < 0) return k;
     n += k;
+    if ((k = tc_end_call(e, F, st)) < 0) return k;
+    n += k;
+  } else {
+    for (int t = 0; t < F; t++) n += nn_step_f32(e, t, st);
   }
   SynthesisArgs s;
   s.zring = e->d_zring; s.ring = e->ring; s.hop0 = e->hop; s.P = e->d_P; s.gr = e->d_gr; s.Ex = e->d_Ex; s.silence = e->d_sil; s.n_streams = S; s.n_frames = F;
   s.tab = e->d_tab; s.synth_mem = e->d_synth; s.out = d_out; s.out16 = d_out16; s.out_stride = out_stride;
   s.postfilter = (e->flags & PNB_POSTFILTER) ? 1 : 0;
+  s.tap_g = e->d_tap_g;
   { ProfScope ps(e, PNB_K_SYNTHESIS, st); n += launch_synthesis(s, st); }
   n += advance_line(e, F, st);
   if (d_gr) CK(cudaMemcpyAsync(d_gr, e->d_gr, (size_t)F * S * 68 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   CK(cudaGetLastError());
+  *n_out = n;
+  return PNB_OK;
+}
+
+static int process_device(pnb_engine *e, const float *d_in, const short *d_in16, size_t in_stride, float *d_out,
+                          short *d_out16, size_t out_stride, int F, float *d_gr, cudaStream_t st) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  if (e->flags & PNB_TRAIN_DATA) return fail(PNB_ERR_ARG, "engine was created with PNB_TRAIN_DATA: use pnb_train_records_*");
+  if (e->poisoned) return fail(PNB_ERR_CUDA, "an earlier call failed while enqueuing work; the streams' state is undefined until pnb_reset");
+  if (F < 1 || F > e->Fmax) return fail(PNB_ERR_ARG, "n_frames %d outside [1, %d]", F, e->Fmax);
+  if ((!d_in && !d_in16) || (!d_out && !d_out16)) return fail(PNB_ERR_ARG, "input/output pointer is NULL");
+  if (in_stride < (size_t)F * kFrame || out_stride < (size_t)F * kFrame)
+    return fail(PNB_ERR_ARG, "row stride smaller than n_frames*480");
+  CK(cudaSetDevice(e->device));
+  long long n = 0;
+  const int rc = process_device_enqueue(e, d_in, d_in16, in_stride, d_out, d_out16, out_stride, F, d_gr, st, &n);
+  if (rc) {
+    e->poisoned = true;
+    return rc;
+  }
   e->hop += F;
   e->last_frames = F;
   e->launches += n;
@@ -600,6 +628,15 @@ extern "C" int pnb_train_records_host(pnb_engine *e, const short *speech, size_t
   return PNB_OK;
 }
 
+// after the stream that carried the status copy was synchronised
+static int report_status(pnb_engine *e) {
+  if (*e->h_status & 1)
+    return fail(PNB_ERR_DOMAIN, "tensor path: a pre-activation left the domain of the reference's tansig_approx (|x| >= 8.5e7, "
+                                "src/vec.h:63 is undefined there); results since the last pnb_reset are not the reference's -- "
+                                "use PNB_NN_FP32 for such input");
+  return PNB_OK;
+}
+
 template <typename T>
 static int process_host(pnb_engine *e, const T *in, size_t in_stride, T *out, size_t out_stride, int F, float *gr,
                         T **d_in_p, T **d_out_p) {
@@ -623,8 +660,9 @@ static int process_host(pnb_engine *e, const T *in, size_t in_stride, T *out, si
   if (rc) return rc;
   CK(cudaMemcpy2DAsync(out, out_stride * sizeof(T), *d_out_p, row * sizeof(T), w, S, cudaMemcpyDeviceToHost, e->stream));
   if (gr) CK(cudaMemcpyAsync(gr, e->d_gr, (size_t)F * S * 68 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->h_status, e->d_status, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  return PNB_OK;
+  return report_status(e);
 }
 
 extern "C" int pnb_process_host_f32(pnb_engine *e, const float *in, size_t in_stride, float *out, size_t out_stride,
@@ -747,8 +785,18 @@ extern "C" int pnb_wait(pnb_engine *e) {
   if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
   CK(cudaSetDevice(e->device));
   if (e->s_in) CK(cudaStreamSynchronize(e->s_in));
+  CK(cudaMemcpyAsync(e->h_status, e->d_status, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   if (e->s_out) CK(cudaStreamSynchronize(e->s_out));
+  return report_status(e);
+}
+extern "C" int pnb_check(pnb_engine *e, void *cuda_stream) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  int rc = pnb_wait(e);
+  if (rc) return rc;
+  if (e->poisoned) return fail(PNB_ERR_CUDA, "an earlier call failed while enqueuing work; pnb_reset the engine");
   return PNB_OK;
 }
 
@@ -777,6 +825,7 @@ extern "C" int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes
     case PNB_TAP_P: src = e->d_P; bytes = n * kBins * 8; break;
     case PNB_TAP_EX: src = e->d_Ex; bytes = n * kBands * 4; break;
     case PNB_TAP_GR: src = e->d_gr; bytes = n * 68 * 4; break;
+    case PNB_TAP_G_USED: src = e->d_tap_g; bytes = n * kBands * 4; break;
     case PNB_TAP_NN_C2: src = e->c2; bytes = (size_t)e->S * 512 * 4; break;
     case PNB_TAP_NN_H0: case PNB_TAP_NN_H0 + 1: case PNB_TAP_NN_H0 + 2: case PNB_TAP_NN_H0 + 3: case PNB_TAP_NN_H0 + 4: {
       int li = what - PNB_TAP_NN_H0;
@@ -788,6 +837,115 @@ extern "C" int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes
   if (dst_bytes < bytes) return fail(PNB_ERR_ARG, "tap %d needs %zu bytes, got %zu", what, bytes, dst_bytes);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return PNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-stream state export / import (the reference's DenoiseState + RNNState, src/denoise.cpp:71-85, nnet_data.h:28-38,
+// reduced to what is live: SURVEY.md App. A.2) -- for moving a stream between engines / GPUs at a call boundary
+// ------------------------------------------------------------------------------------------
+namespace {
+struct StreamState {
+  unsigned magic, version;
+  float pcm[kKeep];          // the last 5280 input samples (comb_buf without its newest hop)
+  float synth[kFrame];       // overlap-add memory
+  int last_period;
+  float last_gain;
+  float spec[5][2 * kBins];  // spectra of the last five windowed blocks (analysis spectrum of the next five hops), oldest first
+  float eband[5][kBands];    // their band energies
+  float fc_hist[4][128];     // conv1 input history (last four fc outputs), oldest first
+  float c1_hist[2][512];     // conv2 input history (last two conv1 outputs)
+  float h[4 * 512 + 128];    // gru1, gru2, gru3, gru_gb, gru_rb
+};
+constexpr unsigned kStateMagic = 0x53424E50u;  // "PNBS"
+}  // namespace
+
+extern "C" size_t pnb_state_size(void) { return sizeof(StreamState); }
+
+static int state_args(pnb_engine *e, int stream, const void *buf, size_t bytes) {
+  if (!e || !buf) return fail(PNB_ERR_ARG, "NULL argument");
+  if (stream < 0 || stream >= e->S) return fail(PNB_ERR_ARG, "stream %d outside [0, %d)", stream, e->S);
+  if (bytes < sizeof(StreamState)) return fail(PNB_ERR_ARG, "state buffer of %zu bytes, need pnb_state_size() = %zu", bytes, sizeof(StreamState));
+  if (e->poisoned) return fail(PNB_ERR_CUDA, "engine state is undefined after a failed call; pnb_reset it");
+  return PNB_OK;
+}
+
+extern "C" int pnb_get_state(pnb_engine *e, int stream, void *dst, size_t bytes) {
+  int rc = state_args(e, stream, dst, bytes);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  StreamState *st = static_cast<StreamState *>(dst);
+  memset(st, 0, sizeof *st);
+  st->magic = kStateMagic; st->version = 1;
+  const size_t s = stream, S = e->S;
+  CK(cudaMemcpy(st->pcm, e->d_pcm + s * e->pcm_stride + e->line_off, kKeep * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(st->synth, e->d_synth + s * kFrame, kFrame * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&st->last_period, e->d_last_period + s, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&st->last_gain, e->d_last_gain + s, 4, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 5; k++) {
+    const long c = e->hop - 5 + k;
+    const size_t slot = (size_t)((c % e->ring + e->ring) % e->ring);
+    CK(cudaMemcpy(st->spec[k], e->d_zring + (slot * S + s) * kBins, kBins * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(st->eband[k], e->d_ering + (slot * S + s) * kBands, kBands * 4, cudaMemcpyDeviceToHost));
+  }
+  if (e->flags & PNB_TRAIN_DATA) return PNB_OK;
+  size_t off = 0;
+  for (int li = 0; li < 5; li++) {
+    const size_t H = e->gru[li].H;
+    CK(cudaMemcpy(st->h + off, e->h[li][e->par[li]] + s * H, H * 4, cudaMemcpyDeviceToHost));
+    off += H;
+  }
+  if (e->flags & PNB_NN_TENSOR) return tc_get_stream_hist(e, stream, &st->fc_hist[0][0], &st->c1_hist[0][0]);
+  for (int k = 0; k < 4; k++) {
+    const long c = e->hop - 4 + k;
+    CK(cudaMemcpy(st->fc_hist[k], e->ring_fc + ((size_t)((c % 5 + 5) % 5) * S + s) * 128, 128 * 4, cudaMemcpyDeviceToHost));
+  }
+  for (int k = 0; k < 2; k++) {
+    const long c = e->hop - 2 + k;
+    CK(cudaMemcpy(st->c1_hist[k], e->ring_c1 + ((size_t)((c % 3 + 3) % 3) * S + s) * 512, 512 * 4, cudaMemcpyDeviceToHost));
+  }
+  return PNB_OK;
+}
+
+extern "C" int pnb_set_state(pnb_engine *e, int stream, const void *src, size_t bytes) {
+  int rc = state_args(e, stream, src, bytes);
+  if (rc) return rc;
+  const StreamState *st = static_cast<const StreamState *>(src);
+  if (st->magic != kStateMagic || st->version != 1) return fail(PNB_ERR_ARG, "not a pnb_get_state blob (magic/version)");
+  if (e->flags & PNB_NN_TENSOR)
+    for (size_t i = 0; i < sizeof st->h / sizeof(float); i++)
+      if (!(fabsf(st->h[i]) <= 1.0001f))
+        return fail(PNB_ERR_ARG, "GRU state value %g outside [-1, 1]: not a state the network can reach", (double)st->h[i]);
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  const size_t s = stream, S = e->S;
+  CK(cudaMemcpy(e->d_pcm + s * e->pcm_stride + e->line_off, st->pcm, kKeep * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->d_synth + s * kFrame, st->synth, kFrame * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->d_last_period + s, &st->last_period, 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->d_last_gain + s, &st->last_gain, 4, cudaMemcpyHostToDevice));
+  for (int k = 0; k < 5; k++) {
+    const long c = e->hop - 5 + k;
+    const size_t slot = (size_t)((c % e->ring + e->ring) % e->ring);
+    CK(cudaMemcpy(e->d_zring + (slot * S + s) * kBins, st->spec[k], kBins * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_ering + (slot * S + s) * kBands, st->eband[k], kBands * 4, cudaMemcpyHostToDevice));
+  }
+  if (e->flags & PNB_TRAIN_DATA) return PNB_OK;
+  size_t off = 0;
+  for (int li = 0; li < 5; li++) {
+    const size_t H = e->gru[li].H;
+    CK(cudaMemcpy(e->h[li][e->par[li]] + s * H, st->h + off, H * 4, cudaMemcpyHostToDevice));
+    off += H;
+  }
+  if (e->flags & PNB_NN_TENSOR) return tc_set_stream_hist(e, stream, &st->fc_hist[0][0], &st->c1_hist[0][0], st->h);
+  for (int k = 0; k < 4; k++) {
+    const long c = e->hop - 4 + k;
+    CK(cudaMemcpy(e->ring_fc + ((size_t)((c % 5 + 5) % 5) * S + s) * 128, st->fc_hist[k], 128 * 4, cudaMemcpyHostToDevice));
+  }
+  for (int k = 0; k < 2; k++) {
+    const long c = e->hop - 2 + k;
+    CK(cudaMemcpy(e->ring_c1 + ((size_t)((c % 3 + 3) % 3) * S + s) * 512, st->c1_hist[k], 512 * 4, cudaMemcpyHostToDevice));
+  }
   return PNB_OK;
 }
 
@@ -857,11 +1015,62 @@ extern "C" void pnb_model_free(pnb_model *m) {
   if (m) delete reinterpret_cast<BlobModel *>(m);
 }
 
+// ------------------------------------------------------------------------------------------
+// the pitch analysis alone (BASELINE.json config 5)
+// ------------------------------------------------------------------------------------------
+extern "C" int pnb_pitch_only_device(const float *d_pitch_buf, size_t stride, long long n_units, const int *d_prev_period,
+                                     const float *d_prev_gain, int *d_period, float *d_corr, float *d_gain, int *d_lag,
+                                     void *cuda_stream) {
+  if (!d_pitch_buf || !d_period || !d_corr || !d_gain) return fail(PNB_ERR_ARG, "NULL argument");
+  if (n_units < 1 || stride < 1728) return fail(PNB_ERR_ARG, "n_units must be >= 1 and stride >= 1728");
+  if (n_units > (1ll << 31) - 8) return fail(PNB_ERR_ARG, "n_units above 2^31");
+  PitchOnlyArgs a;
+  a.buf = d_pitch_buf; a.stride = stride; a.n_units = (long)n_units; a.prev_period = d_prev_period; a.prev_gain = d_prev_gain;
+  a.T = d_period; a.corr = d_corr; a.gain = d_gain; a.lag = d_lag;
+  if (launch_pitch_only(a, (cudaStream_t)cuda_stream) < 0) return fail(PNB_ERR_CUDA, "pitch_only_kernel could not be configured");
+  CK(cudaGetLastError());
+  return PNB_OK;
+}
+
+// host buffers: staging grows on demand and is kept per host thread (there is no engine to own it)
+extern "C" int pnb_pitch_only_host(const float *pitch_buf, size_t stride, long long n_units, const int *prev_period,
+                                   const float *prev_gain, int *period, float *corr, float *gain, int *lag) {
+  if (!pitch_buf || !period || !corr || !gain) return fail(PNB_ERR_ARG, "NULL argument");
+  if (n_units < 1 || stride < 1728) return fail(PNB_ERR_ARG, "n_units must be >= 1 and stride >= 1728");
+  struct Staging { float *buf = nullptr; int *i4 = nullptr; float *f3 = nullptr; long long cap = 0; int dev = -1; cudaStream_t st = nullptr; };
+  static thread_local Staging g;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (g.cap < n_units || g.dev != dev) {
+    if (g.buf) { cudaFree(g.buf); cudaFree(g.i4); cudaFree(g.f3); g.buf = nullptr; }
+    if (!g.st || g.dev != dev) CK(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
+    CK(cudaMalloc((void **)&g.buf, (size_t)n_units * 1728 * sizeof(float)));
+    CK(cudaMalloc((void **)&g.i4, (size_t)n_units * 3 * sizeof(int)));
+    CK(cudaMalloc((void **)&g.f3, (size_t)n_units * 3 * sizeof(float)));
+    g.cap = n_units; g.dev = dev;
+  }
+  const size_t n = (size_t)n_units;
+  int *d_T = g.i4, *d_lag = g.i4 + n, *d_pT = g.i4 + 2 * n;
+  float *d_corr = g.f3, *d_gain = g.f3 + n, *d_pg = g.f3 + 2 * n;
+  CK(cudaMemcpy2DAsync(g.buf, 1728 * sizeof(float), pitch_buf, stride * sizeof(float), 1728 * sizeof(float), n, cudaMemcpyHostToDevice, g.st));
+  if (prev_period) CK(cudaMemcpyAsync(d_pT, prev_period, n * sizeof(int), cudaMemcpyHostToDevice, g.st));
+  if (prev_gain) CK(cudaMemcpyAsync(d_pg, prev_gain, n * sizeof(float), cudaMemcpyHostToDevice, g.st));
+  int rc = pnb_pitch_only_device(g.buf, 1728, n_units, prev_period ? d_pT : nullptr, prev_gain ? d_pg : nullptr, d_T, d_corr, d_gain,
+                                 lag ? d_lag : nullptr, g.st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(period, d_T, n * sizeof(int), cudaMemcpyDeviceToHost, g.st));
+  CK(cudaMemcpyAsync(corr, d_corr, n * sizeof(float), cudaMemcpyDeviceToHost, g.st));
+  CK(cudaMemcpyAsync(gain, d_gain, n * sizeof(float), cudaMemcpyDeviceToHost, g.st));
+  if (lag) CK(cudaMemcpyAsync(lag, d_lag, n * sizeof(int), cudaMemcpyDeviceToHost, g.st));
+  CK(cudaStreamSynchronize(g.st));
+  return PNB_OK;
+}
+
 extern "C" long long pnb_launch_count(const pnb_engine *e) { return e ? e->launches : 0; }
 extern "C" int pnb_launches_per_call(const pnb_engine *e, int n_frames) {
   if (!e) return 0;
   // without the history move of advance_line (at most one more launch per call)
-  if (e->flags & PNB_NN_TENSOR) return 3 + tc_launches_per_call(e) + tc_launches_per_step(e) * n_frames;
+  if (e->flags & PNB_NN_TENSOR) return 3 + tc_launches_per_call(e);
   return 3 + 25 * n_frames;
 }
 extern "C" int pnb_n_streams(const pnb_engine *e) { return e ? e->S : 0; }

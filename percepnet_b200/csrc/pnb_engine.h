@@ -43,6 +43,7 @@ struct pnb_engine {
   float *d_gr = nullptr;
   int *d_tap_pitch = nullptr;
   float *d_tap_pitchf = nullptr;
+  float *d_tap_g = nullptr;   // [F][S][34] gains as applied (PNB_KEEP_TAPS)
 
   // network state (fp32 path): conv rings, GRU states (ping-pong), scratch sums
   float *ring_fc = nullptr;  // [5][S][128] outputs of fc for hops c-4..c
@@ -67,6 +68,12 @@ struct pnb_engine {
   pnb_tc_state *tc = nullptr;
   int last_frames = 0;
   long long launches = 0;
+  // status word on the device: bit 0 = an activation left the domain in which the reference's tansig_approx is
+  // defined (tensor path only; reported as PNB_ERR_DOMAIN by the synchronising entry points, cleared by pnb_reset)
+  int *d_status = nullptr;
+  int *h_status = nullptr;  // pinned host copy, refreshed by the synchronising entry points
+  // a call failed after it had started to enqueue work: the streams' state is undefined until pnb_reset
+  bool poisoned = false;
 
   // optional per-kernel-class timing (pnb_profile_enable): CUDA events around every launch
   bool profiling = false;
@@ -81,15 +88,16 @@ struct pnb_engine {
   }
 };
 
-// tensor-core path hooks (pnb_nn_tc.cu); return PNB_OK / negative error, tc_step returns launches
+// tensor-core path hooks (pnb_nn_tc.cu); return PNB_OK / negative error; the call phases return their launch count
 int tc_prepare(pnb_engine *e, const pnb_model *model);
 void tc_release(pnb_engine *e);
 int tc_reset(pnb_engine *e);
 int tc_begin_call(pnb_engine *e, int F, cudaStream_t st);  // hop-parallel front of the network, all F hops
-int tc_step(pnb_engine *e, int t, cudaStream_t st);
-int tc_end_call(pnb_engine *e, int F, cudaStream_t st);    // hop-parallel tail: the two output layers, state carry
+int tc_gru_chain(pnb_engine *e, int F, cudaStream_t st);   // the five GRUs of all F hops, one persistent launch
+int tc_end_call(pnb_engine *e, int F, cudaStream_t st);    // hop-parallel tail: the two output layers, slot carry
 int tc_launches_per_call(const pnb_engine *e);
-int tc_launches_per_step(const pnb_engine *e);
+int tc_get_stream_hist(pnb_engine *e, int s, float *fc_hist, float *c1_hist);   // pnb_get_state
+int tc_set_stream_hist(pnb_engine *e, int s, const float *fc_hist, const float *c1_hist, const float *h);  // pnb_set_state
 
 // RAII marker used by the launch schedule: records an event pair around a launch when profiling
 struct ProfScope {

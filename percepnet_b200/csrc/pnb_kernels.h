@@ -40,6 +40,7 @@ struct SynthesisArgs {
   short *out16;            // int16 output rows or null
   size_t out_stride;
   int postfilter;
+  float *tap_g;            // [F][S][34] or null: the band gains as applied (after the optional post-filter)
 };
 
 // training-data records (train(), denoise.cpp:600-787): streams [0,N) are the noisy signals, [N,2N) the clean ones
@@ -53,6 +54,20 @@ struct LabelArgs {
   size_t pair_stride;
 };
 int launch_train_labels(const LabelArgs &a, cudaStream_t st);
+
+// pitch analysis alone (BASELINE.json config 5): unit u reads buf[u*stride .. +1728), writes T/corr/gain (and the
+// pitch_search lag when lag != null); prev_period / prev_gain null = 0 (a fresh stream)
+struct PitchOnlyArgs {
+  const float *buf;
+  size_t stride;
+  long n_units;
+  const int *prev_period;
+  const float *prev_gain;
+  int *T;
+  float *corr, *gain;
+  int *lag;
+};
+int launch_pitch_only(const PitchOnlyArgs &a, cudaStream_t st);
 
 cudaError_t dsp_configure();
 int launch_analysis(const AnalysisArgs &a, cudaStream_t st);

@@ -1,25 +1,35 @@
 // pnb_nn_tc.cu -- the gain network on Blackwell tensor cores (tcgen05 + TMEM + TMA), batched over streams.
 //
 // Replaces the reference's 35 scalar GEMVs per hop (/root/reference/src/nnet.cpp:59-200, rnn.cpp:42-81)
-// for the layers that carry 99 % of the MACs: conv1, conv2 and the five GRUs.  The rows of every
-// contraction are the concurrent streams (M = S), so the operation is genuinely dense.
+// for the layers that carry 99.9 % of the MACs: conv1, conv2, the five GRUs and the two output layers.  The rows
+// of every contraction are the concurrent streams (M = S), so the operation is genuinely dense.
 //
 // Precision.  The parity bar (1e-4 relative on g/r, +-1 LSB on PCM) rules out plain 16-bit operands.
-// Every fp32 operand is therefore split into 16-bit terms whose sum reproduces it, and the product is
-// expanded into the tensor-core products that matter, all accumulated in fp32 in TMEM:
-//   GRUs (bounded inputs):    x = xh + xl, w = wh + wl in fp16, both pre-scaled by powers of two
-//                             x w ~= xh wh + xh wl + xl wh                       (3 MMAs, error ~2^-22)
-//   conv1/conv2 (ReLU inputs, unbounded): three bf16 terms each side, the six products >= 2^-16 (6 MMAs)
-// Per tile: TMA (SWIZZLE_64B boxes of 32 k) -> 4/5-stage shared-memory ring -> one elected thread issues
-// tcgen05.mma (M=128) -> accumulators in TMEM -> four epilogue warps read them back with tcgen05.ld and
-// apply bias, the reference's tansig-table activations and the GRU gate arithmetic, writing the new
-// state in fp32 and already split for the next contraction.
+// Every fp32 operand is therefore split into two 16-bit terms whose sum reproduces it to ~2^-22, and the three
+// significant products are issued as separate tensor-core MMAs into the same fp32 TMEM accumulator:
+//   x w ~= xh wh + xh wl + xl wh
+//   GRUs / output layers (inputs bounded by tanh): fp16 terms, both sides pre-scaled by powers of two
+//   conv1 / conv2 (ReLU inputs, unbounded):        bf16 terms
+//
+// Two kernels, both persistent, warp-specialised, one CTA per SM, CTAs paired into clusters of two that act as
+// ONE tensor-core unit (tcgen05 cta_group::2, M = 256):
+//   tc_gemm_kernel   one dense layer over all rows (conv1, conv2, fc_gb, fc_rb run once per call over F*S rows)
+//   gru_chain_kernel the five GRUs of all F hops of a call in ONE launch.  A tile (hop, layer, 256 streams,
+//                    64 hidden units) depends only on tiles of the same 256 streams (layer below at this hop,
+//                    own layer at the previous hop), so the recurrence is a per-(layer, row-pair) counter that
+//                    the epilogue warps bump (release) and the TMA producer polls (acquire) -- no grid barrier,
+//                    no launch boundary between layers or hops.
+// Warp roles per CTA: warp 0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_64B boxes of 32 k into a 7-stage
+// ring; its own 128 activation rows and HALF of the weight rows of the tile), warp 1 (leader CTA) = MMA issuer,
+// warp 2 = TMEM allocator, warps 4-11 = epilogue (tcgen05.ld, one stream per thread).  Two accumulator buffers in
+// TMEM: the epilogue of tile i overlaps the MMAs of tile i+1.  The issue loops run warp-converged on uniform
+// values so that descriptors live in uniform registers (no per-instruction lane election): ~6 SASS instructions
+// per tcgen05.mma instead of 23 -- with one thread issuing, that loop was what paced the tensor pipe in round 1.
 //
 // The GRU tile holds, for 64 hidden units, four accumulators per unit (z, r, W_n x, U_n h: nnet.cpp:136-173
 // needs the last two apart), 256 TMEM columns [nx | z | r | nh]; weight rows are packed gate-interleaved per tile
-// (input part [n|z|r], recurrent part [z|r|n]) so that one TMA box brings a tile's rows and one N = 192 MMA
-// covers it -- the kernel is bound by shared-memory operand reads (A is re-read by every MMA), so fewer, wider
-// MMAs matter more than anything else here.
+// (input part [n|z|r], recurrent part [z|r|n]) so that one TMA box brings a tile's rows and ONE N = 192 MMA
+// per product covers it.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -37,34 +47,41 @@ using namespace pnb;
 
 namespace {
 
-constexpr int TM = 128;   // streams per tile (UMMA M)
+constexpr int TM = 128;   // streams per CTA tile (UMMA M = 256 per pair)
 constexpr int BK = 32;    // k per pipeline stage: 64-byte rows, SWIZZLE_64B
 constexpr int HT = 64;    // hidden units per GRU tile
 constexpr int GRU_BN = 3 * HT;  // weight rows per GRU tile (z|r|n)
 // Epilogue warps per CTA: warp 4 + q + 4 k reads TMEM lane quadrant q; the kEpiSets warps of a quadrant share its
-// rows' columns 16 at a time.  The epilogue (gate math, splits, stores) is what a tile costs most, see DESIGN.md 3.2.
+// rows' columns 16 at a time.
 constexpr int kEpiSets = 2;
-constexpr int kTcThreads = 32 * (4 + 4 * kEpiSets);
+constexpr int kEpiWarps = 4 * kEpiSets;
+constexpr int kTcThreads = 32 * (4 + kEpiWarps);
 constexpr int DENSE_BN = 256;   // output columns per dense (conv) tile: the widest MMA, least operand traffic per MAC
-constexpr int kConvTerms = 2;         // bf16 terms per operand on the conv layers (2: 16-bit operands, 3 products)
 constexpr float kActScale = 1024.f;  // fp16 activations are stored x 2^10 (keeps the low term normal)
+// |pre-activation| from which the reference's tansig_approx (vec.h:63) overflows its float->int conversion
+constexpr float kTanhDomain = 8.5e7f;
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity)
       : "memory");
 }
 // ---- CTA-pair (cta_group::2) forms: the two CTAs of a cluster act as one M = 256 tensor-core unit ----
@@ -78,16 +95,16 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // TMA load into this CTA's shared memory whose bytes are accounted on the LEADER CTA's mbarrier
-__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(x), "r"(y),
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(x), "r"(y),
       "l"(0x1000000000000000ull)  // EVICT_NORMAL
       : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {  // arrive on the leader CTA's copy of `bar`
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the leader CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
@@ -96,20 +113,19 @@ __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
 }
-// D[256 x N] (+)= A[256 x 16] B[N x 16]^T : rows 0..127 from the leader's A tile / TMEM, 128..255 from the peer's;
-// each CTA's shared memory supplies N/2 rows of B
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[256 x N] += A[256 x 16] B[N x 16]^T : rows 0..127 from the leader's A tile / TMEM, 128..255 from the peer's;
+// each CTA's shared memory supplies N/2 rows of B.  Every MMA accumulates (the epilogue zeroes the buffer).
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "l"(adesc), "l"(bdesc), "r"(idesc)
       : "memory");
 }
 // completion of all MMAs issued so far arrives on `bar` in BOTH CTAs
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"((uint16_t)3)
                : "memory");
 }
@@ -120,369 +136,584 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
-  uint32_t r[16];
+// 16 consecutive accumulator columns of this thread's TMEM lane; the values are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// shared-memory matrix descriptor, K-major operand, SWIZZLE_64B: rows of 64 bytes, 8-row groups 512 bytes apart
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO [16,30), SBO [32,46), version=1 [46,48), layout [61,64) with 4 = SW64)
-__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)4 << 61);
-}
+// Shared-memory matrix descriptor, K-major operand, SWIZZLE_64B: rows of 64 bytes, 8-row groups 512 bytes apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO [16,30), SBO [32,46), version=1 [46,48), layout [61,64) with 4 = SW64).
+// The high word is a constant; the low word is (address >> 4) | LBO and advances by plain addition (the shared
+// window is < 256 KB, so the 14-bit field never carries).
+constexpr uint32_t kDescHi = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFF) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 // instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, A/B format (0 fp16, 1 bf16), both K-major
 __host__ __device__ constexpr uint32_t idesc_f16(int n, int fmt) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);  // M = 256: the CTA pair
 }
 
 // ------------------------------------------------------------------------------------------ activations
-__device__ __forceinline__ float tansig_s(float x, const float *tbl) {  // vec.h:53-71, table in shared memory
-  float sign = 1.f;
-  if (x < 0.f) { x = -x; sign = -1.f; }
-  float fi = floorf(.5f + 25.f * x);
-  int i = (fi < 2147483648.f) ? (int)fi : (int)0x80000000;  // x86 cvttss2si semantics of the reference build
-  i = i < 200 ? i : 200;
-  i = i > 0 ? i : 0;
-  x -= .04f * i;
-  float y = tbl[i];
-  float dy = 1.f - y * y;
-  y = y + x * dy * (1.f - y * x);
-  return sign * y;
+// tansig_approx of vec.h:53-71 on the FMA/ALU pipes only.  The reference forms the table index with
+// floor(.5f + 25 x) -> (int); here t + 2^23 rounded toward -inf leaves floor(t) in the low mantissa bits (exact for
+// 0 <= t < 2^23), which replaces FRND + F2I + I2F (quarter-rate conversion pipe) by one FADD.RM and one FADD.
+// |x| is clamped at 8: from there on the reference returns exactly +-1 (index clamped at 200, where dy = 0).
+// NaN propagates (min.NaN); beyond |x| = 8.6e7 the reference's conversion overflows (undefined behaviour, x86
+// returns its argument) -- callers whose pre-activations can get there raise the engine's domain flag instead.
+__device__ __forceinline__ float tansig_s(float x, const float *tbl) {
+  float ax;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(ax) : "f"(fabsf(x)), "f"(8.0f));
+  const float t = fmaf(25.f, ax, .5f);
+  const float r = __fadd_rd(t, 8388608.f);
+  const int idx = __float_as_int(r) & 0xFF;           // floor(t) <= 200 (255 at most for a NaN payload; table has 256 slots)
+  const float fi = r - 8388608.f;
+  const float xr = fmaf(-.04f, fi, ax);
+  const float y = tbl[idx];
+  const float dy = fmaf(-y, y, 1.f);
+  const float u = fmaf(-y, xr, 1.f);
+  const float v = fmaf(xr * dy, u, y);
+  return __int_as_float(__float_as_int(v) | (__float_as_int(x) & 0x80000000));
 }
-__device__ __forceinline__ float sigmoid_s(float x, const float *tbl) { return .5f + .5f * tansig_s(.5f * x, tbl); }
+__device__ __forceinline__ float sigmoid_s(float x, const float *tbl) { return fmaf(.5f, tansig_s(.5f * x, tbl), .5f); }
 
-// ------------------------------------------------------------------------------------------ kernel
-struct TcSeg {
-  int a_map, b_map;  // indices into TcArgs::maps
-  int k_blocks;      // K / 32
-  int a_k0, b_k0;    // starting k (elements) in the A / B matrices
-  int recurrent;     // GRU: 0 -> the n rows accumulate W_n x, 1 -> U_n h
-  int a_row0;        // row of the A matrix that holds tile row 0 (hop / tap offset inside a multi-hop buffer)
-  int a_term_rows;   // row distance between the split terms inside this A buffer
-};
+// fp16 two-term split of 16 values (x 2^10), written as two 32-byte rows
+__device__ __forceinline__ void store_split_h16(const float *v, __half *hi_p, __half *lo_p) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float s0 = v[2 * i] * kActScale, s1 = v[2 * i + 1] * kActScale;
+    const __half2 h = __floats2half2_rn(s0, s1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+    hi[i] = *reinterpret_cast<const uint32_t *>(&h);
+    lo[i] = *reinterpret_cast<const uint32_t *>(&l);
+  }
+  uint4 *ph = reinterpret_cast<uint4 *>(hi_p), *pl = reinterpret_cast<uint4 *>(lo_p);
+  ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+}
+__device__ __forceinline__ void store_split_b16(const float *v, __nv_bfloat16 *t0_p, __nv_bfloat16 *t1_p) {
+  uint32_t a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    a[i] = *reinterpret_cast<const uint32_t *>(&h);
+    b[i] = *reinterpret_cast<const uint32_t *>(&l);
+  }
+  uint4 *p0 = reinterpret_cast<uint4 *>(t0_p), *p1 = reinterpret_cast<uint4 *>(t1_p);
+  p0[0] = make_uint4(a[0], a[1], a[2], a[3]); p0[1] = make_uint4(a[4], a[5], a[6], a[7]);
+  p1[0] = make_uint4(b[0], b[1], b[2], b[3]); p1[1] = make_uint4(b[4], b[5], b[6], b[7]);
+}
 
-struct TcArgs {
-  CUtensorMap maps[10];
-  TcSeg seg[5];
-  int n_seg;
-  int M;                // streams
-  int tiles_m, tiles_n; // tile grid; a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-  int b_term_rows;      // row distance between the split terms inside a packed weight matrix
-  int fmt;              // 0 fp16, 1 bf16
-  int debug;            // timing diagnostics (PNB_TC_DEBUG): 1 = issue no MMA (operand streaming only), 2 = issue no TMA load
-  float out_scale;      // 2^-(activation scale + weight scale)
-  const float *tansig;  // 201-entry table (global)
-  const float *bias;
-  // dense epilogue
-  int act;
-  int N;                // valid output columns
-  int ldc;              // row stride of out_f32
-  float *out_f32;       // [M][ldc] or null
-  int f32_row0;         // only rows >= f32_row0 are written to out_f32, at row - f32_row0
-  __half *out_h;        // fp16 two-term split [2][out_plane_rows][N] (x 2^10) or null
-  __nv_bfloat16 *out_b; // bf16 split [terms][out_plane_rows][N] or null
-  int out_row0;         // first row written inside a term plane of out_h / out_b
-  int out_plane_rows;   // rows per term plane of out_h / out_b
-  // GRU epilogue
-  int H;
-  const float *h_old;   // [M][H] fp32
-  float *h_new;         // [M][H] fp32
-  __half *h_new_h;      // fp16 split of the new state (x 2^10): [2][out_plane_rows][H], first row out_row0
-};
-
-template <int NA, int NB, int BN>
-struct StageLayout {
+// ------------------------------------------------------------------------------------------ shared kernel pieces
+template <int BN>
+struct StageLayout {  // two terms of A (this CTA's 128 rows) and two terms of this CTA's half of the B rows
   static constexpr int kABytes = TM * BK * 2;
-  static constexpr int kBBytes = (BN / 2) * BK * 2;  // each CTA of the pair holds half of the weight rows
-  static constexpr int kBytes = NA * kABytes + NB * kBBytes;
-  static constexpr int kPairBytes = kBytes;          // bytes one CTA brings per stage
+  static constexpr int kBBytes = (BN / 2) * BK * 2;
+  static constexpr int kBytes = 2 * kABytes + 2 * kBBytes;
 };
 
-// products of split terms that are kept: (a term, b term), largest first
-template <int NA, int NB> struct Products;
-template <> struct Products<2, 2> {
-  static constexpr int n = 3;
-  __device__ static constexpr int a(int i) { return i == 2 ? 1 : 0; }
-  __device__ static constexpr int b(int i) { return i == 1 ? 1 : 0; }
+struct Pipe {  // position in an mbarrier ring
+  uint32_t st = 0, ph = 0;
+  __device__ __forceinline__ void advance(uint32_t stages) {
+    if (++st == stages) { st = 0; ph ^= 1; }
+  }
 };
-__device__ __forceinline__ void split_h2(float v, __half &hi, __half &lo) {
-  // fp16 operands hold |x| < 64 (x 2^10 < 65504).  GRU inputs are tanh / state values in [-1, 1]; only when
-  // the reference's own tansig_approx leaves its defined domain (|pre-activation| >= 8.6e7, see tests) does
-  // a "tanh" exceed that, and then this path saturates instead of propagating the reference's garbage.
-  float s = fminf(fmaxf(v * kActScale, -65000.f), 65000.f);
-  hi = __float2half_rn(s);
-  lo = __float2half_rn(s - __half2float(hi));
-}
-__device__ __forceinline__ void split_b3(float v, __nv_bfloat16 &t0, __nv_bfloat16 &t1, __nv_bfloat16 &t2) {
-  t0 = __float2bfloat16_rn(v);
-  float r = v - __bfloat162float(t0);
-  t1 = __float2bfloat16_rn(r);
-  r = r - __bfloat162float(t1);
-  t2 = __float2bfloat16_rn(r);
-}
 
-__host__ __device__ constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
-
-// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = epilogue.  Two accumulator buffers in TMEM: the epilogue of tile i overlaps the MMAs of tile i+1.
-// CTAs run as pairs (cluster of 2, tcgen05 cta_group::2): the pair works on one weight tile for two adjacent
-// 128-stream row tiles as a single M = 256 MMA.  Each CTA loads its own A rows and HALF of the weight rows, the
-// leader issues the MMAs and the tensor cores of both SMs read B from both shared memories -- per SM that halves
-// the B operand traffic (global->shared and shared->tensor core), which is what bounds this kernel.
-// The accumulators are zeroed by the epilogue warps (tcgen05.st) so that every MMA accumulates.
-template <int NA, int NB, int BN, int STAGES, bool GRU>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_constant__ TcArgs args) {
-  using SL = StageLayout<NA, NB, BN>;
-  using PR = Products<NA, NB>;
-  constexpr int kAccCols = GRU ? 4 * HT : pow2_cols(BN);  // TMEM columns per accumulator buffer
-  constexpr int kTmemCols = 2 * kAccCols;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
+struct SmemCarve {
+  uint8_t *stages;
+  uint32_t full, empty, acc_full, acc_empty;  // shared-window addresses of the barrier arrays
+  uint32_t *tmem_slot;
+  float *tbl;
+};
+template <int STAGES, int STAGE_BYTES>
+__device__ __forceinline__ SmemCarve carve(uint8_t *smem_raw) {
   // the swizzled tiles need 512-byte (SW64) alignment; align the carve-up to 1024 by hand
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // carve: stages | barriers | tmem slot | tansig table
-  uint8_t *stage_base = smem;
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * SL::kBytes);
-  uint64_t *empty_bar = full_bar + STAGES;
-  uint64_t *acc_full = empty_bar + STAGES;   // [2] MMA -> epilogue
-  uint64_t *acc_empty = acc_full + 2;        // [2] epilogue -> MMA
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-  float *tbl = reinterpret_cast<float *>(tmem_slot + 2);
+  SmemCarve c;
+  c.stages = smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+  c.full = smem_u32(bars);
+  c.empty = c.full + 8 * STAGES;
+  c.acc_full = c.empty + 8 * STAGES;
+  c.acc_empty = c.acc_full + 16;
+  c.tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+  c.tbl = reinterpret_cast<float *>(c.tmem_slot + 4);
+  return c;
+}
+template <int STAGES, int STAGE_BYTES>
+constexpr size_t tc_smem_bytes() {
+  return (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 256 * 4 + 1024;
+}
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int crank = (int)cluster_ctarank();  // 0 = leader
-  const int n_pairs_cta = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
-  const int total_pairs = ((args.tiles_m + 1) >> 1) * args.tiles_n;  // work unit: one B tile x two row tiles
-
+// common prologue: barriers, TMEM allocation (2 accumulator buffers), activation table, zeroed accumulators
+template <int STAGES, int TMEM_COLS>
+__device__ __forceinline__ uint32_t tc_prologue(const SmemCarve &c, const float *tansig, int warp, int lane) {
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * 128 * kEpiSets); }  // every epilogue thread of both CTAs
+    for (int i = 0; i < STAGES; i++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(c.full + 8 * i));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(c.empty + 8 * i));
+    }
+    for (int i = 0; i < 2; i++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(c.acc_full + 8 * i));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(c.acc_empty + 8 * i), "r"(2 * 32 * kEpiWarps));  // every epilogue thread of both CTAs
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
-  for (int i = threadIdx.x; i < 201; i += blockDim.x) tbl[i] = args.tansig[i];
+  if (warp == 2) tmem_alloc(c.tmem_slot, TMEM_COLS);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) c.tbl[i] = i < 201 ? tansig[i] : 1.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *c.tmem_slot;
   if (warp >= 4) {  // zero both accumulator buffers: every MMA accumulates
     const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    for (int c = 0; c < kTmemCols; c += 16) tmem_st16_zero(tl + c);
+    for (int col = 0; col < TMEM_COLS; col += 16) tmem_st16_zero(tl + col);
     tmem_st_wait();
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // both CTAs' barriers and TMEM are ready before the leader issues anything
   tc_fence_after();
-
-  if (warp == 0) {
-    // ===== TMA producer (both CTAs): own A rows, own half of the B rows; bytes counted on the leader's barrier =====
-    if (lane == 0) {
-      int it = 0;
-      for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta) {
-        const int n_tile = pair % args.tiles_n, m0 = (2 * (pair / args.tiles_n) + crank) * TM;
-        for (int s = 0; s < args.n_seg; s++) {
-          const TcSeg sg = args.seg[s];
-          const CUtensorMap *ma = &args.maps[sg.a_map], *mb = &args.maps[sg.b_map];
-          for (int kb = 0; kb < sg.k_blocks; kb++, it++) {
-            const int st = it % STAGES;
-            mbar_wait(&empty_bar[st], ((it / STAGES) & 1) ^ 1);  // fresh barrier: passes immediately
-            if (args.debug & 2) {  // diagnostic: the MMAs run on whatever the stage holds
-              if (crank == 0) mbar_expect_tx(&full_bar[st], 0);
-              continue;
-            }
-            if (crank == 0) mbar_expect_tx(&full_bar[st], 2 * SL::kPairBytes);
-            uint8_t *sp = stage_base + st * SL::kBytes;
-#pragma unroll
-            for (int ta = 0; ta < NA; ta++)
-              tma_load_2d_pair(sp + ta * SL::kABytes, ma, &full_bar[st], sg.a_k0 + kb * BK, ta * sg.a_term_rows + sg.a_row0 + m0);
-#pragma unroll
-            for (int tb = 0; tb < NB; tb++)
-              tma_load_2d_pair(sp + NA * SL::kABytes + tb * SL::kBBytes, mb, &full_bar[st], sg.b_k0 + kb * BK,
-                               tb * args.b_term_rows + n_tile * BN + crank * (BN / 2));
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
-    if (lane == 0 && crank == 0) {
-      const uint32_t id_main = idesc_f16(GRU ? 3 * HT : BN, args.fmt);
-      int it = 0, j = 0;
-      for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta, j++) {
-        const int buf = j & 1;
-        const uint32_t acc = tmem_base + buf * kAccCols;
-        mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);  // both epilogues drained (and re-zeroed) this buffer
-        tc_fence_after();
-        for (int s = 0; s < args.n_seg; s++) {
-          const TcSeg sg = args.seg[s];
-          // GRU accumulator columns [nx | z | r | nh]: input part (rows [n|z|r]) at column 0, recurrent part
-          // (rows [z|r|n]) at column 64; each is one N = 192 MMA
-          const uint32_t dcol = (GRU && sg.recurrent) ? acc + HT : acc;
-          for (int kb = 0; kb < sg.k_blocks; kb++, it++) {
-            const int st = it % STAGES;
-            mbar_wait(&full_bar[st], (it / STAGES) & 1);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(stage_base + st * SL::kBytes);
-            const uint32_t sb = sa + NA * SL::kABytes;
-#pragma unroll
-            for (int ks = 0; ks < BK / 16; ks++) {
-#pragma unroll
-              for (int p = 0; p < PR::n; p++) {
-                const uint64_t ad = smem_desc_sw64(sa + PR::a(p) * SL::kABytes) + (uint64_t)(ks * 2);
-                const uint64_t bd = smem_desc_sw64(sb + PR::b(p) * SL::kBBytes) + (uint64_t)(ks * 2);
-                if (!(args.debug & 1)) umma_f16(dcol, ad, bd, id_main, 1u);
-              }
-            }
-            umma_commit(&empty_bar[st]);  // frees the stage in both CTAs once these MMAs have read it
-          }
-        }
-        umma_commit(&acc_full[buf]);  // both epilogues
-      }
-    }
-  } else if (warp >= 4) {
-    // ===== epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31, one stream per thread =====
-    const int wq = warp & 3, eset = (warp - 4) >> 2;
-    const float sc = args.out_scale;
-    int j = 0;
-    for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta, j++) {
-      const int n_tile = pair % args.tiles_n, m0 = (2 * (pair / args.tiles_n) + crank) * TM;
-      const int buf = j & 1;
-      mbar_wait(&acc_full[buf], (j >> 1) & 1);
-      tc_fence_after();
-      const int row = m0 + wq * 32 + lane;
-      const bool row_ok = row < args.M;
-      const uint32_t tlane = tmem_base + buf * kAccCols + ((uint32_t)(wq * 32) << 16);
-      if (GRU) {
-        const int H = args.H;
-        const float *b = args.bias;
-        for (int c = 16 * eset; c < HT; c += 16 * kEpiSets) {
-          float zs[16], rs[16], nx[16], nh[16];
-          tmem_ld16(tlane + HT + c, zs);      // accumulator columns: [nx | z | r | nh]
-          tmem_ld16(tlane + 2 * HT + c, rs);
-          tmem_ld16(tlane + c, nx);
-          tmem_ld16(tlane + 3 * HT + c, nh);
-          const int j0 = n_tile * HT + c;
-          if (row_ok) {
-            float hn[16];
-            const float4 *ho = reinterpret_cast<const float4 *>(args.h_old + (size_t)row * H + j0);
-            float hold[16];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              float4 t = ho[q];
-              hold[4 * q] = t.x; hold[4 * q + 1] = t.y; hold[4 * q + 2] = t.z; hold[4 * q + 3] = t.w;
-            }
-#pragma unroll
-            for (int i = 0; i < 16; i++) {  // nnet.cpp:136-178 (reset_after)
-              const int jj = j0 + i;
-              float z = sigmoid_s((__ldg(b + jj) + __ldg(b + 3 * H + jj)) + zs[i] * sc, tbl);
-              float r = sigmoid_s((__ldg(b + H + jj) + __ldg(b + 4 * H + jj)) + rs[i] * sc, tbl);
-              float tmp = __ldg(b + 5 * H + jj) + nh[i] * sc;
-              float cnd = __ldg(b + 2 * H + jj) + tmp * r;
-              cnd = cnd + nx[i] * sc;
-              float n = tansig_s(cnd, tbl);
-              hn[i] = z * hold[i] + (1.f - z) * n;
-            }
-            float4 *hw = reinterpret_cast<float4 *>(args.h_new + (size_t)row * H + j0);
-#pragma unroll
-            for (int q = 0; q < 4; q++) hw[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
-            __align__(16) __half hi[16], lo[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) split_h2(hn[i], hi[i], lo[i]);
-            const size_t orow = (size_t)args.out_row0 + row;
-            uint4 *ph = reinterpret_cast<uint4 *>(args.h_new_h + orow * H + j0);
-            uint4 *pl = reinterpret_cast<uint4 *>(args.h_new_h + ((size_t)args.out_plane_rows + orow) * H + j0);
-            ph[0] = reinterpret_cast<uint4 *>(hi)[0]; ph[1] = reinterpret_cast<uint4 *>(hi)[1];
-            pl[0] = reinterpret_cast<uint4 *>(lo)[0]; pl[1] = reinterpret_cast<uint4 *>(lo)[1];
-          }
-        }
-      } else {
-        const int N = args.N;
-        for (int c = 16 * eset; c < BN; c += 16 * kEpiSets) {
-          float d[16];
-          tmem_ld16(tlane + c, d);
-          const int j0 = n_tile * BN + c;
-          if (row_ok && j0 < N) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-              float x = d[i] * sc + ((j0 + i < N) ? __ldg(args.bias + j0 + i) : 0.f);
-              v[i] = args.act == PNB_ACT_TANH ? tansig_s(x, tbl) : args.act == PNB_ACT_RELU ? (x < 0.f ? 0.f : x)
-                   : args.act == PNB_ACT_SIGMOID ? sigmoid_s(x, tbl) : x;
-            }
-            if (args.out_f32 && row >= args.f32_row0) {
-              float *op = args.out_f32 + (size_t)(row - args.f32_row0) * args.ldc + j0;
-              if ((reinterpret_cast<uintptr_t>(op) & 15) == 0 && j0 + 16 <= N) {
-                float4 *o = reinterpret_cast<float4 *>(op);
-#pragma unroll
-                for (int q = 0; q < 4; q++) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; i++)
-                  if (j0 + i < N) op[i] = v[i];
-              }
-            }
-            if (args.out_h) {
-              __align__(16) __half hi[16], lo[16];
-#pragma unroll
-              for (int i = 0; i < 16; i++) split_h2(v[i], hi[i], lo[i]);
-              const size_t orow = (size_t)args.out_row0 + row;
-              uint4 *ph = reinterpret_cast<uint4 *>(args.out_h + orow * N + j0);
-              uint4 *pl = reinterpret_cast<uint4 *>(args.out_h + ((size_t)args.out_plane_rows + orow) * N + j0);
-              ph[0] = reinterpret_cast<uint4 *>(hi)[0]; ph[1] = reinterpret_cast<uint4 *>(hi)[1];
-              pl[0] = reinterpret_cast<uint4 *>(lo)[0]; pl[1] = reinterpret_cast<uint4 *>(lo)[1];
-            }
-            if (args.out_b) {
-              __align__(16) __nv_bfloat16 t0[16], t1[16], t2[16];
-#pragma unroll
-              for (int i = 0; i < 16; i++) split_b3(v[i], t0[i], t1[i], t2[i]);
-              const size_t plane = (size_t)args.out_plane_rows * N;
-              const size_t orow = (size_t)args.out_row0 + row;
-              uint4 *p0 = reinterpret_cast<uint4 *>(args.out_b + orow * N + j0);
-              uint4 *p1 = reinterpret_cast<uint4 *>(args.out_b + plane + orow * N + j0);
-              p0[0] = reinterpret_cast<uint4 *>(t0)[0]; p0[1] = reinterpret_cast<uint4 *>(t0)[1];
-              p1[0] = reinterpret_cast<uint4 *>(t1)[0]; p1[1] = reinterpret_cast<uint4 *>(t1)[1];
-              if (kConvTerms == 3) {
-                uint4 *p2 = reinterpret_cast<uint4 *>(args.out_b + 2 * plane + orow * N + j0);
-                p2[0] = reinterpret_cast<uint4 *>(t2)[0]; p2[1] = reinterpret_cast<uint4 *>(t2)[1];
-              }
-            }
-          }
-        }
-      }
-      // zero the buffer for its next tile and hand it back to the leader's MMA thread
-      for (int c = 16 * eset; c < kAccCols; c += 16 * kEpiSets) tmem_st16_zero(tlane + c);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive_leader(&acc_empty[buf]);
-    }
-  }
+  return tmem_base;
+}
+template <int TMEM_COLS>
+__device__ __forceinline__ void tc_teardown(uint32_t tmem_base, int warp) {
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the pair still has work in flight
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-constexpr int GRU_STAGES = 7, DENSE_STAGES = 6, SMALL_BN = 48, SMALL_STAGES = 8;
-template <int NA, int NB, int BN, int STAGES>
-constexpr size_t tc_smem_bytes() {
-  return (size_t)STAGES * StageLayout<NA, NB, BN>::kBytes + (2 * STAGES + 4) * 8 + 16 + 208 * 4 + 1024;
+// One k-block of a tile on the MMA side: the three products of both 16-wide k-steps, then the stage is released.
+// Runs warp-converged; `a_lo` / `b_lo` are the descriptor low words of the stage's first A / B term.
+template <int BN>
+__device__ __forceinline__ void mma_kblock(uint32_t dcol, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t empty_bar) {
+  using SL = StageLayout<BN>;
+  if (elect_one()) {
+#pragma unroll
+    for (int ks = 0; ks < BK / 16; ks++) {
+      // (a term, b term): hi hi, hi lo, lo hi
+      umma_f16(dcol, desc64(a_lo + ks * 2), desc64(b_lo + ks * 2), idesc);
+      umma_f16(dcol, desc64(a_lo + ks * 2), desc64(b_lo + (SL::kBBytes >> 4) + ks * 2), idesc);
+      umma_f16(dcol, desc64(a_lo + (SL::kABytes >> 4) + ks * 2), desc64(b_lo + ks * 2), idesc);
+    }
+    umma_commit(empty_bar);  // frees the stage in both CTAs once these MMAs have read it
+  }
+  __syncwarp();
 }
 
-// fc 70 -> 128 relu in fp32 FMA (0.1 % of the MACs; K = 70 is no tensor-core shape), emitting the three bf16
-// terms conv1 consumes.  One block per 4 streams, one thread per output.
+// ------------------------------------------------------------------------------------------ dense layers
+struct TcSeg {
+  int a_map, b_map;  // indices into TcArgs::maps
+  int k_blocks;      // K / 32
+  int a_k0, b_k0;    // starting k (elements) in the A / B matrices
+  int a_row0;        // row of the A matrix that holds tile row 0 (hop / tap offset inside a multi-hop buffer)
+  int a_term_rows;   // row distance between the split terms inside this A buffer
+};
+
+struct TcArgs {
+  CUtensorMap maps[8];
+  TcSeg seg[5];
+  int n_seg;
+  int M;                // rows
+  int tiles_m, tiles_n; // tile grid; a CTA pair walks pair-tiles pair_id, pair_id + n_pairs, ...
+  int b_term_rows;      // row distance between the split terms inside a packed weight matrix
+  int fmt;              // 0 fp16, 1 bf16
+  float out_scale;      // 2^-(activation scale + weight scale)
+  const float *tansig;  // 201-entry table (global)
+  const float *bias;    // padded to a multiple of 16 entries
+  int *status;          // engine status word: bit 0 = an activation left the reference's defined domain
+  int act;
+  int N;                // valid output columns
+  int ldc;              // row stride of out_f32
+  float *out_f32;       // [M][ldc] or null
+  int f32_row0;         // only rows >= f32_row0 are written to out_f32, at row - f32_row0
+  __half *out_h;        // fp16 two-term split [2][out_plane_rows][N] (x 2^10) or null
+  __nv_bfloat16 *out_b; // bf16 two-term split [2][out_plane_rows][N] or null
+  int out_row0;         // first row written inside a term plane of out_h / out_b
+  int out_plane_rows;   // rows per term plane of out_h / out_b
+};
+
+__host__ __device__ constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_constant__ TcArgs args) {
+  using SL = StageLayout<BN>;
+  constexpr int kAccCols = pow2_cols(BN);  // TMEM columns per accumulator buffer
+  constexpr int kTmemCols = 2 * kAccCols;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const SmemCarve c = carve<STAGES, SL::kBytes>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();  // 0 = leader
+  const int n_pairs_cta = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
+  const int total_pairs = ((args.tiles_m + 1) >> 1) * args.tiles_n;  // work unit: one B tile x two row tiles
+  const uint32_t tmem_base = tc_prologue<STAGES, kTmemCols>(c, args.tansig, warp, lane);
+  const uint32_t stage0 = smem_u32(c.stages);
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own A rows, own half of the B rows; bytes counted on the leader's barrier =====
+    Pipe p;
+    for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta) {
+      const int n_tile = pair % args.tiles_n, m0 = (2 * (pair / args.tiles_n) + crank) * TM;
+      for (int s = 0; s < args.n_seg; s++) {
+        const TcSeg &sg = args.seg[s];
+        const CUtensorMap *ma = &args.maps[sg.a_map], *mb = &args.maps[sg.b_map];
+        const int arow = sg.a_row0 + m0, brow = n_tile * BN + crank * (BN / 2);
+        for (int kb = 0; kb < sg.k_blocks; kb++) {
+          mbar_wait(c.empty + 8 * p.st, p.ph ^ 1);  // fresh barrier: passes immediately
+          if (elect_one()) {
+            const uint32_t fb = c.full + 8 * p.st;
+            if (crank == 0) mbar_expect_tx(fb, 2 * SL::kBytes);
+            const uint32_t sp = stage0 + p.st * SL::kBytes;
+            tma_load_2d_pair(sp, ma, fb, sg.a_k0 + kb * BK, arow);
+            tma_load_2d_pair(sp + SL::kABytes, ma, fb, sg.a_k0 + kb * BK, sg.a_term_rows + arow);
+            tma_load_2d_pair(sp + 2 * SL::kABytes, mb, fb, sg.b_k0 + kb * BK, brow);
+            tma_load_2d_pair(sp + 2 * SL::kABytes + SL::kBBytes, mb, fb, sg.b_k0 + kb * BK, args.b_term_rows + brow);
+          }
+          __syncwarp();
+          p.advance(STAGES);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader CTA's warp 1 drives both SMs' tensor cores =====
+    if (crank == 0) {
+      const uint32_t idesc = idesc_f16(BN, args.fmt);
+      const uint32_t a_lo0 = desc_lo(stage0);
+      Pipe p;
+      int j = 0;
+      for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta, j++) {
+        const int buf = j & 1;
+        mbar_wait(c.acc_empty + 8 * buf, ((j >> 1) & 1) ^ 1);  // both epilogues drained (and re-zeroed) this buffer
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * kAccCols;
+        for (int s = 0; s < args.n_seg; s++) {
+          const int nkb = args.seg[s].k_blocks;
+          for (int kb = 0; kb < nkb; kb++) {
+            mbar_wait(c.full + 8 * p.st, p.ph);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + p.st * (SL::kBytes >> 4);
+            mma_kblock<BN>(acc, a_lo, a_lo + ((2 * SL::kABytes) >> 4), idesc, c.empty + 8 * p.st);
+            p.advance(STAGES);
+          }
+        }
+        if (elect_one()) umma_commit(c.acc_full + 8 * buf);  // both epilogues
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31, one row per thread =====
+    const int wq = warp & 3, eset = (warp - 4) >> 2;
+    const float sc = args.out_scale;
+    const float *tbl = c.tbl;
+    const int N = args.N, act = args.act;
+    int j = 0;
+    for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta, j++) {
+      const int n_tile = pair % args.tiles_n, m0 = (2 * (pair / args.tiles_n) + crank) * TM;
+      const int buf = j & 1;
+      mbar_wait(c.acc_full + 8 * buf, (j >> 1) & 1);
+      tc_fence_after();
+      const int row = m0 + wq * 32 + lane;
+      const bool row_ok = row < args.M;
+      const uint32_t tlane = tmem_base + buf * kAccCols + ((uint32_t)(wq * 32) << 16);
+      for (int col = 16 * eset; col < BN; col += 16 * kEpiSets) {
+        uint32_t d[16];
+        tmem_ld16_nowait(tlane + col, d);
+        const int j0 = n_tile * BN + col;
+        float4 bq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) bq[q] = __ldg(reinterpret_cast<const float4 *>(args.bias + j0) + q);
+        tmem_ld_wait();
+        if (row_ok && j0 < N) {
+          const float *bs = reinterpret_cast<const float *>(bq);
+          float v[16];
+          bool bad = false;
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const float x = fmaf(__uint_as_float(d[i]), sc, bs[i]);
+            if (act == PNB_ACT_TANH) { v[i] = tansig_s(x, tbl); bad |= fabsf(x) >= kTanhDomain; }
+            else if (act == PNB_ACT_RELU) v[i] = x < 0.f ? 0.f : x;
+            else if (act == PNB_ACT_SIGMOID) { v[i] = sigmoid_s(x, tbl); bad |= fabsf(x) >= 2.f * kTanhDomain; }
+            else v[i] = x;
+          }
+          if (bad) atomicOr(args.status, 1);
+          if (args.out_f32 && row >= args.f32_row0) {
+            float *op = args.out_f32 + (size_t)(row - args.f32_row0) * args.ldc + j0;
+            if ((reinterpret_cast<uintptr_t>(op) & 15) == 0 && j0 + 16 <= N) {
+              float4 *o = reinterpret_cast<float4 *>(op);
+#pragma unroll
+              for (int q = 0; q < 4; q++) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; i++)
+                if (j0 + i < N) op[i] = v[i];
+            }
+          }
+          const size_t orow = (size_t)args.out_row0 + row;
+          if (args.out_h)
+            store_split_h16(v, args.out_h + orow * N + j0, args.out_h + ((size_t)args.out_plane_rows + orow) * N + j0);
+          if (args.out_b)
+            store_split_b16(v, args.out_b + orow * N + j0, args.out_b + ((size_t)args.out_plane_rows + orow) * N + j0);
+        }
+        tmem_st16_zero(tlane + col);  // this thread's columns are read: zero them for the buffer's next tile
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_leader(c.acc_empty + 8 * buf);
+    }
+  }
+  tc_teardown<kTmemCols>(tmem_base, warp);
+}
+
+// ------------------------------------------------------------------------------------------ the GRU chain
+struct ChainLayer {
+  int n_x;              // input segments (2 for gru_rb: [gru3 state, conv2 out])
+  int x_map[2];         // A tensor maps of the input segments
+  int x_kb[2];          // their k-blocks
+  int x_bk0[2];         // starting k in the packed input weights
+  int x_row1[2];        // 0: the segment is indexed by hop (conv2 out, slot t); 1: state slots (slot t+1 = after hop t)
+  int x_term_rows[2];   // row distance between the two split terms in that buffer
+  int h_map, w_map, u_map;
+  int h_kb;             // H / 32
+  int H;
+  int tiles_log2;       // log2(H / 64)
+  int b_term_rows;      // rows of one term plane of the packed weights
+  int dep;              // layer whose output at the same hop is this layer's input (-1: produced before the launch)
+  int unit0;            // first unit of this layer inside a hop
+  int par0;             // which fp32 state buffer holds the state before hop 0
+  float scale;          // 2^-(10 + weight scale)
+  const float4 *bias4;  // per unit {b_z + b'_z, b_r + b'_r, b_n, b'_n}
+  float *h32[2];        // fp32 state, ping-pong by hop
+  __half *h_hl;         // fp16 terms [2][(Fmax+1) S][H]
+  int h_term_rows;      // (Fmax+1) S
+};
+struct ChainArgs {
+  CUtensorMap maps[16];  // 0: conv2 out, 1..5: state slots of the five GRUs, 6..10: input weights, 11..15: recurrent weights
+  ChainLayer L[5];
+  int S, F;
+  int tiles_mp;          // row pairs (256 streams each)
+  int units_per_hop;
+  unsigned *cnt;         // [5][tiles_mp] epilogue-warp completions, zero at launch
+  const float *tansig;
+};
+
+struct Unit { int t, l, mp, nt; };
+__device__ __forceinline__ Unit decode_unit(const ChainArgs &a, int u) {
+  Unit x;
+  x.t = u / a.units_per_hop;
+  int r = u - x.t * a.units_per_hop;
+  x.l = 0;
+#pragma unroll
+  for (int i = 1; i < 5; i++) x.l = (r >= a.L[i].unit0) ? i : x.l;
+  r -= a.L[x.l].unit0;
+  const int sh = a.L[x.l].tiles_log2;
+  x.mp = r >> sh;
+  x.nt = r & ((1 << sh) - 1);
+  return x;
+}
+// all epilogue warps of both CTAs of every tile of (layer, row pair) have finished `hops` hops
+__device__ __forceinline__ void wait_layer(const ChainArgs &a, int layer, int mp, int hops) {
+  const unsigned target = (unsigned)hops * (2u * kEpiWarps) << a.L[layer].tiles_log2;
+  const unsigned *p = a.cnt + layer * a.tiles_mp + mp;
+  unsigned spins = 0;
+  while (ld_acquire_gpu(p) < target)
+    if (++spins > (1u << 26)) __trap();  // tens of seconds: a broken schedule becomes a launch error, not a hang
+}
+
+constexpr int GRU_STAGES = 7;
+
+__global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_constant__ ChainArgs args) {
+  using SL = StageLayout<GRU_BN>;
+  constexpr int STAGES = GRU_STAGES;
+  constexpr int kAccCols = 4 * HT, kTmemCols = 2 * kAccCols;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const SmemCarve c = carve<STAGES, SL::kBytes>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  const int n_pairs_cta = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
+  const int total_units = args.F * args.units_per_hop;
+  const int S = args.S;
+  const uint32_t tmem_base = tc_prologue<STAGES, kTmemCols>(c, args.tansig, warp, lane);
+  const uint32_t stage0 = smem_u32(c.stages);
+
+  if (warp == 0) {
+    // ===== TMA producer: waits for the rows it is about to read, then streams the tile's operands =====
+    Pipe p;
+    for (int u = pair_id; u < total_units; u += n_pairs_cta) {
+      const Unit un = decode_unit(args, u);
+      const ChainLayer &L = args.L[un.l];
+      if (elect_one()) {  // the same lane issues the TMA loads below
+        if (L.dep >= 0) wait_layer(args, L.dep, un.mp, un.t + 1);  // input: layer below, this hop
+        if (un.t > 0) wait_layer(args, un.l, un.mp, un.t);        // own state after the previous hop
+        fence_proxy_async();  // the rows were written with st.global by other SMs; TMA reads them through the async proxy
+      }
+      __syncwarp();
+      const int m0 = (2 * un.mp + crank) * TM;
+      const int brow = un.nt * GRU_BN + crank * (GRU_BN / 2);
+      for (int s = 0; s <= L.n_x; s++) {
+        const bool rec = s == L.n_x;
+        const CUtensorMap *ma = &args.maps[rec ? L.h_map : L.x_map[s]], *mb = &args.maps[rec ? L.u_map : L.w_map];
+        const int nkb = rec ? L.h_kb : L.x_kb[s];
+        const int arow = (rec ? un.t : un.t + L.x_row1[s]) * S + m0;
+        const int aterm = rec ? L.h_term_rows : L.x_term_rows[s];
+        const int bk0 = rec ? 0 : L.x_bk0[s];
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(c.empty + 8 * p.st, p.ph ^ 1);
+          if (elect_one()) {
+            const uint32_t fb = c.full + 8 * p.st;
+            if (crank == 0) mbar_expect_tx(fb, 2 * SL::kBytes);
+            const uint32_t sp = stage0 + p.st * SL::kBytes;
+            tma_load_2d_pair(sp, ma, fb, kb * BK, arow);
+            tma_load_2d_pair(sp + SL::kABytes, ma, fb, kb * BK, aterm + arow);
+            tma_load_2d_pair(sp + 2 * SL::kABytes, mb, fb, bk0 + kb * BK, brow);
+            tma_load_2d_pair(sp + 2 * SL::kABytes + SL::kBBytes, mb, fb, bk0 + kb * BK, L.b_term_rows + brow);
+          }
+          __syncwarp();
+          p.advance(STAGES);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA) =====
+    if (crank == 0) {
+      const uint32_t idesc = idesc_f16(GRU_BN, 0);
+      const uint32_t a_lo0 = desc_lo(stage0);
+      Pipe p;
+      int j = 0;
+      for (int u = pair_id; u < total_units; u += n_pairs_cta, j++) {
+        const Unit un = decode_unit(args, u);
+        const ChainLayer &L = args.L[un.l];
+        const int buf = j & 1;
+        mbar_wait(c.acc_empty + 8 * buf, ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * kAccCols;
+        // accumulator columns [nx | z | r | nh]: input part (rows [n|z|r]) at column 0, recurrent part (rows [z|r|n]) at 64
+        int nkb = 0;
+        for (int s = 0; s < L.n_x; s++) nkb += L.x_kb[s];
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(c.full + 8 * p.st, p.ph);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + p.st * (SL::kBytes >> 4);
+          mma_kblock<GRU_BN>(acc, a_lo, a_lo + ((2 * SL::kABytes) >> 4), idesc, c.empty + 8 * p.st);
+          p.advance(STAGES);
+        }
+        for (int kb = 0; kb < L.h_kb; kb++) {
+          mbar_wait(c.full + 8 * p.st, p.ph);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + p.st * (SL::kBytes >> 4);
+          mma_kblock<GRU_BN>(acc + HT, a_lo, a_lo + ((2 * SL::kABytes) >> 4), idesc, c.empty + 8 * p.st);
+          p.advance(STAGES);
+        }
+        if (elect_one()) umma_commit(c.acc_full + 8 * buf);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: gate math of nnet.cpp:136-178 (reset_after) on this thread's stream, 16 units at a time =====
+    const int wq = warp & 3, eset = (warp - 4) >> 2;
+    const float *tbl = c.tbl;
+    int j = 0;
+    for (int u = pair_id; u < total_units; u += n_pairs_cta, j++) {
+      const Unit un = decode_unit(args, u);
+      const ChainLayer &L = args.L[un.l];
+      const int H = L.H, buf = j & 1;
+      const int row = (2 * un.mp + crank) * TM + wq * 32 + lane;
+      const bool row_ok = row < S;
+      const int pold = (L.par0 + un.t) & 1;
+      const float *h_old = L.h32[pold] + (size_t)row * H + un.nt * HT;
+      float *h_new = L.h32[pold ^ 1] + (size_t)row * H + un.nt * HT;
+      // the previous hop's state of these rows is complete (other SMs wrote it): acquire before reading it
+      if (un.t > 0) {
+        if (lane == 0) wait_layer(args, un.l, un.mp, un.t);
+        __syncwarp();
+      }
+      float4 hold[2][4];
+#pragma unroll
+      for (int b = 0; b < 2; b++)
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          hold[b][q] = row_ok ? __ldcg(reinterpret_cast<const float4 *>(h_old + 16 * eset + 32 * b) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait(c.acc_full + 8 * buf, (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tlane = tmem_base + buf * kAccCols + ((uint32_t)(wq * 32) << 16);
+      const float sc = L.scale;
+      const size_t orow = (size_t)(un.t + 1) * S + row;
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        const int col = 16 * eset + 32 * b;
+        uint32_t zs[16], rs[16], nx[16], nh[16];
+        tmem_ld16_nowait(tlane + HT + col, zs);      // accumulator columns: [nx | z | r | nh]
+        tmem_ld16_nowait(tlane + 2 * HT + col, rs);
+        tmem_ld16_nowait(tlane + col, nx);
+        tmem_ld16_nowait(tlane + 3 * HT + col, nh);
+        const float4 *b4 = L.bias4 + un.nt * HT + col;
+        tmem_ld_wait();
+        // this thread's columns are in registers: zero them for the buffer's next tile
+        tmem_st16_zero(tlane + col); tmem_st16_zero(tlane + HT + col);
+        tmem_st16_zero(tlane + 2 * HT + col); tmem_st16_zero(tlane + 3 * HT + col);
+        if (b == 1) {  // hand the buffer back to the MMA thread before the second half of the gate math
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive_leader(c.acc_empty + 8 * buf);
+        }
+        const float *ho = reinterpret_cast<const float *>(hold[b]);
+        float hn[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const float4 bb = __ldg(b4 + i);
+          const float z = sigmoid_s(fmaf(__uint_as_float(zs[i]), sc, bb.x), tbl);
+          const float r = sigmoid_s(fmaf(__uint_as_float(rs[i]), sc, bb.y), tbl);
+          const float tmp = fmaf(__uint_as_float(nh[i]), sc, bb.w);
+          float cnd = fmaf(tmp, r, bb.z);
+          cnd = fmaf(__uint_as_float(nx[i]), sc, cnd);
+          const float n = tansig_s(cnd, tbl);
+          hn[i] = fmaf(z, ho[i] - n, n);  // z h + (1 - z) n
+        }
+        if (row_ok) {
+          float4 *hw = reinterpret_cast<float4 *>(h_new + col);
+#pragma unroll
+          for (int q = 0; q < 4; q++) hw[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
+          __half *ph = L.h_hl + orow * H + un.nt * HT + col;
+          store_split_h16(hn, ph, ph + (size_t)L.h_term_rows * H);
+        }
+      }
+      // publish: every store of this warp for this tile is ordered before the counter bump
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        red_release_gpu_add(args.cnt + un.l * args.tiles_mp + un.mp, 1u);
+      }
+    }
+  }
+  tc_teardown<kTmemCols>(tmem_base, warp);
+}
+
+constexpr int DENSE_STAGES = 6, SMALL_BN = 48, SMALL_STAGES = 8;
+
+// fc 70 -> 128 relu in fp32 FMA (0.1 % of the MACs; K = 70 is no tensor-core shape), emitting the two bf16
+// terms conv1 consumes.  One block per 4 rows, one thread per output.
 __global__ void __launch_bounds__(128) fc_split_kernel(const float *__restrict__ feat, const float *__restrict__ W,
                                                        const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out,
                                                        int M, size_t plane_rows) {
@@ -504,12 +735,29 @@ __global__ void __launch_bounds__(128) fc_split_kernel(const float *__restrict__
   for (int rr = 0; rr < 4; rr++) {
     if (r0 + rr >= M) break;
     float v = a[rr] < 0.f ? 0.f : a[rr];
-    __nv_bfloat16 t0, t1, t2;
-    split_b3(v, t0, t1, t2);
+    __nv_bfloat16 t0 = __float2bfloat16_rn(v);
+    __nv_bfloat16 t1 = __float2bfloat16_rn(v - __bfloat162float(t0));
     size_t o = (size_t)(r0 + rr) * 128 + n;
     out[o] = t0; out[plane + o] = t1;
-    if (kConvTerms == 3) out[2 * plane + o] = t2;
   }
+}
+
+// End-of-call bookkeeping in one launch: the hop slots the next call reads first (last 4 fc / 2 conv1 outputs,
+// last GRU states) move to the front of their buffers, and the chain's dependency counters return to zero.
+struct CarrySeg { uint4 *dst; const uint4 *src; size_t n16; };
+struct CarryArgs {
+  CarrySeg seg[14];
+  int n_seg;
+  unsigned *cnt;
+  int n_cnt;
+};
+__global__ void __launch_bounds__(256) tc_carry_kernel(const __grid_constant__ CarryArgs a) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  for (int s = 0; s < a.n_seg; s++) {
+    const CarrySeg sg = a.seg[s];
+    for (size_t i = tid; i < sg.n16; i += nth) sg.dst[i] = sg.src[i];
+  }
+  for (size_t i = tid; i < (size_t)a.n_cnt; i += nth) a.cnt[i] = 0u;
 }
 
 }  // namespace
@@ -520,17 +768,21 @@ struct pnb_tc_state {
   // Multi-hop buffers: rows are (hop slot, stream).  The conv layers carry no recurrence, so they run once per
   // call over all F hops (M = F S rows); a tap is the same buffer read `tap` slots later.  Slots 0..3 (0..1) hold
   // the last hops of the previous call.
-  __nv_bfloat16 *fc_all = nullptr;   // [terms][(Fmax+4) S][128]  fc outputs, bf16 terms
-  __nv_bfloat16 *c1_all = nullptr;   // [terms][(Fmax+2) S][512]  conv1 outputs
-  __half *c2_h = nullptr;            // [2][Fmax S][512]          conv2 outputs, fp16 terms
-  __half *h_all[5] = {};             // [2][(Fmax+1) S][H]        GRU states as fp16 terms, slot t+1 = after hop t,
-                                     //                           slot 0 = carried from the previous call
+  __nv_bfloat16 *fc_all = nullptr;   // [2][(Fmax+4) S][128]  fc outputs, bf16 terms
+  __nv_bfloat16 *c1_all = nullptr;   // [2][(Fmax+2) S][512]  conv1 outputs
+  __half *c2_h = nullptr;            // [2][Fmax S][512]      conv2 outputs, fp16 terms
+  __half *h_all[5] = {};             // [2][(Fmax+1) S][H]    GRU states as fp16 terms, slot t+1 = after hop t,
+                                     //                       slot 0 = carried from the previous call
   // packed weights
-  __nv_bfloat16 *w_conv1 = nullptr, *w_conv2 = nullptr;  // [3][512][K]
+  __nv_bfloat16 *w_conv1 = nullptr, *w_conv2 = nullptr;  // [2][512][K]
   __half *w_gru[5] = {}, *u_gru[5] = {};                 // [2][tiles*192][K]
   float scale_gru[5] = {};                               // 2^-(10 + e)
+  float4 *bias4[5] = {};                                 // per unit {b_z + b'_z, b_r + b'_r, b_n, b'_n}
   __half *w_gb = nullptr, *w_rb = nullptr;               // [2][48][2560], [2][48][128] (34 rows used)
   float scale_gb = 0.f, scale_rb = 0.f;
+  float *bias_pad = nullptr;                             // conv1 [512] | conv2 [512] | fc_gb [48] | fc_rb [48]
+  unsigned *cnt = nullptr;                               // chain dependency counters [5][tiles_mp]
+  int tiles_mp = 0;
   // tensor maps
   CUtensorMap m_fc_all, m_c1_all, m_c2, m_h[5], m_wconv1, m_wconv2, m_w[5], m_u[5], m_wgb, m_wrb;
 };
@@ -598,20 +850,15 @@ static void pack_gru(const float *W, int K, int H, float scale, const int order[
         }
       }
 }
-// dense/conv weights: W[k*N + n] -> [n][k], three bf16 terms
-static void pack_dense_b3(const float *W, int K, int N, std::vector<__nv_bfloat16> &out) {
-  out.assign((size_t)kConvTerms * N * K, __float2bfloat16(0.f));
+// dense/conv weights: W[k*N + n] -> [n][k], two bf16 terms
+static void pack_dense_b2(const float *W, int K, int N, std::vector<__nv_bfloat16> &out) {
+  out.assign((size_t)2 * N * K, __float2bfloat16(0.f));
   for (int n = 0; n < N; n++)
     for (int k = 0; k < K; k++) {
       float w = W[(size_t)k * N + n];
       __nv_bfloat16 t0 = __float2bfloat16_rn(w);
-      float r = w - __bfloat162float(t0);
-      __nv_bfloat16 t1 = __float2bfloat16_rn(r);
-      r -= __bfloat162float(t1);
-      __nv_bfloat16 t2 = __float2bfloat16_rn(r);
       out[(size_t)n * K + k] = t0;
-      out[((size_t)N + n) * K + k] = t1;
-      if (kConvTerms == 3) out[((size_t)2 * N + n) * K + k] = t2;
+      out[((size_t)N + n) * K + k] = __float2bfloat16_rn(w - __bfloat162float(t0));
     }
 }
 
@@ -625,6 +872,24 @@ static void pack_small_h2(const float *W, int K, int N, float scale, std::vector
       out[(size_t)n * K + k] = hi;
       out[((size_t)SMALL_BN + n) * K + k] = __float2half_rn(w - __half2float(hi));
     }
+}
+
+// Largest |pre-activation| a layer can form from inputs bounded by 1 (tanh outputs / GRU states): the row sums of
+// |W| (+ |U|) plus |b|.  The tensor path is validated inside the reference's defined domain only (tansig_approx
+// overflows its float->int conversion from 8.6e7 on, vec.h:63); weights that could leave it are refused up front.
+static double max_preact(const float *W, int K, int N, int ld, const float *U, int KU, const float *b0, const float *b1) {
+  std::vector<double> acc(N, 0.0);
+  for (int k = 0; k < K; k++)
+    for (int n = 0; n < N; n++) acc[n] += fabs((double)W[(size_t)k * ld + n]);
+  if (U)
+    for (int k = 0; k < KU; k++)
+      for (int n = 0; n < N; n++) acc[n] += fabs((double)U[(size_t)k * ld + n]);
+  double mx = 0.0;
+  for (int n = 0; n < N; n++) {
+    double v = acc[n] + (b0 ? fabs((double)b0[n]) : 0.0) + (b1 ? fabs((double)b1[n]) : 0.0);
+    if (!(v <= mx)) mx = v;  // NaN-propagating max
+  }
+  return mx;
 }
 
 template <typename T>
@@ -648,22 +913,42 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
     if (r != cudaSuccess || !fn) return tc_fail(PNB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     g_encode = (EncodeTiledFn)fn;
   }
+  const pnb_gru_layer *g5[5] = {model->gru1, model->gru2, model->gru3, model->gru_gb, model->gru_rb};
+  {  // inputs of the GRUs and output layers are bounded by 1 inside the reference's domain: bound their pre-activations
+    double mx = 0.0;
+    for (int i = 0; i < 5; i++) {
+      const int K = g5[i]->nb_inputs, H = g5[i]->nb_neurons;
+      for (int g = 0; g < 3; g++) {
+        double v = max_preact(g5[i]->input_weights + g * H, K, H, 3 * H, g5[i]->recurrent_weights + g * H, H,
+                              g5[i]->bias + g * H, g5[i]->bias + (3 + g) * H);
+        if (!(v <= mx)) mx = v;
+      }
+    }
+    double v = max_preact(model->fc_gb->input_weights, 2560, 34, 34, nullptr, 0, model->fc_gb->bias, nullptr);
+    if (!(v <= mx)) mx = v;
+    v = max_preact(model->fc_rb->input_weights, 128, 34, 34, nullptr, 0, model->fc_rb->bias, nullptr);
+    if (!(v <= mx)) mx = v;
+    if (!(mx < kTanhDomain))
+      return tc_fail(PNB_ERR_ARG, "PNB_NN_TENSOR: a GRU / output layer can form pre-activations >= 8.5e7 (or NaN), outside the "
+                                  "domain of the reference's tansig_approx; use PNB_NN_FP32 for this model");
+  }
   pnb_tc_state *t = new pnb_tc_state();
   e->tc = t;
   const size_t S = e->S;
   const size_t Fm = e->Fmax;
-  TCK(dev_zeros(&t->fc_all, kConvTerms * (Fm + 4) * S * 128));
-  TCK(dev_zeros(&t->c1_all, kConvTerms * (Fm + 2) * S * 512));
+  TCK(dev_zeros(&t->fc_all, 2 * (Fm + 4) * S * 128));
+  TCK(dev_zeros(&t->c1_all, 2 * (Fm + 2) * S * 512));
   TCK(dev_zeros(&t->c2_h, 2 * Fm * S * 512));
   for (int i = 0; i < 5; i++) TCK(dev_zeros(&t->h_all[i], 2 * (Fm + 1) * S * e->gru[i].H));
+  t->tiles_mp = (int)((S + 2 * TM - 1) / (2 * TM));
+  TCK(dev_zeros(&t->cnt, (size_t)5 * t->tiles_mp));
   {
     std::vector<__nv_bfloat16> p;
-    pack_dense_b3(model->conv1->input_weights, 640, 512, p);
+    pack_dense_b2(model->conv1->input_weights, 640, 512, p);
     TCK(dev_upload(&t->w_conv1, p));
-    pack_dense_b3(model->conv2->input_weights, 1536, 512, p);
+    pack_dense_b2(model->conv2->input_weights, 1536, 512, p);
     TCK(dev_upload(&t->w_conv2, p));
   }
-  const pnb_gru_layer *g5[5] = {model->gru1, model->gru2, model->gru3, model->gru_gb, model->gru_rb};
   for (int i = 0; i < 5; i++) {
     const int K = g5[i]->nb_inputs, H = g5[i]->nb_neurons;
     int ex;
@@ -675,6 +960,11 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
     TCK(dev_upload(&t->w_gru[i], p));
     pack_gru(g5[i]->recurrent_weights, H, H, sc, order_u, p);
     TCK(dev_upload(&t->u_gru[i], p));
+    // nnet.cpp:136-160: z and r start from b + b' (one float add), the candidate keeps b_n and b'_n apart
+    const float *b = g5[i]->bias;
+    std::vector<float4> b4(H);
+    for (int j = 0; j < H; j++) b4[j] = make_float4(b[j] + b[3 * H + j], b[H + j] + b[4 * H + j], b[2 * H + j], b[5 * H + j]);
+    TCK(dev_upload(&t->bias4[i], b4));
   }
   {
     int ex;
@@ -687,41 +977,48 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
     t->scale_rb = ldexpf(1.f, -(10 + ex));
     pack_small_h2(model->fc_rb->input_weights, 128, 34, sc, p);
     TCK(dev_upload(&t->w_rb, p));
+    std::vector<float> bp(512 + 512 + 48 + 48, 0.f);
+    memcpy(bp.data(), model->conv1->bias, 512 * 4);
+    memcpy(bp.data() + 512, model->conv2->bias, 512 * 4);
+    memcpy(bp.data() + 1024, model->fc_gb->bias, 34 * 4);
+    memcpy(bp.data() + 1072, model->fc_rb->bias, 34 * 4);
+    TCK(dev_upload(&t->bias_pad, bp));
   }
   int bad = 0;
   bad |= make_map(&t->m_wgb, t->w_gb, false, 2 * SMALL_BN, 2560, SMALL_BN / 2);
   bad |= make_map(&t->m_wrb, t->w_rb, false, 2 * SMALL_BN, 128, SMALL_BN / 2);
-  bad |= make_map(&t->m_fc_all, t->fc_all, true, kConvTerms * (Fm + 4) * S, 128, TM);
-  bad |= make_map(&t->m_c1_all, t->c1_all, true, kConvTerms * (Fm + 2) * S, 512, TM);
+  bad |= make_map(&t->m_fc_all, t->fc_all, true, 2 * (Fm + 4) * S, 128, TM);
+  bad |= make_map(&t->m_c1_all, t->c1_all, true, 2 * (Fm + 2) * S, 512, TM);
   bad |= make_map(&t->m_c2, t->c2_h, false, 2 * Fm * S, 512, TM);
   for (int i = 0; i < 5; i++)
     bad |= make_map(&t->m_h[i], t->h_all[i], false, 2 * (Fm + 1) * S, e->gru[i].H, TM);
-  bad |= make_map(&t->m_wconv1, t->w_conv1, true, kConvTerms * 512, 640, DENSE_BN / 2);
-  bad |= make_map(&t->m_wconv2, t->w_conv2, true, kConvTerms * 512, 1536, DENSE_BN / 2);
+  bad |= make_map(&t->m_wconv1, t->w_conv1, true, 2 * 512, 640, DENSE_BN / 2);
+  bad |= make_map(&t->m_wconv2, t->w_conv2, true, 2 * 512, 1536, DENSE_BN / 2);
   for (int i = 0; i < 5; i++) {
     const int rows = (e->gru[i].H / HT) * GRU_BN;
     bad |= make_map(&t->m_w[i], t->w_gru[i], false, 2 * rows, e->gru[i].M, GRU_BN / 2);
     bad |= make_map(&t->m_u[i], t->u_gru[i], false, 2 * rows, e->gru[i].H, GRU_BN / 2);
   }
   if (bad) return tc_fail(PNB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-  TCK(cudaFuncSetAttribute(tc_gemm_kernel<2, 2, GRU_BN, GRU_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)tc_smem_bytes<2, 2, GRU_BN, GRU_STAGES>()));
-  TCK(cudaFuncSetAttribute(tc_gemm_kernel<kConvTerms, kConvTerms, DENSE_BN, DENSE_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)tc_smem_bytes<kConvTerms, kConvTerms, DENSE_BN, DENSE_STAGES>()));
-  TCK(cudaFuncSetAttribute(tc_gemm_kernel<2, 2, SMALL_BN, SMALL_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)tc_smem_bytes<2, 2, SMALL_BN, SMALL_STAGES>()));
+  TCK(cudaFuncSetAttribute(gru_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)tc_smem_bytes<GRU_STAGES, StageLayout<GRU_BN>::kBytes>()));
+  TCK(cudaFuncSetAttribute(tc_gemm_kernel<DENSE_BN, DENSE_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)tc_smem_bytes<DENSE_STAGES, StageLayout<DENSE_BN>::kBytes>()));
+  TCK(cudaFuncSetAttribute(tc_gemm_kernel<SMALL_BN, SMALL_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)tc_smem_bytes<SMALL_STAGES, StageLayout<SMALL_BN>::kBytes>()));
   return PNB_OK;
 }
 
 void tc_release(pnb_engine *e) {
   pnb_tc_state *t = e->tc;
   if (!t) return;
-  void *ptrs[] = {t->fc_all, t->c1_all, t->c2_h, t->w_conv1, t->w_conv2, t->w_gb, t->w_rb};
+  void *ptrs[] = {t->fc_all, t->c1_all, t->c2_h, t->w_conv1, t->w_conv2, t->w_gb, t->w_rb, t->bias_pad, t->cnt};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 5; i++) {
     if (t->h_all[i]) cudaFree(t->h_all[i]);
     if (t->w_gru[i]) cudaFree(t->w_gru[i]);
     if (t->u_gru[i]) cudaFree(t->u_gru[i]);
+    if (t->bias4[i]) cudaFree(t->bias4[i]);
   }
   delete t;
   e->tc = nullptr;
@@ -732,60 +1029,112 @@ int tc_reset(pnb_engine *e) {
   if (!t) return PNB_OK;
   const size_t S = e->S;
   const size_t Fm = e->Fmax;
-  TCK(cudaMemset(t->fc_all, 0, kConvTerms * (Fm + 4) * S * 128 * 2));
-  TCK(cudaMemset(t->c1_all, 0, kConvTerms * (Fm + 2) * S * 512 * 2));
+  TCK(cudaMemset(t->fc_all, 0, 2 * (Fm + 4) * S * 128 * 2));
+  TCK(cudaMemset(t->c1_all, 0, 2 * (Fm + 2) * S * 512 * 2));
   TCK(cudaMemset(t->c2_h, 0, 2 * Fm * S * 512 * 2));
   for (int i = 0; i < 5; i++) TCK(cudaMemset(t->h_all[i], 0, 2 * (Fm + 1) * S * e->gru[i].H * 2));
+  TCK(cudaMemset(t->cnt, 0, (size_t)5 * t->tiles_mp * sizeof(unsigned)));
   return PNB_OK;
 }
 
-int tc_launches_per_step(const pnb_engine *) { return 5; }
-int tc_launches_per_call(const pnb_engine *) { return 3 + 2; }  // kernels only; the slot carry uses copy engines
+// One stream's conv input history (the last 4 fc outputs, the last 2 conv1 outputs; oldest first) as fp32, for
+// pnb_get_state / pnb_set_state.  Between calls the history sits in hop slots 0..3 / 0..1 as two bf16 terms.
+int tc_get_stream_hist(pnb_engine *e, int s, float *fc_hist, float *c1_hist) {
+  pnb_tc_state *t = e->tc;
+  const size_t S = e->S, Fm = e->Fmax;
+  std::vector<__nv_bfloat16> a(128), b(128), c(512), d(512);
+  for (int i = 0; i < 4; i++) {
+    const __nv_bfloat16 *p0 = t->fc_all + ((size_t)i * S + s) * 128;
+    TCK(cudaMemcpy(a.data(), p0, 128 * 2, cudaMemcpyDeviceToHost));
+    TCK(cudaMemcpy(b.data(), p0 + (Fm + 4) * S * 128, 128 * 2, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 128; k++) fc_hist[i * 128 + k] = __bfloat162float(a[k]) + __bfloat162float(b[k]);
+  }
+  for (int i = 0; i < 2; i++) {
+    const __nv_bfloat16 *p0 = t->c1_all + ((size_t)i * S + s) * 512;
+    TCK(cudaMemcpy(c.data(), p0, 512 * 2, cudaMemcpyDeviceToHost));
+    TCK(cudaMemcpy(d.data(), p0 + (Fm + 2) * S * 512, 512 * 2, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 512; k++) c1_hist[i * 512 + k] = __bfloat162float(c[k]) + __bfloat162float(d[k]);
+  }
+  return PNB_OK;
+}
+// h: the five GRU states of the stream, concatenated (4 x 512 + 128), already stored as fp32 by the caller
+int tc_set_stream_hist(pnb_engine *e, int s, const float *fc_hist, const float *c1_hist, const float *h) {
+  pnb_tc_state *t = e->tc;
+  const size_t S = e->S, Fm = e->Fmax;
+  auto put_b2 = [&](const float *v, int n, __nv_bfloat16 *p0, size_t term_stride) -> cudaError_t {
+    std::vector<__nv_bfloat16> a(n), b(n);
+    for (int k = 0; k < n; k++) {
+      a[k] = __float2bfloat16_rn(v[k]);
+      b[k] = __float2bfloat16_rn(v[k] - __bfloat162float(a[k]));
+    }
+    cudaError_t r = cudaMemcpy(p0, a.data(), n * 2, cudaMemcpyHostToDevice);
+    if (r != cudaSuccess) return r;
+    return cudaMemcpy(p0 + term_stride, b.data(), n * 2, cudaMemcpyHostToDevice);
+  };
+  for (int i = 0; i < 4; i++) TCK(put_b2(fc_hist + i * 128, 128, t->fc_all + ((size_t)i * S + s) * 128, (Fm + 4) * S * 128));
+  for (int i = 0; i < 2; i++) TCK(put_b2(c1_hist + i * 512, 512, t->c1_all + ((size_t)i * S + s) * 512, (Fm + 2) * S * 512));
+  size_t off = 0;
+  for (int li = 0; li < 5; li++) {
+    const size_t H = e->gru[li].H;
+    std::vector<__half> hi(H), lo(H);
+    for (size_t k = 0; k < H; k++) {
+      const float sv = h[off + k] * kActScale;
+      hi[k] = __float2half_rn(sv);
+      lo[k] = __float2half_rn(sv - __half2float(hi[k]));
+    }
+    __half *p0 = t->h_all[li] + (size_t)s * H;  // slot 0
+    TCK(cudaMemcpy(p0, hi.data(), H * 2, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(p0 + (Fm + 1) * S * H, lo.data(), H * 2, cudaMemcpyHostToDevice));
+    off += H;
+  }
+  return PNB_OK;
+}
 
-template <int NA, int NB, int BN, int STAGES, bool GRU>
-static void tc_launch(pnb_engine *e, TcArgs &a, int rows, int tiles_n, cudaStream_t st) {
-  // timing diagnostics only (profiles/README.md): with PNB_TC_DEBUG set the network's results are garbage
-  static const int dbg = [] {
-    const char *v = getenv("PNB_TC_DEBUG");
-    const int d = v ? atoi(v) : 0;
-    if (d) fprintf(stderr, "percepnet_b200: PNB_TC_DEBUG=%d -- network outputs are INVALID (timing diagnostics)\n", d);
-    return d;
-  }();
-  a.debug = dbg;
-  a.M = rows;
-  a.tiles_m = (rows + TM - 1) / TM;
-  a.tiles_n = tiles_n;
-  int pairs = ((a.tiles_m + 1) / 2) * a.tiles_n;
+int tc_launches_per_call(const pnb_engine *) { return 7; }  // fc, conv1, conv2, GRU chain, fc_gb, fc_rb, carry
+
+template <typename K, typename A>
+static int tc_launch(pnb_engine *e, K kernel, const A &a, int pairs, size_t smem, cudaStream_t st) {
   int clusters = pairs < e->sm_count / 2 ? pairs : e->sm_count / 2;
+  if (clusters < 1) clusters = 1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(kTcThreads);
-  cfg.dynamicSmemBytes = tc_smem_bytes<NA, NB, BN, STAGES>();
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, tc_gemm_kernel<NA, NB, BN, STAGES, GRU>, a);
+  TCK(cudaLaunchKernelEx(&cfg, kernel, a));
+  return PNB_OK;
+}
+template <int BN, int STAGES>
+static int tc_launch_dense(pnb_engine *e, TcArgs &a, int rows, int tiles_n, cudaStream_t st) {
+  a.M = rows;
+  a.tiles_m = (rows + TM - 1) / TM;
+  a.tiles_n = tiles_n;
+  a.status = e->d_status;
+  const int pairs = ((a.tiles_m + 1) / 2) * a.tiles_n;
+  return tc_launch(e, tc_gemm_kernel<BN, STAGES>, a, pairs, tc_smem_bytes<STAGES, StageLayout<BN>::kBytes>(), st);
 }
 
-static TcSeg mkseg(int a_map, int b_map, int K, int a_k0, int b_k0, int rec, int a_row0, int a_term_rows) {
+static TcSeg mkseg(int a_map, int b_map, int K, int a_k0, int b_k0, int a_row0, int a_term_rows) {
   TcSeg s;
-  s.a_map = a_map; s.b_map = b_map; s.k_blocks = K / BK; s.a_k0 = a_k0; s.b_k0 = b_k0; s.recurrent = rec;
+  s.a_map = a_map; s.b_map = b_map; s.k_blocks = K / BK; s.a_k0 = a_k0; s.b_k0 = b_k0;
   s.a_row0 = a_row0; s.a_term_rows = a_term_rows;
   return s;
 }
 
 // The non-recurrent front of the network for all F hops of the call at once (rnn.cpp:50-52 on F S rows):
-// fc -> conv1 -> conv2.  Returns the number of launches.
+// fc -> conv1 -> conv2.  Returns the number of launches or a negative error.
 int tc_begin_call(pnb_engine *e, int F, cudaStream_t st) {
   pnb_tc_state *t = e->tc;
   const int S = e->S, Fm = e->Fmax;
   const float *tbl = e->tansig();
   const int rows = F * S;
-  int n = 0;
+  int n = 0, rc;
   // fc (fp32 FMA) for every hop -> bf16 terms at slots 4 .. F+3
   {
     ProfScope ps(e, PNB_K_TC_AUX, st);
@@ -798,128 +1147,144 @@ int tc_begin_call(pnb_engine *e, int F, cudaStream_t st) {
   memset(&a, 0, sizeof a);
   a.maps[0] = t->m_fc_all;
   a.maps[1] = t->m_wconv1;
-  for (int q = 0; q < 5; q++) a.seg[q] = mkseg(0, 1, 128, 0, q * 128, 0, q * S, (Fm + 4) * S);
+  for (int q = 0; q < 5; q++) a.seg[q] = mkseg(0, 1, 128, 0, q * 128, q * S, (Fm + 4) * S);
   a.n_seg = 5; a.b_term_rows = 512; a.fmt = 1; a.out_scale = 1.f; a.tansig = tbl;
-  a.bias = e->conv1.b; a.act = e->act_conv1; a.N = 512;
+  a.bias = t->bias_pad; a.act = PNB_ACT_RELU; a.N = 512;
   a.out_b = t->c1_all; a.out_row0 = 2 * S; a.out_plane_rows = (Fm + 2) * S;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    tc_launch<kConvTerms, kConvTerms, DENSE_BN, DENSE_STAGES, false>(e, a, rows, 512 / DENSE_BN, st);
+    if ((rc = tc_launch_dense<DENSE_BN, DENSE_STAGES>(e, a, rows, 512 / DENSE_BN, st))) return rc;
     n++;
   }
   // conv2: three taps -> tanh -> fp16 terms for every hop (gru1 / gru_rb / fc_gb inputs); fp32 copy of the last hop
   memset(&a, 0, sizeof a);
   a.maps[0] = t->m_c1_all;
   a.maps[1] = t->m_wconv2;
-  for (int q = 0; q < 3; q++) a.seg[q] = mkseg(0, 1, 512, 0, q * 512, 0, q * S, (Fm + 2) * S);
+  for (int q = 0; q < 3; q++) a.seg[q] = mkseg(0, 1, 512, 0, q * 512, q * S, (Fm + 2) * S);
   a.n_seg = 3; a.b_term_rows = 512; a.fmt = 1; a.out_scale = 1.f; a.tansig = tbl;
-  a.bias = e->conv2.b; a.act = e->act_conv2; a.N = 512;
+  a.bias = t->bias_pad + 512; a.act = PNB_ACT_TANH; a.N = 512;
   a.out_f32 = e->c2; a.ldc = 512; a.f32_row0 = (F - 1) * S;
   a.out_h = t->c2_h; a.out_row0 = 0; a.out_plane_rows = Fm * S;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    tc_launch<kConvTerms, kConvTerms, DENSE_BN, DENSE_STAGES, false>(e, a, rows, 512 / DENSE_BN, st);
+    if ((rc = tc_launch_dense<DENSE_BN, DENSE_STAGES>(e, a, rows, 512 / DENSE_BN, st))) return rc;
     n++;
-  }
-  // carry the last 4 (2) hop slots to the front for the next call; slot by slot, ascending (ranges may overlap)
-  for (int tm = 0; tm < kConvTerms; tm++) {
-    for (int i = 0; i < 4; i++) {
-      __nv_bfloat16 *base = t->fc_all + (size_t)tm * (Fm + 4) * S * 128;
-      cudaMemcpyAsync(base + (size_t)i * S * 128, base + (size_t)(F + i) * S * 128, (size_t)S * 128 * 2,
-                      cudaMemcpyDeviceToDevice, st);
-    }
-    for (int i = 0; i < 2; i++) {
-      __nv_bfloat16 *base = t->c1_all + (size_t)tm * (Fm + 2) * S * 512;
-      cudaMemcpyAsync(base + (size_t)i * S * 512, base + (size_t)(F + i) * S * 512, (size_t)S * 512 * 2,
-                      cudaMemcpyDeviceToDevice, st);
-    }
   }
   return n;
 }
 
-// The recurrent part of one hop: the five GRUs (rnn.cpp:58-71).  State slot t holds the state BEFORE hop t.
-int tc_step(pnb_engine *e, int tstep, cudaStream_t st) {
+// The recurrent part of all F hops: five GRUs per hop (rnn.cpp:58-71) in one persistent launch.
+// State slot t holds the state BEFORE hop t.
+int tc_gru_chain(pnb_engine *e, int F, cudaStream_t st) {
   pnb_tc_state *t = e->tc;
   const int S = e->S, Fm = e->Fmax;
-  const float *tbl = e->tansig();
-  int n = 0;
-  TcArgs a;
-  const int c2_row0 = tstep * S, c2_terms = Fm * S;
-  const int h_terms = (Fm + 1) * S, h_prev = tstep * S, h_next = (tstep + 1) * S;
-  // each GRU consumes the freshly written state (slot t+1) of the layer below and its own previous state (slot t)
+  ChainArgs a;
+  memset(&a, 0, sizeof a);
+  a.maps[0] = t->m_c2;
+  for (int i = 0; i < 5; i++) { a.maps[1 + i] = t->m_h[i]; a.maps[6 + i] = t->m_w[i]; a.maps[11 + i] = t->m_u[i]; }
+  a.S = S; a.F = F; a.tiles_mp = t->tiles_mp; a.cnt = t->cnt; a.tansig = e->tansig();
+  const int c2_terms = Fm * S, h_terms = (Fm + 1) * S;
+  int unit0 = 0;
   for (int li = 0; li < 5; li++) {
-    const int H = e->gru[li].H, p = e->par[li];
-    memset(&a, 0, sizeof a);
-    int ns = 0;
-    if (li == 0) {
-      a.maps[0] = t->m_c2;
-      a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0, c2_row0, c2_terms);
-    } else if (li < 4) {
-      a.maps[0] = t->m_h[li - 1];
-      a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0, h_next, h_terms);
-    } else {  // gru_rb input = [gru3 state, conv2 out]
-      a.maps[0] = t->m_h[2];
-      a.maps[4] = t->m_c2;
-      a.seg[ns++] = mkseg(0, 2, 512, 0, 0, 0, h_next, h_terms);
-      a.seg[ns++] = mkseg(4, 2, 512, 0, 512, 0, c2_row0, c2_terms);
+    ChainLayer &L = a.L[li];
+    const int H = e->gru[li].H, tiles = H / HT;
+    L.H = H; L.h_kb = H / BK; L.tiles_log2 = tiles == 8 ? 3 : tiles == 4 ? 2 : tiles == 2 ? 1 : 0;
+    L.b_term_rows = tiles * GRU_BN;
+    L.h_map = 1 + li; L.w_map = 6 + li; L.u_map = 11 + li;
+    L.unit0 = unit0; unit0 += t->tiles_mp * tiles;
+    L.par0 = e->par[li];
+    L.scale = t->scale_gru[li];
+    L.bias4 = t->bias4[li];
+    L.h32[0] = e->h[li][0]; L.h32[1] = e->h[li][1];
+    L.h_hl = t->h_all[li]; L.h_term_rows = h_terms;
+    // each GRU consumes the freshly written state (slot t+1) of the layer below (rnn.cpp:58-71)
+    if (li == 0) {          // gru1 <- conv2 out
+      L.n_x = 1; L.x_map[0] = 0; L.x_kb[0] = 512 / BK; L.x_bk0[0] = 0; L.x_row1[0] = 0; L.x_term_rows[0] = c2_terms; L.dep = -1;
+    } else if (li < 4) {    // gru2 <- gru1, gru3 <- gru2, gru_gb <- gru3
+      L.n_x = 1; L.x_map[0] = li; L.x_kb[0] = 512 / BK; L.x_bk0[0] = 0; L.x_row1[0] = 1; L.x_term_rows[0] = h_terms; L.dep = li - 1;
+    } else {                // gru_rb <- [gru3 state, conv2 out]
+      L.n_x = 2;
+      L.x_map[0] = 3; L.x_kb[0] = 512 / BK; L.x_bk0[0] = 0; L.x_row1[0] = 1; L.x_term_rows[0] = h_terms;
+      L.x_map[1] = 0; L.x_kb[1] = 512 / BK; L.x_bk0[1] = 512; L.x_row1[1] = 0; L.x_term_rows[1] = c2_terms;
+      L.dep = 2;
     }
-    a.maps[1] = t->m_h[li];
-    a.maps[2] = t->m_w[li];
-    a.maps[3] = t->m_u[li];
-    a.seg[ns++] = mkseg(1, 3, H, 0, 0, 1, h_prev, h_terms);
-    a.n_seg = ns; a.b_term_rows = (H / HT) * GRU_BN; a.fmt = 0;
-    a.out_scale = t->scale_gru[li]; a.tansig = tbl; a.bias = e->gru[li].b; a.H = H;
-    a.h_old = e->h[li][p]; a.h_new = e->h[li][p ^ 1];
-    a.h_new_h = t->h_all[li]; a.out_row0 = h_next; a.out_plane_rows = h_terms;
-    {
-      ProfScope ps(e, PNB_K_TC_GEMM, st);
-      tc_launch<2, 2, GRU_BN, GRU_STAGES, true>(e, a, S, H / HT, st);
-      n++;
-    }
-    e->par[li] ^= 1;
   }
-  return n;
+  a.units_per_hop = unit0;
+  {
+    ProfScope ps(e, PNB_K_TC_GEMM, st);
+    int rc = tc_launch(e, gru_chain_kernel, a, F * unit0, tc_smem_bytes<GRU_STAGES, StageLayout<GRU_BN>::kBytes>(), st);
+    if (rc) return rc;
+  }
+  if (F & 1)
+    for (int li = 0; li < 5; li++) e->par[li] ^= 1;
+  return 1;
 }
 
 // The two 34-wide output layers for all F hops at once (rnn.cpp:73-80; N padded to 48, fp16 two-term split,
-// sigmoid epilogue), then the carry of the last state slot to slot 0 for the next call.
+// sigmoid epilogue), then the carry of the last slots to the front for the next call.
 int tc_end_call(pnb_engine *e, int F, cudaStream_t st) {
   pnb_tc_state *t = e->tc;
   const int S = e->S, Fm = e->Fmax;
   const float *tbl = e->tansig();
   const int rows = F * S, h_terms = (Fm + 1) * S;
-  int n = 0;
+  int n = 0, rc;
   TcArgs a;
   memset(&a, 0, sizeof a);
   a.maps[0] = t->m_c2;
   for (int q = 0; q < 4; q++) a.maps[1 + q] = t->m_h[q];
   a.maps[5] = t->m_wgb;
-  a.seg[0] = mkseg(0, 5, 512, 0, 0, 0, 0, Fm * S);
-  for (int q = 1; q < 5; q++) a.seg[q] = mkseg(q, 5, 512, 0, q * 512, 0, S, h_terms);  // state after hop t = slot t+1
+  a.seg[0] = mkseg(0, 5, 512, 0, 0, 0, Fm * S);
+  for (int q = 1; q < 5; q++) a.seg[q] = mkseg(q, 5, 512, 0, q * 512, S, h_terms);  // state after hop t = slot t+1
   a.n_seg = 5; a.b_term_rows = SMALL_BN; a.fmt = 0; a.out_scale = t->scale_gb; a.tansig = tbl;
-  a.bias = e->fc_gb.b; a.act = e->act_gb; a.N = 34; a.ldc = 68; a.out_f32 = e->d_gr;
+  a.bias = t->bias_pad + 1024; a.act = PNB_ACT_SIGMOID; a.N = 34; a.ldc = 68; a.out_f32 = e->d_gr;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    tc_launch<2, 2, SMALL_BN, SMALL_STAGES, false>(e, a, rows, 1, st);
+    if ((rc = tc_launch_dense<SMALL_BN, SMALL_STAGES>(e, a, rows, 1, st))) return rc;
     n++;
   }
   memset(&a, 0, sizeof a);
   a.maps[0] = t->m_h[4];
   a.maps[1] = t->m_wrb;
-  a.seg[0] = mkseg(0, 1, 128, 0, 0, 0, S, h_terms);
+  a.seg[0] = mkseg(0, 1, 128, 0, 0, S, h_terms);
   a.n_seg = 1; a.b_term_rows = SMALL_BN; a.fmt = 0; a.out_scale = t->scale_rb; a.tansig = tbl;
-  a.bias = e->fc_rb.b; a.act = e->act_rb; a.N = 34; a.ldc = 68; a.out_f32 = e->d_gr + 34;
+  a.bias = t->bias_pad + 1072; a.act = PNB_ACT_SIGMOID; a.N = 34; a.ldc = 68; a.out_f32 = e->d_gr + 34;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    tc_launch<2, 2, SMALL_BN, SMALL_STAGES, false>(e, a, rows, 1, st);
+    if ((rc = tc_launch_dense<SMALL_BN, SMALL_STAGES>(e, a, rows, 1, st))) return rc;
     n++;
+  }
+  // carry: the last 4 fc / 2 conv1 hop slots and the last state slot move to the front; counters back to zero.
+  // Source and destination ranges are disjoint when F >= 4; shorter calls copy slot by slot, ascending.
+  CarryArgs ca;
+  memset(&ca, 0, sizeof ca);
+  ca.cnt = t->cnt; ca.n_cnt = 5 * t->tiles_mp;
+  int ns = 0;
+  const bool disjoint = F >= 4;
+  for (int tm = 0; tm < 2; tm++) {
+    __nv_bfloat16 *bf = t->fc_all + (size_t)tm * (Fm + 4) * S * 128;
+    __nv_bfloat16 *bc = t->c1_all + (size_t)tm * (Fm + 2) * S * 512;
+    if (disjoint) {
+      ca.seg[ns++] = CarrySeg{reinterpret_cast<uint4 *>(bf), reinterpret_cast<const uint4 *>(bf + (size_t)F * S * 128), (size_t)4 * S * 128 * 2 / 16};
+      ca.seg[ns++] = CarrySeg{reinterpret_cast<uint4 *>(bc), reinterpret_cast<const uint4 *>(bc + (size_t)F * S * 512), (size_t)2 * S * 512 * 2 / 16};
+    } else {
+      for (int i = 0; i < 4; i++)
+        TCK(cudaMemcpyAsync(bf + (size_t)i * S * 128, bf + (size_t)(F + i) * S * 128, (size_t)S * 128 * 2, cudaMemcpyDeviceToDevice, st));
+      for (int i = 0; i < 2; i++)
+        TCK(cudaMemcpyAsync(bc + (size_t)i * S * 512, bc + (size_t)(F + i) * S * 512, (size_t)S * 512 * 2, cudaMemcpyDeviceToDevice, st));
+    }
   }
   for (int li = 0; li < 5; li++) {
     const size_t H = e->gru[li].H;
     for (int tm = 0; tm < 2; tm++) {
       __half *base = t->h_all[li] + (size_t)tm * h_terms * H;
-      cudaMemcpyAsync(base, base + (size_t)F * S * H, (size_t)S * H * 2, cudaMemcpyDeviceToDevice, st);
+      ca.seg[ns++] = CarrySeg{reinterpret_cast<uint4 *>(base), reinterpret_cast<const uint4 *>(base + (size_t)F * S * H), (size_t)S * H * 2 / 16};
     }
+  }
+  ca.n_seg = ns;
+  {
+    ProfScope ps(e, PNB_K_TC_AUX, st);
+    tc_carry_kernel<<<2 * e->sm_count, 256, 0, st>>>(ca);
+    n++;
   }
   return n;
 }

@@ -1,0 +1,83 @@
+"""The tensor-core network path judged against a DOUBLE-PRECISION evaluation of the same network
+(oracle/pn_oracle.c: pn_oracle_compute_rnn_f64 -- same wiring, same tansig table), next to the reference's own
+single-precision arithmetic judged the same way.
+
+Both the reference (sequential fp32 sums, /root/reference/src/nnet.cpp:59-72) and the GPU path (fp32 operands split
+into two 16-bit terms, three tensor-core products, fp32 accumulation) are approximations of that double-precision
+network; the parity bar of 1e-4 relative on g/r is asserted at every amplitude scale, and the tensor path's distance
+from the truth is reported beside the reference's own.
+
+Domain.  The reference's tansig_approx converts floor(.5f + 25 x) to int (src/vec.h:63): undefined for |x| >= 8.6e7
+(on x86 "tanh" then returns its argument).  Frames whose pre-activations get there are outside what the tensor path
+reproduces; the engine must then say so (PNB_ERR_DOMAIN) instead of returning plausible numbers.
+"""
+import numpy as np
+import pytest
+
+from test_gpu_parity import GR_RTOL, _inputs, _oracle_run, api  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+DOMAIN = 8.5e7
+
+
+def _truth(oracle, model, x):
+    """per stream: reference-equivalent fp32 g/r [F,S,68], fp64 g/r [F,S,68], max |pre-activation| [S]"""
+    _, gr32, taps = _oracle_run(oracle, model, x)
+    S = x.shape[0]
+    g64 = np.empty(gr32.shape, np.float64)
+    mp = np.empty(S)
+    for s in range(S):
+        feats = np.stack([t.np("features") for t in taps[s]])
+        g, r, m = oracle.rnn_f64(model, feats)
+        g64[:, s, :34], g64[:, s, 34:] = g, r
+        mp[s] = m.max()
+    return gr32, g64, mp
+
+
+@pytest.mark.parametrize("scale", [1.0, 256.0, 32768.0], ids=["unit", "x256", "int16scale"])
+def test_tensor_path_vs_double_precision(api, oracle, model0, scale):
+    F = 16
+    x = _inputs(scale, F, n_synth=6)
+    if scale == 256.0:
+        x = (x * np.float32(4.0)).astype(np.float32)          # loud enough for the comb-filter branch (sum Ex >= 0.1)
+    gr32, g64, mp = _truth(oracle, model0, x)
+    inside = mp < DOMAIN
+    print(f"scale {scale:g}: {inside.sum()} of {len(mp)} streams stay inside the tanh domain (max |pre| {mp.max():.3g})")
+    assert inside.sum() >= 6
+    xi = np.ascontiguousarray(x[inside])
+    eng = api.Engine(xi.shape[0], 8, model0, api.NN_TENSOR)
+    _, gr = eng.process_stream_chunks(xi, want_gr=True)
+    eng.check()                                               # no domain flag for in-domain input
+    eng.close()
+    t64 = g64[:, inside]
+    den = np.maximum(np.abs(t64), 1e-6)
+    e_tc = (np.abs(gr - t64) / den).max()
+    e_ref = (np.abs(gr32[:, inside] - t64) / den).max()
+    e_pair = (np.abs(gr - gr32[:, inside]) / den).max()
+    print(f"  relative distance to the double-precision network: tensor path {e_tc:.3e}, reference fp32 {e_ref:.3e}; "
+          f"tensor vs reference {e_pair:.3e}")
+    assert e_tc < GR_RTOL
+    assert e_pair < GR_RTOL
+
+
+def test_domain_flag_is_raised_outside_the_tanh_domain(api, oracle, model0):
+    """Input that drives a pre-activation past 8.6e7 (full-scale periodic signals at int16 scale: feature 69, the raw
+    pitch xcorr, reaches 1e10): the tensor engine reports PNB_ERR_DOMAIN; the fp32 engine follows the reference."""
+    from util import edge_signals
+    F = 12
+    sig = edge_signals(F, 32768.0)
+    x = np.stack([sig["sine62"], sig["fullscale_sq"], sig["octave"]]).astype(np.float32)
+    _, _, mp = _truth(oracle, model0, x)
+    print("max |pre-activation| per stream:", mp)
+    if not (mp >= DOMAIN).any():
+        pytest.skip("these weights keep full-scale input inside the domain")
+    eng = api.Engine(x.shape[0], F, model0, api.NN_TENSOR)
+    with pytest.raises(api.PnbError, match="-5"):
+        eng.process(x)
+    with pytest.raises(api.PnbError, match="-5"):            # sticky until reset
+        eng.check()
+    eng.reset()
+    eng.process(np.zeros_like(x))
+    eng.check()
+    eng.close()

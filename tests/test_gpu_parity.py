@@ -181,11 +181,15 @@ def test_latency_and_impulse(api, model0):
 
 def test_postfilter_flag(api, oracle, model0):
     x = _inputs(32768.0, 9, n_synth=2)[:3]
-    ref_out, _, _ = _oracle_run(oracle, model0, x, flags=1)
-    eng = api.Engine(3, 9, model0, api.NN_FP32 | api.POSTFILTER)
+    ref_out, _, taps = _oracle_run(oracle, model0, x, flags=1)
+    ref_g = np.stack([[t.np("g_used") for t in tp] for tp in taps], axis=1)          # [F, S, 34]
+    eng = api.Engine(3, 9, model0, api.NN_FP32 | api.POSTFILTER | api.KEEP_TAPS)
     out, _ = eng.process(x)
+    gr_used = eng.read_tap("g_used", 9)
     eng.close()
-    assert np.abs(out - ref_out).max() <= 2.0        # device sinf vs libm sinf: a few 1e-7 relative on g
+    assert np.abs(np.trunc(out.astype(np.float64)) - np.trunc(ref_out.astype(np.float64))).max() <= PCM_LSB
+    rel = np.abs(gr_used - ref_g) / np.maximum(np.abs(ref_g), 1e-6)
+    assert rel.max() < 1e-6                          # the post-filtered gains themselves
     plain = api.Engine(3, 9, model0)
     out_p, _ = plain.process(x)
     plain.close()
