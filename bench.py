@@ -530,6 +530,10 @@ def main():
         nn_mode = "fp32"
         eng = api.Engine(S, F, model, api.NN_FP32, device=local)
 
+    ov = eng.overlap_info()
+    sched = ({"kind": "chunked overlap", **ov, "note": "network of chunk k on net_sms SMs while analysis k+1 / synthesis k-1 run "
+              "on the other dsp_sms SMs (green contexts); applies to calls of at least two chunks"}
+             if ov["net_sms"] and F >= 2 * ov["chunk_hops"] else {"kind": "serial", **ov})
     n_buf = 3
     bufs = make_step_inputs(S, F, n_buf, rank, device)
     outs = [torch.empty_like(b) for b in bufs]
@@ -706,7 +710,7 @@ def main():
                        "weights": "random-init, reference architecture (7,962,564 params)"},
             "x_realtime": value / 100.0, "samples_per_sec": value * FRAME,
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e, "int16_scale_run": i16run,
-            "cpu_baseline": cpu, "host_numa": numa,
+            "cpu_baseline": cpu, "host_numa": numa, "schedule": sched,
         }
         print(json.dumps(line))
     if world > 1:

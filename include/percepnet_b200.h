@@ -72,7 +72,7 @@ typedef struct pnb_engine pnb_engine;
 /* model: the reference's weight layout (a `const RNNModel*` from a compiled nnet_data.cpp may be
  * passed as is); the weights are copied to the device, the caller's arrays are not retained. */
 int pnb_create(pnb_engine **out, int n_streams, int max_frames_per_call, const pnb_model *model,
-               unsigned flags, int device);
+               unsigned flags, int device);   /* device: CUDA ordinal, or -1 = the calling thread's current device */
 void pnb_destroy(pnb_engine *e);
 int pnb_reset(pnb_engine *e);
 
@@ -80,6 +80,9 @@ int pnb_reset(pnb_engine *e);
  * as raw float32, 32 MB instead of 180 MB of C source and no 46 s compile.  The returned model owns its arrays;
  * release it with pnb_model_free (after pnb_create has copied it, at any time). */
 int pnb_model_load_blob(const char *path, pnb_model **out);
+/* the same from an open stream (a FILE* positioned at the start of the blob; passed as void* to keep <stdio.h> out
+ * of this header); the stream is left open, positioned behind the blob */
+int pnb_model_load_stream(void *file, pnb_model **out);
 void pnb_model_free(pnb_model *m);
 
 /* Host buffers (pageable or pinned).  in/out: n_streams rows of n_frames*480 samples, row strides
@@ -190,6 +193,12 @@ long long pnb_launch_count(const pnb_engine *e);
  * streams' history back to the start of their rows, at most every call, typically every eighth). */
 int pnb_launches_per_call(const pnb_engine *e, int n_frames);
 
+/* How long calls are scheduled on this engine (PNB_NN_TENSOR engines with many streams): calls of at least two
+ * chunks of `chunk_hops` hops run the network of chunk k on `net_sms` SMs while analysis of chunk k+1 and synthesis
+ * of chunk k-1 run on the other `dsp_sms` SMs (two green contexts).  net_sms = 0: every call runs its kernels one
+ * after the other on all SMs.  Environment: PNB_OVERLAP=0 disables, =2 forces it for small batches; PNB_NET_SMS,
+ * PNB_CHUNK tune it (read by pnb_create).  Results do not depend on the schedule. */
+int pnb_overlap_info(const pnb_engine *e, int *net_sms, int *dsp_sms, int *chunk_hops);
 int pnb_n_streams(const pnb_engine *e);
 int pnb_max_frames(const pnb_engine *e);
 const char *pnb_last_error(void);

@@ -69,6 +69,7 @@ def load_library() -> C.CDLL:
     L.pnb_launch_count.restype = C.c_longlong
     L.pnb_launches_per_call.argtypes = [vp, i]
     L.pnb_n_streams.argtypes = [vp]
+    L.pnb_overlap_info.argtypes = [vp, vp, vp, vp]
     L.pnb_max_frames.argtypes = [vp]
     L.pnb_profile_enable.argtypes = [vp, i]
     L.pnb_profile_read.argtypes = [vp, vp, vp]
@@ -81,9 +82,9 @@ def load_library() -> C.CDLL:
 
 
 EXPORTS = ("pnb_create", "pnb_destroy", "pnb_reset", "pnb_process_host_f32", "pnb_process_host_i16",
-           "pnb_model_load_blob", "pnb_model_free", "pnb_train_records_host", "pnb_train_records_device", "pnb_submit_train_records", "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_wait", "pnb_check",
+           "pnb_model_load_blob", "pnb_model_load_stream", "pnb_model_free", "pnb_train_records_host", "pnb_train_records_device", "pnb_submit_train_records", "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_wait", "pnb_check",
            "pnb_read_tap", "pnb_state_size", "pnb_get_state", "pnb_set_state", "pnb_pitch_only_device", "pnb_pitch_only_host", "pnb_launch_count",
-           "pnb_launches_per_call", "pnb_profile_enable", "pnb_profile_read", "pnb_kernel_class_name", "pnb_n_streams", "pnb_max_frames", "pnb_last_error", "pnb_version")
+           "pnb_launches_per_call", "pnb_profile_enable", "pnb_profile_read", "pnb_kernel_class_name", "pnb_n_streams", "pnb_overlap_info", "pnb_max_frames", "pnb_last_error", "pnb_version")
 
 
 def pitch_only_device(d_buf: int, stride: int, n_units: int, d_period: int, d_corr: int, d_gain: int, d_lag: int = 0,
@@ -263,6 +264,11 @@ class Engine:
         cnt = (C.c_longlong * n)()
         self._ck(self.L.pnb_profile_read(self.h, ms, cnt), "pnb_profile_read")
         return {self.L.pnb_kernel_class_name(k).decode(): (ms[k], int(cnt[k])) for k in range(n) if cnt[k]}
+
+    def overlap_info(self) -> dict:
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.pnb_overlap_info(self.h, C.byref(a), C.byref(b), C.byref(c)), "pnb_overlap_info")
+        return {"net_sms": a.value, "dsp_sms": b.value, "chunk_hops": c.value}
 
     @property
     def launches(self) -> int:

@@ -1097,32 +1097,21 @@ template <int L>
 static size_t analysis_smem_bytes() {
   return ((sizeof(BlockSmem) + 15) / 16) * 16 + AnaCfg<L>::kStreamsPerBlock * sizeof(WarpSmem);
 }
-// lanes per stream in the analysis kernel.  32 (a warp per stream) is faster on B200: with 16 (two streams per
-// warp) the serial pitch stretches cost half, but only 8 warps fit per SM and the kernel becomes latency-bound
-// (5.65 ms vs 5.05 ms per step, profiles/bench_history.md).  PNB_ANALYSIS_LANES=16 selects the other variant.
-static int g_ana_lanes = 32;
 static size_t synthesis_smem_bytes() { return ((sizeof(SynBlockSmem) + 15) / 16) * 16 + kSynWarps * sizeof(SynWarpSmem); }
 
 cudaError_t dsp_configure() {
-  if (const char *v = getenv("PNB_ANALYSIS_LANES")) g_ana_lanes = (atoi(v) == 16) ? 16 : 32;
+  // a warp per stream; the two-streams-per-warp variant (L = 16) of round 1 was measured slower on B200 (only 8 warps
+  // fit per SM: 5.65 vs 5.05 ms per step, profiles/bench_history.md) and is no longer instantiated
   cudaError_t e = cudaFuncSetAttribute(analysis_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)analysis_smem_bytes<32>());
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(analysis_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)analysis_smem_bytes<16>());
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)synthesis_smem_bytes());
 }
 
 int launch_analysis(const AnalysisArgs &a, cudaStream_t st) {
-  if (g_ana_lanes == 32) {
-    dim3 grid((a.n_streams + AnaCfg<32>::kStreamsPerBlock - 1) / AnaCfg<32>::kStreamsPerBlock);
-    analysis_kernel<32><<<grid, AnaCfg<32>::kWarps * 32, analysis_smem_bytes<32>(), st>>>(a);
-  } else {
-    dim3 grid((a.n_streams + AnaCfg<16>::kStreamsPerBlock - 1) / AnaCfg<16>::kStreamsPerBlock);
-    analysis_kernel<16><<<grid, AnaCfg<16>::kWarps * 32, analysis_smem_bytes<16>(), st>>>(a);
-  }
+  dim3 grid((a.n_streams + AnaCfg<32>::kStreamsPerBlock - 1) / AnaCfg<32>::kStreamsPerBlock);
+  analysis_kernel<32><<<grid, AnaCfg<32>::kWarps * 32, analysis_smem_bytes<32>(), st>>>(a);
   return 1;
 }
 // ------------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 //   stage_in -> analysis (all F hops; one warp per stream) -> F x network step -> synthesis -> slide history
 // The network step is the only part that is sequential in time across the batch; analysis and synthesis
 // need no network state, so hops are processed F at a time.
+#include <cuda.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -134,6 +135,79 @@ static int check_model(const pnb_model *m) {
   return PNB_OK;
 }
 
+constexpr int kMaxChunks = 512;  // chunks one call may be cut into (chunked overlap schedule)
+
+// ------------------------------------------------------------------------------------------
+// SM partition (driver green contexts, reached through the runtime's entry-point query: no libcuda link)
+// ------------------------------------------------------------------------------------------
+namespace {
+struct GreenApi {
+  CUresult (*DeviceGet)(CUdevice *, int) = nullptr;
+  CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource *, CUdevResourceType) = nullptr;
+  CUresult (*DevSmResourceSplitByCount)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int) = nullptr;
+  CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int) = nullptr;
+  CUresult (*GreenCtxCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*GreenCtxStreamCreate)(CUstream *, CUgreenCtx, unsigned int, int) = nullptr;
+  CUresult (*GreenCtxDestroy)(CUgreenCtx) = nullptr;
+  bool ok = false;
+};
+const GreenApi &green_api() {
+  static GreenApi g = [] {
+    GreenApi a;
+    auto get = [](const char *name, void **fn) {
+      cudaDriverEntryPointQueryResult qr;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &qr) == cudaSuccess && *fn != nullptr;
+    };
+    a.ok = get("cuDeviceGet", (void **)&a.DeviceGet) && get("cuDeviceGetDevResource", (void **)&a.DeviceGetDevResource) &&
+           get("cuDevSmResourceSplitByCount", (void **)&a.DevSmResourceSplitByCount) &&
+           get("cuDevResourceGenerateDesc", (void **)&a.DevResourceGenerateDesc) && get("cuGreenCtxCreate", (void **)&a.GreenCtxCreate) &&
+           get("cuGreenCtxStreamCreate", (void **)&a.GreenCtxStreamCreate) && get("cuGreenCtxDestroy", (void **)&a.GreenCtxDestroy);
+    return a;
+  }();
+  return g;
+}
+}  // namespace
+
+// Splits the device's SMs into a share for the network kernels and the rest for the DSP kernels and creates one stream
+// in each.  Best effort: on any failure the engine simply keeps the serial schedule (net_sms stays 0).
+static void setup_overlap(pnb_engine *e, int want_net_sms) {
+  const GreenApi &G = green_api();
+  if (!G.ok) return;
+  CUdevice dev;
+  CUdevResource all, grp, rem;
+  unsigned int ngrp = 1;
+  CUdevResourceDesc d_net = nullptr, d_dsp = nullptr;
+  CUgreenCtx g_net = nullptr, g_dsp = nullptr;
+  CUstream s_net = nullptr, s_dsp = nullptr;
+  if (G.DeviceGet(&dev, e->device) != CUDA_SUCCESS) return;
+  if (G.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return;
+  if (G.DevSmResourceSplitByCount(&grp, &ngrp, &all, &rem, 0, (unsigned)want_net_sms) != CUDA_SUCCESS || ngrp != 1) return;
+  if (grp.sm.smCount < 8 || rem.sm.smCount < 8) return;
+  if (G.DevResourceGenerateDesc(&d_net, &grp, 1) != CUDA_SUCCESS || G.DevResourceGenerateDesc(&d_dsp, &rem, 1) != CUDA_SUCCESS) return;
+  if (G.GreenCtxCreate(&g_net, d_net, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
+  if (G.GreenCtxCreate(&g_dsp, d_dsp, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { G.GreenCtxDestroy(g_net); return; }
+  if (G.GreenCtxStreamCreate(&s_net, g_net, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
+      G.GreenCtxStreamCreate(&s_dsp, g_dsp, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+    if (s_net) cudaStreamDestroy((cudaStream_t)s_net);
+    G.GreenCtxDestroy(g_net); G.GreenCtxDestroy(g_dsp);
+    return;
+  }
+  bool ev_ok = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&e->ev_join_net, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&e->ev_join_dsp, cudaEventDisableTiming) == cudaSuccess;
+  const int nchunks = (e->Fmax + e->chunk - 1) / e->chunk + 5;  // + the short chunks at both ends of a call
+  e->ev_ana.assign(nchunks, nullptr);
+  e->ev_net.assign(nchunks, nullptr);
+  for (int k = 0; k < nchunks && ev_ok; k++)
+    ev_ok = cudaEventCreateWithFlags(&e->ev_ana[k], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_net[k], cudaEventDisableTiming) == cudaSuccess;
+  e->green_net = g_net; e->green_dsp = g_dsp;
+  e->s_net = (cudaStream_t)s_net; e->s_dsp = (cudaStream_t)s_dsp;
+  if (!ev_ok) return;  // net_sms stays 0: the serial schedule; pnb_destroy releases what was created
+  e->net_sms = (int)grp.sm.smCount;
+  e->dsp_sms = (int)rem.sm.smCount;
+}
+
 extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const pnb_model *model, unsigned flags,
                           int device) {
   if (!out) return fail(PNB_ERR_ARG, "out is NULL");
@@ -152,6 +226,10 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
   if (ce != cudaSuccess || ndev == 0)
     return fail(PNB_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU path",
                 ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  if (device == -1) {  // the calling thread's current device
+    ce = cudaGetDevice(&device);
+    if (ce != cudaSuccess) return fail(PNB_ERR_CUDA, "cudaGetDevice failed: %s", cudaGetErrorString(ce));
+  }
   if (device < 0 || device >= ndev) return fail(PNB_ERR_ARG, "device %d out of range (have %d)", device, ndev);
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -258,9 +336,17 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
     CKD(dalloc(&e->nx, S * 512));
     CKD(dalloc(&e->nh, S * 512));
   }
+  e->tc_sms = e->sm_count;
   if (flags & PNB_NN_TENSOR) {
     int trc = tc_prepare(e, model);
     if (trc) { pnb_destroy(e); return trc; }
+    // Calls of at least two chunks overlap the DSP kernels with the network on disjoint SMs (pnb_engine.h).
+    // PNB_OVERLAP=0 keeps the serial schedule; PNB_NET_SMS / PNB_CHUNK tune the split and the chunk length.
+    const char *ov = getenv("PNB_OVERLAP"), *ns = getenv("PNB_NET_SMS"), *ch = getenv("PNB_CHUNK");
+    if (ch && atoi(ch) >= 1) e->chunk = atoi(ch);
+    const bool worth = (long long)n_streams >= 2048 && max_frames >= 2 * e->chunk && (max_frames + e->chunk - 1) / e->chunk + 5 <= kMaxChunks;
+    if (!(ov && atoi(ov) == 0) && (worth || (ov && atoi(ov) == 2)) && max_frames >= 2 * e->chunk)
+      setup_overlap(e, ns && atoi(ns) >= 8 ? atoi(ns) : (e->sm_count * 7 / 16 / 8) * 8);
   }
   CKD(cudaDeviceSynchronize());
   *out = e;
@@ -303,6 +389,15 @@ extern "C" void pnb_destroy(pnb_engine *e) {
   }
   if (e->s_in) cudaStreamDestroy(e->s_in);
   if (e->s_out) cudaStreamDestroy(e->s_out);
+  for (cudaEvent_t ev : e->ev_ana) if (ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : e->ev_net) if (ev) cudaEventDestroy(ev);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join_net) cudaEventDestroy(e->ev_join_net);
+  if (e->ev_join_dsp) cudaEventDestroy(e->ev_join_dsp);
+  if (e->s_net) cudaStreamDestroy(e->s_net);
+  if (e->s_dsp) cudaStreamDestroy(e->s_dsp);
+  if (e->green_net) green_api().GreenCtxDestroy((CUgreenCtx)e->green_net);
+  if (e->green_dsp) green_api().GreenCtxDestroy((CUgreenCtx)e->green_dsp);
   for (auto &r : e->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -490,38 +585,116 @@ static int advance_line(pnb_engine *e, int F, cudaStream_t st) {
 
 // Enqueues one call.  Host-side stream state (hop counter, line offset, GRU buffer parity) is committed only after
 // every launch was accepted; a failure in between leaves work half-enqueued, so the engine is poisoned until pnb_reset.
+static AnalysisArgs analysis_args(pnb_engine *e, int h0, int n) {
+  const size_t S = e->S, o = (size_t)h0 * S;
+  AnalysisArgs a;
+  a.pcm = e->d_pcm + e->line_off + (size_t)h0 * kFrame;  // this chunk's [history | new hops] window of every row
+  a.pcm_stride = e->pcm_stride; a.n_streams = e->S; a.n_frames = n; a.tab = e->d_tab;
+  a.feat = e->d_feat + o * kFeat; a.zring = e->d_zring; a.ering = e->d_ering; a.ring = e->ring; a.hop0 = e->hop + h0;
+  a.P = e->d_P ? e->d_P + o * kBins : nullptr; a.Ex = e->d_Ex + o * kBands; a.raw = nullptr; a.silence = e->d_sil + o;
+  a.last_period = e->d_last_period; a.last_gain = e->d_last_gain;
+  a.tap_pitch = e->d_tap_pitch ? e->d_tap_pitch + o * 4 : nullptr;
+  a.tap_pitchf = e->d_tap_pitchf ? e->d_tap_pitchf + o * 2 : nullptr;
+  return a;
+}
+static SynthesisArgs synthesis_args(pnb_engine *e, int h0, int n, float *d_out, short *d_out16, size_t out_stride) {
+  const size_t S = e->S, o = (size_t)h0 * S;
+  SynthesisArgs s;
+  s.zring = e->d_zring; s.ring = e->ring; s.hop0 = e->hop + h0; s.P = e->d_P + o * kBins; s.gr = e->d_gr + o * 68;
+  s.Ex = e->d_Ex + o * kBands; s.silence = e->d_sil + o; s.n_streams = e->S; s.n_frames = n;
+  s.tab = e->d_tab; s.synth_mem = e->d_synth;
+  s.out = d_out ? d_out + (size_t)h0 * kFrame : nullptr;
+  s.out16 = d_out16 ? d_out16 + (size_t)h0 * kFrame : nullptr;
+  s.out_stride = out_stride;
+  s.postfilter = (e->flags & PNB_POSTFILTER) ? 1 : 0;
+  s.tap_g = e->d_tap_g ? e->d_tap_g + o * kBands : nullptr;
+  return s;
+}
+
+// Enqueues one call.  Host-side stream state (hop counter, line offset, GRU buffer parity) is committed only after
+// every launch was accepted; a failure in between leaves work half-enqueued, so the engine is poisoned until pnb_reset.
 static int process_device_enqueue(pnb_engine *e, const float *d_in, const short *d_in16, size_t in_stride, float *d_out,
                                   short *d_out16, size_t out_stride, int F, float *d_gr, cudaStream_t st, long long *n_out) {
   const int S = e->S;
   long long n = 0;
-  float *line = e->d_pcm + e->line_off;  // this call's [history | new hops] window of every row
-  { ProfScope ps(e, PNB_K_STAGE_IN, st); n += launch_stage_in(line, e->pcm_stride, d_in, d_in16, in_stride, S, F * kFrame, st); }
-  AnalysisArgs a;
-  a.pcm = line; a.pcm_stride = e->pcm_stride; a.n_streams = S; a.n_frames = F; a.tab = e->d_tab;
-  a.feat = e->d_feat; a.zring = e->d_zring; a.ering = e->d_ering; a.ring = e->ring; a.hop0 = e->hop;
-  a.P = e->d_P; a.Ex = e->d_Ex; a.raw = nullptr; a.silence = e->d_sil;
-  a.last_period = e->d_last_period; a.last_gain = e->d_last_gain;
-  a.tap_pitch = e->d_tap_pitch; a.tap_pitchf = e->d_tap_pitchf;
-  { ProfScope ps(e, PNB_K_ANALYSIS, st); n += launch_analysis(a, st); }
-  CK(cudaGetLastError());
-  if (e->flags & PNB_NN_TENSOR) {
-    int k = tc_begin_call(e, F, st);
-    if (k < 0) return k;
-    n += k;
-    if ((k = tc_gru_chain(e, F, st)) < 0) return k;
-    n += k;
-    if ((k = tc_end_call(e, F, st)) < 0) return k;
-    n += k;
+  float *line = e->d_pcm + e->line_off;
+  const bool tensor = (e->flags & PNB_NN_TENSOR) != 0;
+  if (tensor && e->net_sms > 0 && F >= 2 * e->chunk) {
+    // ---- chunked two-stream schedule: s_dsp runs analysis k+1 and synthesis k-1 while s_net runs the network of chunk k
+    cudaStream_t sd = e->s_dsp, sn = e->s_net;
+    // chunk lengths: short at both ends (the first analysis and the last network chunk run with the other partition
+    // idle), e->chunk in between
+    int len[kMaxChunks], C = 0;
+    {
+      int left = F, head[2] = {e->chunk / 4 > 0 ? e->chunk / 4 : 1, e->chunk / 2 > 0 ? e->chunk / 2 : 1};
+      const int tail_total = head[0] + head[1];
+      for (int i = 0; i < 2 && left > tail_total + e->chunk; i++) { len[C++] = head[i]; left -= head[i]; }
+      while (left > tail_total + e->chunk) { len[C++] = e->chunk; left -= e->chunk; }
+      if (left > tail_total) { len[C++] = left - tail_total; left = tail_total; }
+      if (left > head[0]) { len[C++] = left - head[0]; left = head[0]; }
+      if (left > 0) len[C++] = left;
+    }
+    CK(cudaEventRecord(e->ev_fork, st));
+    CK(cudaStreamWaitEvent(sd, e->ev_fork, 0));
+    CK(cudaStreamWaitEvent(sn, e->ev_fork, 0));
+    { ProfScope ps(e, PNB_K_STAGE_IN, sd); n += launch_stage_in(line, e->pcm_stride, d_in, d_in16, in_stride, S, F * kFrame, sd); }
+    e->tc_sms = e->net_sms;
+    int h0 = 0, p0 = 0, pn = 0;  // current chunk; previous chunk (start, length)
+    for (int k = 0; k < C; k++) {
+      const int nh = len[k];
+      { ProfScope ps(e, PNB_K_ANALYSIS, sd); n += launch_analysis(analysis_args(e, h0, nh), sd); }
+      CK(cudaEventRecord(e->ev_ana[k], sd));
+      CK(cudaStreamWaitEvent(sn, e->ev_ana[k], 0));
+      int q = tc_front(e, h0, nh, F, sn);
+      if (q < 0) { e->tc_sms = e->sm_count; return q; }
+      n += q;
+      if ((q = tc_gru_chain(e, h0, nh, sn)) < 0) { e->tc_sms = e->sm_count; return q; }
+      n += q;
+      if ((q = tc_out(e, h0, nh, sn)) < 0) { e->tc_sms = e->sm_count; return q; }
+      n += q;
+      CK(cudaEventRecord(e->ev_net[k], sn));
+      if (k >= 1) {  // one chunk behind, so that the next analysis is never queued behind a wait for the network
+        CK(cudaStreamWaitEvent(sd, e->ev_net[k - 1], 0));
+        ProfScope ps(e, PNB_K_SYNTHESIS, sd);
+        n += launch_synthesis(synthesis_args(e, p0, pn, d_out, d_out16, out_stride), sd);
+      }
+      p0 = h0; pn = nh; h0 += nh;
+    }
+    {
+      CK(cudaStreamWaitEvent(sd, e->ev_net[C - 1], 0));
+      ProfScope ps(e, PNB_K_SYNTHESIS, sd);
+      n += launch_synthesis(synthesis_args(e, p0, pn, d_out, d_out16, out_stride), sd);
+    }
+    int q = tc_carry(e, F, sn);
+    e->tc_sms = e->sm_count;
+    if (q < 0) return q;
+    n += q;
+    n += advance_line(e, F, sd);
+    CK(cudaEventRecord(e->ev_join_net, sn));
+    CK(cudaEventRecord(e->ev_join_dsp, sd));
+    CK(cudaStreamWaitEvent(st, e->ev_join_net, 0));
+    CK(cudaStreamWaitEvent(st, e->ev_join_dsp, 0));
   } else {
-    for (int t = 0; t < F; t++) n += nn_step_f32(e, t, st);
+    // ---- serial schedule on the caller's stream
+    { ProfScope ps(e, PNB_K_STAGE_IN, st); n += launch_stage_in(line, e->pcm_stride, d_in, d_in16, in_stride, S, F * kFrame, st); }
+    { ProfScope ps(e, PNB_K_ANALYSIS, st); n += launch_analysis(analysis_args(e, 0, F), st); }
+    CK(cudaGetLastError());
+    if (tensor) {
+      int k = tc_front(e, 0, F, F, st);
+      if (k < 0) return k;
+      n += k;
+      if ((k = tc_gru_chain(e, 0, F, st)) < 0) return k;
+      n += k;
+      if ((k = tc_out(e, 0, F, st)) < 0) return k;
+      n += k;
+      if ((k = tc_carry(e, F, st)) < 0) return k;
+      n += k;
+    } else {
+      for (int t = 0; t < F; t++) n += nn_step_f32(e, t, st);
+    }
+    { ProfScope ps(e, PNB_K_SYNTHESIS, st); n += launch_synthesis(synthesis_args(e, 0, F, d_out, d_out16, out_stride), st); }
+    n += advance_line(e, F, st);
   }
-  SynthesisArgs s;
-  s.zring = e->d_zring; s.ring = e->ring; s.hop0 = e->hop; s.P = e->d_P; s.gr = e->d_gr; s.Ex = e->d_Ex; s.silence = e->d_sil; s.n_streams = S; s.n_frames = F;
-  s.tab = e->d_tab; s.synth_mem = e->d_synth; s.out = d_out; s.out16 = d_out16; s.out_stride = out_stride;
-  s.postfilter = (e->flags & PNB_POSTFILTER) ? 1 : 0;
-  s.tap_g = e->d_tap_g;
-  { ProfScope ps(e, PNB_K_SYNTHESIS, st); n += launch_synthesis(s, st); }
-  n += advance_line(e, F, st);
   if (d_gr) CK(cudaMemcpyAsync(d_gr, e->d_gr, (size_t)F * S * 68 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   CK(cudaGetLastError());
   *n_out = n;
@@ -856,6 +1029,11 @@ struct StreamState {
   float fc_hist[4][128];     // conv1 input history (last four fc outputs), oldest first
   float c1_hist[2][512];     // conv2 input history (last two conv1 outputs)
   float h[4 * 512 + 128];    // gru1, gru2, gru3, gru_gb, gru_rb
+  // tensor-mode engines keep the conv histories as three bf16 terms; the sum above does not always split back into the
+  // same terms (a low term of exactly half an ulp), so the raw terms travel too and a tensor-mode engine restores those
+  unsigned has_terms;
+  unsigned short fc_terms[3][4][128];
+  unsigned short c1_terms[3][2][512];
 };
 constexpr unsigned kStateMagic = 0x53424E50u;  // "PNBS"
 }  // namespace
@@ -896,7 +1074,10 @@ extern "C" int pnb_get_state(pnb_engine *e, int stream, void *dst, size_t bytes)
     CK(cudaMemcpy(st->h + off, e->h[li][e->par[li]] + s * H, H * 4, cudaMemcpyDeviceToHost));
     off += H;
   }
-  if (e->flags & PNB_NN_TENSOR) return tc_get_stream_hist(e, stream, &st->fc_hist[0][0], &st->c1_hist[0][0]);
+  if (e->flags & PNB_NN_TENSOR) {
+    st->has_terms = 1;
+    return tc_get_stream_hist(e, stream, &st->fc_hist[0][0], &st->c1_hist[0][0], &st->fc_terms[0][0][0], &st->c1_terms[0][0][0]);
+  }
   for (int k = 0; k < 4; k++) {
     const long c = e->hop - 4 + k;
     CK(cudaMemcpy(st->fc_hist[k], e->ring_fc + ((size_t)((c % 5 + 5) % 5) * S + s) * 128, 128 * 4, cudaMemcpyDeviceToHost));
@@ -937,7 +1118,9 @@ extern "C" int pnb_set_state(pnb_engine *e, int stream, const void *src, size_t 
     CK(cudaMemcpy(e->h[li][e->par[li]] + s * H, st->h + off, H * 4, cudaMemcpyHostToDevice));
     off += H;
   }
-  if (e->flags & PNB_NN_TENSOR) return tc_set_stream_hist(e, stream, &st->fc_hist[0][0], &st->c1_hist[0][0], st->h);
+  if (e->flags & PNB_NN_TENSOR)
+    return tc_set_stream_hist(e, stream, &st->fc_hist[0][0], &st->c1_hist[0][0], st->h,
+                              st->has_terms ? &st->fc_terms[0][0][0] : nullptr, st->has_terms ? &st->c1_terms[0][0][0] : nullptr);
   for (int k = 0; k < 4; k++) {
     const long c = e->hop - 4 + k;
     CK(cudaMemcpy(e->ring_fc + ((size_t)((c % 5 + 5) % 5) * S + s) * 128, st->fc_hist[k], 128 * 4, cudaMemcpyHostToDevice));
@@ -973,8 +1156,18 @@ extern "C" int pnb_model_load_blob(const char *path, pnb_model **out) {
   *out = nullptr;
   FILE *f = fopen(path, "rb");
   if (!f) return fail(PNB_ERR_ARG, "cannot open %s", path);
+  int rc = pnb_model_load_stream(f, out);
+  fclose(f);
+  return rc;
+}
+
+extern "C" int pnb_model_load_stream(void *file, pnb_model **out) {
+  if (!file || !out) return fail(PNB_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  FILE *f = static_cast<FILE *>(file);
+  const char *path = "weight stream";
   char magic[8];
-  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "PNBW0001", 8) != 0) { fclose(f); return fail(PNB_ERR_ARG, "%s is not a PNBW0001 weight file", path); }
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "PNBW0001", 8) != 0) return fail(PNB_ERR_ARG, "%s is not a PNBW0001 weight file", path);
   BlobModel *b = new BlobModel();
   b->arrays.resize(25);
   int ai = 0;
@@ -1003,7 +1196,6 @@ extern "C" int pnb_model_load_blob(const char *path, pnb_model **out) {
   gru(b->gru[4], 1024, 128);
   dense(b->fc_gb, 2560, 34, PNB_ACT_SIGMOID);
   dense(b->fc_rb, 128, 34, PNB_ACT_SIGMOID);
-  fclose(f);
   if (!ok) { delete b; return fail(PNB_ERR_ARG, "%s is truncated or has unexpected layer sizes", path); }
   b->m.fc = &b->fc; b->m.conv1 = &b->conv1; b->m.conv2 = &b->conv2;
   b->m.gru1 = &b->gru[0]; b->m.gru2 = &b->gru[1]; b->m.gru3 = &b->gru[2]; b->m.gru_gb = &b->gru[3]; b->m.gru_rb = &b->gru[4];
@@ -1070,8 +1262,18 @@ extern "C" long long pnb_launch_count(const pnb_engine *e) { return e ? e->launc
 extern "C" int pnb_launches_per_call(const pnb_engine *e, int n_frames) {
   if (!e) return 0;
   // without the history move of advance_line (at most one more launch per call)
-  if (e->flags & PNB_NN_TENSOR) return 3 + tc_launches_per_call(e);
+  if (e->flags & PNB_NN_TENSOR) {
+    const int C = (e->net_sms > 0 && n_frames >= 2 * e->chunk) ? (n_frames + e->chunk - 1) / e->chunk + 4 : 1;  // upper bound
+    return 1 + C * (2 + tc_launches_per_chunk(e)) + 1;  // stage_in + per chunk (analysis, network, synthesis) + carry
+  }
   return 3 + 25 * n_frames;
+}
+extern "C" int pnb_overlap_info(const pnb_engine *e, int *net_sms, int *dsp_sms, int *chunk_hops) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  if (net_sms) *net_sms = e->net_sms;
+  if (dsp_sms) *dsp_sms = e->dsp_sms;
+  if (chunk_hops) *chunk_hops = e->chunk;
+  return PNB_OK;
 }
 extern "C" int pnb_n_streams(const pnb_engine *e) { return e ? e->S : 0; }
 extern "C" int pnb_max_frames(const pnb_engine *e) { return e ? e->Fmax : 0; }

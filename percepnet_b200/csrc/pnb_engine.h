@@ -66,6 +66,16 @@ struct pnb_engine {
   long long submitted = 0;
 
   pnb_tc_state *tc = nullptr;
+  int tc_sms = 0;  // SMs the persistent network kernels may occupy (all of them, or the network's share of a partition)
+  // Overlap of the DSP kernels with the network inside long calls (tensor mode): the call is cut into chunks of hops,
+  // analysis / synthesis of neighbouring chunks run on s_dsp while the network of a chunk runs on s_net, each stream
+  // in its own green context = its own disjoint set of SMs.  The network phase alone is capped by the board's power
+  // limit (it clocks down to ~1.4 GHz) while the DSP phase leaves that budget unused; side by side they even out.
+  void *green_net = nullptr, *green_dsp = nullptr;  // CUgreenCtx
+  cudaStream_t s_net = nullptr, s_dsp = nullptr;
+  int net_sms = 0, dsp_sms = 0, chunk = 8;
+  cudaEvent_t ev_fork = nullptr, ev_join_net = nullptr, ev_join_dsp = nullptr;
+  std::vector<cudaEvent_t> ev_ana, ev_net;
   int last_frames = 0;
   long long launches = 0;
   // status word on the device: bit 0 = an activation left the domain in which the reference's tansig_approx is
@@ -92,12 +102,16 @@ struct pnb_engine {
 int tc_prepare(pnb_engine *e, const pnb_model *model);
 void tc_release(pnb_engine *e);
 int tc_reset(pnb_engine *e);
-int tc_begin_call(pnb_engine *e, int F, cudaStream_t st);  // hop-parallel front of the network, all F hops
-int tc_gru_chain(pnb_engine *e, int F, cudaStream_t st);   // the five GRUs of all F hops, one persistent launch
-int tc_end_call(pnb_engine *e, int F, cudaStream_t st);    // hop-parallel tail: the two output layers, slot carry
-int tc_launches_per_call(const pnb_engine *e);
-int tc_get_stream_hist(pnb_engine *e, int s, float *fc_hist, float *c1_hist);   // pnb_get_state
-int tc_set_stream_hist(pnb_engine *e, int s, const float *fc_hist, const float *c1_hist, const float *h);  // pnb_set_state
+// the network of hops [h0, h0+n) of a call of F hops: hop-parallel front, the GRU chain, hop-parallel output layers
+int tc_front(pnb_engine *e, int h0, int n, int F, cudaStream_t st);
+int tc_gru_chain(pnb_engine *e, int h0, int n, cudaStream_t st);
+int tc_out(pnb_engine *e, int h0, int n, cudaStream_t st);
+int tc_carry(pnb_engine *e, int F, cudaStream_t st);       // once per call, after its last tc_out
+int tc_launches_per_chunk(const pnb_engine *e);
+// pnb_get_state / pnb_set_state: conv histories as fp32 sums and as the raw bf16 term pairs [2 terms][slots][width]
+int tc_get_stream_hist(pnb_engine *e, int s, float *fc_hist, float *c1_hist, unsigned short *fc_terms, unsigned short *c1_terms);
+int tc_set_stream_hist(pnb_engine *e, int s, const float *fc_hist, const float *c1_hist, const float *h,
+                       const unsigned short *fc_terms, const unsigned short *c1_terms);
 
 // RAII marker used by the launch schedule: records an event pair around a launch when profiling
 struct ProfScope {

@@ -147,6 +147,14 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// Ties 16 loaded registers to the point after tmem_ld_wait(): the empty volatile asm "produces" them, so no use of
+// the values can be scheduled ahead of the wait (the wait itself names no registers).
+__device__ __forceinline__ void tmem_ld_fence16(uint32_t *r) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                    "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -208,27 +216,36 @@ __device__ __forceinline__ void store_split_h16(const float *v, __half *hi_p, __
   ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
   pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
 }
-__device__ __forceinline__ void store_split_b16(const float *v, __nv_bfloat16 *t0_p, __nv_bfloat16 *t1_p) {
-  uint32_t a[8], b[8];
+// bf16 split of 16 values into `terms` (2 or 3) planes `plane` elements apart
+__device__ __forceinline__ void store_split_b16(const float *v, __nv_bfloat16 *t0_p, size_t plane, int terms) {
+  uint32_t a[8], b[8], c3[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    const float r0 = v[2 * i] - hf.x, r1 = v[2 * i + 1] - hf.y;
+    const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+    const float2 lf = __bfloat1622float2(l);
+    const __nv_bfloat162 m = __floats2bfloat162_rn(r0 - lf.x, r1 - lf.y);
     a[i] = *reinterpret_cast<const uint32_t *>(&h);
     b[i] = *reinterpret_cast<const uint32_t *>(&l);
+    c3[i] = *reinterpret_cast<const uint32_t *>(&m);
   }
-  uint4 *p0 = reinterpret_cast<uint4 *>(t0_p), *p1 = reinterpret_cast<uint4 *>(t1_p);
+  uint4 *p0 = reinterpret_cast<uint4 *>(t0_p), *p1 = reinterpret_cast<uint4 *>(t0_p + plane);
   p0[0] = make_uint4(a[0], a[1], a[2], a[3]); p0[1] = make_uint4(a[4], a[5], a[6], a[7]);
   p1[0] = make_uint4(b[0], b[1], b[2], b[3]); p1[1] = make_uint4(b[4], b[5], b[6], b[7]);
+  if (terms == 3) {
+    uint4 *p2 = reinterpret_cast<uint4 *>(t0_p + 2 * plane);
+    p2[0] = make_uint4(c3[0], c3[1], c3[2], c3[3]); p2[1] = make_uint4(c3[4], c3[5], c3[6], c3[7]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ shared kernel pieces
-template <int BN>
-struct StageLayout {  // two terms of A (this CTA's 128 rows) and two terms of this CTA's half of the B rows
+template <int BN, int NT = 2>
+struct StageLayout {  // NT terms of A (this CTA's 128 rows), then NT terms of this CTA's half of the B rows
   static constexpr int kABytes = TM * BK * 2;
   static constexpr int kBBytes = (BN / 2) * BK * 2;
-  static constexpr int kBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kBytes = NT * (kABytes + kBBytes);
 };
 
 struct Pipe {  // position in an mbarrier ring
@@ -244,13 +261,13 @@ struct SmemCarve {
   uint32_t *tmem_slot;
   float *tbl;
 };
-template <int STAGES, int STAGE_BYTES>
+template <int STAGES, int REGION_BYTES>  // REGION_BYTES: the stage ring (the barriers sit behind it)
 __device__ __forceinline__ SmemCarve carve(uint8_t *smem_raw) {
   // the swizzled tiles need 512-byte (SW64) alignment; align the carve-up to 1024 by hand
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   SmemCarve c;
   c.stages = smem;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + REGION_BYTES);
   c.full = smem_u32(bars);
   c.empty = c.full + 8 * STAGES;
   c.acc_full = c.empty + 8 * STAGES;
@@ -259,9 +276,14 @@ __device__ __forceinline__ SmemCarve carve(uint8_t *smem_raw) {
   c.tbl = reinterpret_cast<float *>(c.tmem_slot + 4);
   return c;
 }
-template <int STAGES, int STAGE_BYTES>
+template <int STAGES, int REGION_BYTES>
 constexpr size_t tc_smem_bytes() {
-  return (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 256 * 4 + 1024;
+  return (size_t)REGION_BYTES + (2 * STAGES + 4) * 8 + 16 + 256 * 4 + 1024;
+}
+template <int BN, int ST2, int ST3>
+constexpr size_t dense_smem_bytes() {
+  constexpr int r2 = ST2 * StageLayout<BN, 2>::kBytes, r3 = ST3 * StageLayout<BN, 3>::kBytes;
+  return tc_smem_bytes<(ST2 > ST3 ? ST2 : ST3), (r2 > r3 ? r2 : r3)>();
 }
 
 // common prologue: barriers, TMEM allocation (2 accumulator buffers), activation table, zeroed accumulators
@@ -306,18 +328,36 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem_base, int warp) {
   }
 }
 
-// One k-block of a tile on the MMA side: the three products of both 16-wide k-steps, then the stage is released.
-// Runs warp-converged; `a_lo` / `b_lo` are the descriptor low words of the stage's first A / B term.
-template <int BN>
-__device__ __forceinline__ void mma_kblock(uint32_t dcol, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t empty_bar) {
-  using SL = StageLayout<BN>;
+// One k-block of a tile on the MMA side: the significant products of both 16-wide k-steps, then the stage is released.
+// Runs warp-converged; `a_lo` is the descriptor low word of the stage's first A term (B terms follow the A terms).
+// Two terms per operand: hi hi, hi lo, lo hi.  Three terms (t0 t1 t2, each 8 bits below the previous): the six
+// products of total order <= 2, issued in three passes over K, smallest products first (PASS 0: order 2, PASS 1:
+// order 1, PASS 2: t0 t0).  The tensor core adds into the fp32 accumulator with truncation at the accumulator's
+// magnitude, so correction products added to an already large sum lose exactly the bits they were meant to supply;
+// summed among themselves first, they do not.
+template <int BN, int NT, int PASS = -1>
+__device__ __forceinline__ void mma_kblock(uint32_t dcol, uint32_t a_lo, uint32_t idesc, uint32_t empty_bar) {
+  using SL = StageLayout<BN, NT>;
+  constexpr uint32_t A = SL::kABytes >> 4, B = SL::kBBytes >> 4;
+  const uint32_t b_lo = a_lo + NT * A;
   if (elect_one()) {
 #pragma unroll
     for (int ks = 0; ks < BK / 16; ks++) {
-      // (a term, b term): hi hi, hi lo, lo hi
-      umma_f16(dcol, desc64(a_lo + ks * 2), desc64(b_lo + ks * 2), idesc);
-      umma_f16(dcol, desc64(a_lo + ks * 2), desc64(b_lo + (SL::kBBytes >> 4) + ks * 2), idesc);
-      umma_f16(dcol, desc64(a_lo + (SL::kABytes >> 4) + ks * 2), desc64(b_lo + ks * 2), idesc);
+      const uint32_t a = a_lo + ks * 2, b = b_lo + ks * 2;
+      if (NT == 2) {
+        umma_f16(dcol, desc64(a), desc64(b), idesc);
+        umma_f16(dcol, desc64(a), desc64(b + B), idesc);
+        umma_f16(dcol, desc64(a + A), desc64(b), idesc);
+      } else if (PASS == 0) {
+        umma_f16(dcol, desc64(a + A), desc64(b + B), idesc);
+        umma_f16(dcol, desc64(a), desc64(b + 2 * B), idesc);
+        umma_f16(dcol, desc64(a + 2 * A), desc64(b), idesc);
+      } else if (PASS == 1) {
+        umma_f16(dcol, desc64(a), desc64(b + B), idesc);
+        umma_f16(dcol, desc64(a + A), desc64(b), idesc);
+      } else {
+        umma_f16(dcol, desc64(a), desc64(b), idesc);
+      }
     }
     umma_commit(empty_bar);  // frees the stage in both CTAs once these MMAs have read it
   }
@@ -345,6 +385,8 @@ struct TcArgs {
   const float *tansig;  // 201-entry table (global)
   const float *bias;    // padded to a multiple of 16 entries
   int *status;          // engine status word: bit 0 = an activation left the reference's defined domain
+  const int *wide;      // null, or a device word: non-zero = run with three operand terms (six products) instead of two
+  int out_terms;        // bf16 terms written to out_b (2 or 3)
   int act;
   int N;                // valid output columns
   int ldc;              // row stride of out_f32
@@ -358,25 +400,17 @@ struct TcArgs {
 
 __host__ __device__ constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_constant__ TcArgs args) {
-  using SL = StageLayout<BN>;
-  constexpr int kAccCols = pow2_cols(BN);  // TMEM columns per accumulator buffer
-  constexpr int kTmemCols = 2 * kAccCols;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const SmemCarve c = carve<STAGES, SL::kBytes>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int crank = (int)cluster_ctarank();  // 0 = leader
-  const int n_pairs_cta = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
-  const int total_pairs = ((args.tiles_m + 1) >> 1) * args.tiles_n;  // work unit: one B tile x two row tiles
-  const uint32_t tmem_base = tc_prologue<STAGES, kTmemCols>(c, args.tansig, warp, lane);
-  const uint32_t stage0 = smem_u32(c.stages);
-
-  if (warp == 0) {
-    // ===== TMA producer (both CTAs): own A rows, own half of the B rows; bytes counted on the leader's barrier =====
-    Pipe p;
-    for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta) {
-      const int n_tile = pair % args.tiles_n, m0 = (2 * (pair / args.tiles_n) + crank) * TM;
+// ===== TMA producer (both CTAs): own A rows, own half of the B rows; bytes counted on the leader's barrier =====
+template <int BN, int NT, int STAGES>
+__device__ __forceinline__ void dense_producer(const TcArgs &args, const SmemCarve &c, uint32_t stage0, int crank, int pair_id,
+                                               int n_pairs_cta, int total_pairs) {
+  using SL = StageLayout<BN, NT>;
+  Pipe p;
+  for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta) {
+    const int n_tile = pair % args.tiles_n, m0 = (2 * (pair / args.tiles_n) + crank) * TM;
+    // three-term operands: three passes over K (see mma_kblock); pass q needs the terms below 3 - q of either operand
+    for (int pass = 0; pass < (NT == 3 ? 3 : 1); pass++) {
+      const int nt = NT == 3 ? 3 - pass : NT;
       for (int s = 0; s < args.n_seg; s++) {
         const TcSeg &sg = args.seg[s];
         const CUtensorMap *ma = &args.maps[sg.a_map], *mb = &args.maps[sg.b_map];
@@ -385,43 +419,90 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
           mbar_wait(c.empty + 8 * p.st, p.ph ^ 1);  // fresh barrier: passes immediately
           if (elect_one()) {
             const uint32_t fb = c.full + 8 * p.st;
-            if (crank == 0) mbar_expect_tx(fb, 2 * SL::kBytes);
+            if (crank == 0) mbar_expect_tx(fb, 2 * nt * (SL::kABytes + SL::kBBytes));
             const uint32_t sp = stage0 + p.st * SL::kBytes;
-            tma_load_2d_pair(sp, ma, fb, sg.a_k0 + kb * BK, arow);
-            tma_load_2d_pair(sp + SL::kABytes, ma, fb, sg.a_k0 + kb * BK, sg.a_term_rows + arow);
-            tma_load_2d_pair(sp + 2 * SL::kABytes, mb, fb, sg.b_k0 + kb * BK, brow);
-            tma_load_2d_pair(sp + 2 * SL::kABytes + SL::kBBytes, mb, fb, sg.b_k0 + kb * BK, args.b_term_rows + brow);
+#pragma unroll
+            for (int tm = 0; tm < NT; tm++) {
+              if (tm < nt) {
+                tma_load_2d_pair(sp + tm * SL::kABytes, ma, fb, sg.a_k0 + kb * BK, tm * sg.a_term_rows + arow);
+                tma_load_2d_pair(sp + NT * SL::kABytes + tm * SL::kBBytes, mb, fb, sg.b_k0 + kb * BK, tm * args.b_term_rows + brow);
+              }
+            }
           }
           __syncwarp();
           p.advance(STAGES);
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer: the leader CTA's warp 1 drives both SMs' tensor cores =====
-    if (crank == 0) {
-      const uint32_t idesc = idesc_f16(BN, args.fmt);
-      const uint32_t a_lo0 = desc_lo(stage0);
-      Pipe p;
-      int j = 0;
-      for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta, j++) {
-        const int buf = j & 1;
-        mbar_wait(c.acc_empty + 8 * buf, ((j >> 1) & 1) ^ 1);  // both epilogues drained (and re-zeroed) this buffer
+  }
+}
+// ===== MMA issuer: the leader CTA's warp 1 drives both SMs' tensor cores =====
+template <int BN, int NT, int STAGES, int ACC_COLS>
+__device__ __forceinline__ void dense_mma(const TcArgs &args, const SmemCarve &c, uint32_t stage0, uint32_t tmem_base, int pair_id,
+                                          int n_pairs_cta, int total_pairs) {
+  using SL = StageLayout<BN, NT>;
+  const uint32_t idesc = idesc_f16(BN, args.fmt);
+  const uint32_t a_lo0 = desc_lo(stage0);
+  Pipe p;
+  int j = 0;
+  for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta, j++) {
+    const int buf = j & 1;
+    mbar_wait(c.acc_empty + 8 * buf, ((j >> 1) & 1) ^ 1);  // both epilogues drained (and re-zeroed) this buffer
+    tc_fence_after();
+    const uint32_t acc = tmem_base + buf * ACC_COLS;
+    int nkb = 0;
+    for (int s = 0; s < args.n_seg; s++) nkb += args.seg[s].k_blocks;
+    if (NT == 3) {
+      for (int kb = 0; kb < nkb; kb++) {
+        mbar_wait(c.full + 8 * p.st, p.ph);
         tc_fence_after();
-        const uint32_t acc = tmem_base + buf * kAccCols;
-        for (int s = 0; s < args.n_seg; s++) {
-          const int nkb = args.seg[s].k_blocks;
-          for (int kb = 0; kb < nkb; kb++) {
-            mbar_wait(c.full + 8 * p.st, p.ph);
-            tc_fence_after();
-            const uint32_t a_lo = a_lo0 + p.st * (SL::kBytes >> 4);
-            mma_kblock<BN>(acc, a_lo, a_lo + ((2 * SL::kABytes) >> 4), idesc, c.empty + 8 * p.st);
-            p.advance(STAGES);
-          }
-        }
-        if (elect_one()) umma_commit(c.acc_full + 8 * buf);  // both epilogues
-        __syncwarp();
+        mma_kblock<BN, NT, 0>(acc, a_lo0 + p.st * (SL::kBytes >> 4), idesc, c.empty + 8 * p.st);
+        p.advance(STAGES);
       }
+      for (int kb = 0; kb < nkb; kb++) {
+        mbar_wait(c.full + 8 * p.st, p.ph);
+        tc_fence_after();
+        mma_kblock<BN, NT, 1>(acc, a_lo0 + p.st * (SL::kBytes >> 4), idesc, c.empty + 8 * p.st);
+        p.advance(STAGES);
+      }
+    }
+    for (int kb = 0; kb < nkb; kb++) {
+      mbar_wait(c.full + 8 * p.st, p.ph);
+      tc_fence_after();
+      mma_kblock<BN, NT, 2>(acc, a_lo0 + p.st * (SL::kBytes >> 4), idesc, c.empty + 8 * p.st);
+      p.advance(STAGES);
+    }
+    if (elect_one()) umma_commit(c.acc_full + 8 * buf);  // both epilogues
+    __syncwarp();
+  }
+}
+
+// ST2 stages of two-term operands; ST3 > 0 adds a three-term mode (ST3 stages) chosen at run time from *args.wide
+template <int BN, int ST2, int ST3>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_constant__ TcArgs args) {
+  constexpr int kStagesMax = ST2 > ST3 ? ST2 : ST3;
+  constexpr int kRegion = (ST2 * StageLayout<BN, 2>::kBytes > ST3 * StageLayout<BN, 3>::kBytes) ? ST2 * StageLayout<BN, 2>::kBytes
+                                                                                               : ST3 * StageLayout<BN, 3>::kBytes;
+  constexpr int kAccCols = pow2_cols(BN);  // TMEM columns per accumulator buffer
+  constexpr int kTmemCols = 2 * kAccCols;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const SmemCarve c = carve<kStagesMax, kRegion>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();  // 0 = leader
+  const int n_pairs_cta = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
+  const int total_pairs = ((args.tiles_m + 1) >> 1) * args.tiles_n;  // work unit: one B tile x two row tiles
+  const uint32_t tmem_base = tc_prologue<kStagesMax, kTmemCols>(c, args.tansig, warp, lane);
+  const uint32_t stage0 = smem_u32(c.stages);
+  // the same word for every thread of the launch (written by an earlier launch): both CTAs take the same branch
+  const bool wide = ST3 > 0 && args.wide != nullptr && *args.wide != 0;
+
+  if (warp == 0) {
+    if (ST3 > 0 && wide) dense_producer<BN, 3, ST3 ? ST3 : 1>(args, c, stage0, crank, pair_id, n_pairs_cta, total_pairs);
+    else dense_producer<BN, 2, ST2>(args, c, stage0, crank, pair_id, n_pairs_cta, total_pairs);
+  } else if (warp == 1) {
+    if (crank == 0) {
+      if (ST3 > 0 && wide) dense_mma<BN, 3, ST3 ? ST3 : 1, kAccCols>(args, c, stage0, tmem_base, pair_id, n_pairs_cta, total_pairs);
+      else dense_mma<BN, 2, ST2, kAccCols>(args, c, stage0, tmem_base, pair_id, n_pairs_cta, total_pairs);
     }
   } else if (warp >= 4) {
     // ===== epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31, one row per thread =====
@@ -446,6 +527,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
         for (int q = 0; q < 4; q++) bq[q] = __ldg(reinterpret_cast<const float4 *>(args.bias + j0) + q);
         tmem_ld_wait();
+        tmem_ld_fence16(d);
         if (row_ok && j0 < N) {
           const float *bs = reinterpret_cast<const float *>(bq);
           float v[16];
@@ -475,7 +557,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
           if (args.out_h)
             store_split_h16(v, args.out_h + orow * N + j0, args.out_h + ((size_t)args.out_plane_rows + orow) * N + j0);
           if (args.out_b)
-            store_split_b16(v, args.out_b + orow * N + j0, args.out_b + ((size_t)args.out_plane_rows + orow) * N + j0);
+            store_split_b16(v, args.out_b + orow * N + j0, (size_t)args.out_plane_rows * N, args.out_terms);
         }
         tmem_st16_zero(tlane + col);  // this thread's columns are read: zero them for the buffer's next tile
       }
@@ -512,7 +594,8 @@ struct ChainLayer {
 struct ChainArgs {
   CUtensorMap maps[16];  // 0: conv2 out, 1..5: state slots of the five GRUs, 6..10: input weights, 11..15: recurrent weights
   ChainLayer L[5];
-  int S, F;
+  int S, F;              // streams; hops this launch covers
+  int t0;                // first hop of this launch inside the call (slot / counter arithmetic is per call)
   int tiles_mp;          // row pairs (256 streams each)
   int units_per_hop;
   unsigned *cnt;         // [5][tiles_mp] epilogue-warp completions, zero at launch
@@ -522,8 +605,9 @@ struct ChainArgs {
 struct Unit { int t, l, mp, nt; };
 __device__ __forceinline__ Unit decode_unit(const ChainArgs &a, int u) {
   Unit x;
-  x.t = u / a.units_per_hop;
-  int r = u - x.t * a.units_per_hop;
+  const int tl = u / a.units_per_hop;
+  int r = u - tl * a.units_per_hop;
+  x.t = a.t0 + tl;
   x.l = 0;
 #pragma unroll
   for (int i = 1; i < 5; i++) x.l = (r >= a.L[i].unit0) ? i : x.l;
@@ -549,7 +633,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_c
   constexpr int STAGES = GRU_STAGES;
   constexpr int kAccCols = 4 * HT, kTmemCols = 2 * kAccCols;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const SmemCarve c = carve<STAGES, SL::kBytes>(smem_raw);
+  const SmemCarve c = carve<STAGES, STAGES * SL::kBytes>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int crank = (int)cluster_ctarank();
   const int n_pairs_cta = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
@@ -616,14 +700,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_c
           mbar_wait(c.full + 8 * p.st, p.ph);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + p.st * (SL::kBytes >> 4);
-          mma_kblock<GRU_BN>(acc, a_lo, a_lo + ((2 * SL::kABytes) >> 4), idesc, c.empty + 8 * p.st);
+          mma_kblock<GRU_BN, 2>(acc, a_lo, idesc, c.empty + 8 * p.st);
           p.advance(STAGES);
         }
         for (int kb = 0; kb < L.h_kb; kb++) {
           mbar_wait(c.full + 8 * p.st, p.ph);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + p.st * (SL::kBytes >> 4);
-          mma_kblock<GRU_BN>(acc + HT, a_lo, a_lo + ((2 * SL::kABytes) >> 4), idesc, c.empty + 8 * p.st);
+          mma_kblock<GRU_BN, 2>(acc + HT, a_lo, idesc, c.empty + 8 * p.st);
           p.advance(STAGES);
         }
         if (elect_one()) umma_commit(c.acc_full + 8 * buf);
@@ -670,6 +754,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_c
         tmem_ld16_nowait(tlane + 3 * HT + col, nh);
         const float4 *b4 = L.bias4 + un.nt * HT + col;
         tmem_ld_wait();
+        tmem_ld_fence16(zs); tmem_ld_fence16(rs); tmem_ld_fence16(nx); tmem_ld_fence16(nh);
         // this thread's columns are in registers: zero them for the buffer's next tile
         tmem_st16_zero(tlane + col); tmem_st16_zero(tlane + HT + col);
         tmem_st16_zero(tlane + 2 * HT + col); tmem_st16_zero(tlane + 3 * HT + col);
@@ -710,13 +795,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_c
   tc_teardown<kTmemCols>(tmem_base, warp);
 }
 
-constexpr int DENSE_STAGES = 6, SMALL_BN = 48, SMALL_STAGES = 8;
+constexpr int DENSE_STAGES = 6, DENSE_STAGES3 = 4, SMALL_BN = 48, SMALL_STAGES = 8;
+// conv layers: fc / conv1 outputs are stored as THREE bf16 terms.  Two terms (16 bits, three products) reproduce the
+// network to 1e-5 while activations are O(10) -- every input at the CLI's amplitude scale; louder input (fc outputs
+// in the thousands at x256) needs the third term (six products) to stay inside 1e-4 of the double-precision network
+// (tests/test_gpu_fp64_truth.py).  fc_split_kernel raises the engine's `wide` word when an fc output reaches
+// kWideThreshold; the conv launches read it.
+constexpr int kConvTerms = 3;
+constexpr float kWideThreshold = 128.f;
 
-// fc 70 -> 128 relu in fp32 FMA (0.1 % of the MACs; K = 70 is no tensor-core shape), emitting the two bf16
-// terms conv1 consumes.  One block per 4 rows, one thread per output.
+// fc 70 -> 128 relu in fp32 FMA (0.1 % of the MACs; K = 70 is no tensor-core shape), emitting the three bf16
+// terms conv1 consumes.  One block per 4 rows, one thread per output.  Raises bit 1 of *wide when an output
+// reaches kWideThreshold (see kConvTerms).
 __global__ void __launch_bounds__(128) fc_split_kernel(const float *__restrict__ feat, const float *__restrict__ W,
                                                        const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out,
-                                                       int M, size_t plane_rows) {
+                                                       int M, size_t plane_rows, int *__restrict__ wide) {
   __shared__ float f[4][72];
   const int r0 = blockIdx.x * 4;
   for (int i = threadIdx.x; i < 4 * 70; i += blockDim.x) {
@@ -732,32 +825,43 @@ __global__ void __launch_bounds__(128) fc_split_kernel(const float *__restrict__
     for (int rr = 0; rr < 4; rr++) a[rr] = fmaf(w, f[rr][k], a[rr]);
   }
   const size_t plane = plane_rows * 128;
+  bool big = false;
   for (int rr = 0; rr < 4; rr++) {
     if (r0 + rr >= M) break;
     float v = a[rr] < 0.f ? 0.f : a[rr];
+    big |= !(v < kWideThreshold);  // also NaN
     __nv_bfloat16 t0 = __float2bfloat16_rn(v);
-    __nv_bfloat16 t1 = __float2bfloat16_rn(v - __bfloat162float(t0));
+    float r = v - __bfloat162float(t0);
+    __nv_bfloat16 t1 = __float2bfloat16_rn(r);
+    __nv_bfloat16 t2 = __float2bfloat16_rn(r - __bfloat162float(t1));
     size_t o = (size_t)(r0 + rr) * 128 + n;
-    out[o] = t0; out[plane + o] = t1;
+    out[o] = t0; out[plane + o] = t1; out[2 * plane + o] = t2;
   }
+  if (__any_sync(0xffffffffu, big) && (threadIdx.x & 31) == 0) atomicOr(wide, 2);
 }
 
 // End-of-call bookkeeping in one launch: the hop slots the next call reads first (last 4 fc / 2 conv1 outputs,
 // last GRU states) move to the front of their buffers, and the chain's dependency counters return to zero.
-struct CarrySeg { uint4 *dst; const uint4 *src; size_t n16; };
+// A segment shifts `n_slots` slots down by `shift` slots.  One thread owns the same element of every slot and walks
+// the slots in ascending order, so a slot that is both source and destination (shift < n_slots) is read before it is
+// overwritten -- by the same thread, no cross-thread ordering needed.
+struct CarrySeg { uint4 *base; size_t slot16; int n_slots, shift; };
 struct CarryArgs {
-  CarrySeg seg[14];
+  CarrySeg seg[16];
   int n_seg;
   unsigned *cnt;
   int n_cnt;
+  int *wide;  // bit 1 = this call saw a large fc output, bit 0 = the previous call did (its hops are still in the conv taps)
 };
 __global__ void __launch_bounds__(256) tc_carry_kernel(const __grid_constant__ CarryArgs a) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
   for (int s = 0; s < a.n_seg; s++) {
     const CarrySeg sg = a.seg[s];
-    for (size_t i = tid; i < sg.n16; i += nth) sg.dst[i] = sg.src[i];
+    for (size_t i = tid; i < sg.slot16; i += nth)
+      for (int k = 0; k < sg.n_slots; k++) sg.base[(size_t)k * sg.slot16 + i] = sg.base[(size_t)(k + sg.shift) * sg.slot16 + i];
   }
   for (size_t i = tid; i < (size_t)a.n_cnt; i += nth) a.cnt[i] = 0u;
+  if (tid == 0) *a.wide = (*a.wide >> 1) & 1;
 }
 
 }  // namespace
@@ -768,13 +872,13 @@ struct pnb_tc_state {
   // Multi-hop buffers: rows are (hop slot, stream).  The conv layers carry no recurrence, so they run once per
   // call over all F hops (M = F S rows); a tap is the same buffer read `tap` slots later.  Slots 0..3 (0..1) hold
   // the last hops of the previous call.
-  __nv_bfloat16 *fc_all = nullptr;   // [2][(Fmax+4) S][128]  fc outputs, bf16 terms
-  __nv_bfloat16 *c1_all = nullptr;   // [2][(Fmax+2) S][512]  conv1 outputs
+  __nv_bfloat16 *fc_all = nullptr;   // [3][(Fmax+4) S][128]  fc outputs, bf16 terms
+  __nv_bfloat16 *c1_all = nullptr;   // [3][(Fmax+2) S][512]  conv1 outputs
   __half *c2_h = nullptr;            // [2][Fmax S][512]      conv2 outputs, fp16 terms
   __half *h_all[5] = {};             // [2][(Fmax+1) S][H]    GRU states as fp16 terms, slot t+1 = after hop t,
                                      //                       slot 0 = carried from the previous call
   // packed weights
-  __nv_bfloat16 *w_conv1 = nullptr, *w_conv2 = nullptr;  // [2][512][K]
+  __nv_bfloat16 *w_conv1 = nullptr, *w_conv2 = nullptr;  // [3][512][K]
   __half *w_gru[5] = {}, *u_gru[5] = {};                 // [2][tiles*192][K]
   float scale_gru[5] = {};                               // 2^-(10 + e)
   float4 *bias4[5] = {};                                 // per unit {b_z + b'_z, b_r + b'_r, b_n, b'_n}
@@ -782,6 +886,7 @@ struct pnb_tc_state {
   float scale_gb = 0.f, scale_rb = 0.f;
   float *bias_pad = nullptr;                             // conv1 [512] | conv2 [512] | fc_gb [48] | fc_rb [48]
   unsigned *cnt = nullptr;                               // chain dependency counters [5][tiles_mp]
+  int *wide = nullptr;                                   // see kConvTerms
   int tiles_mp = 0;
   // tensor maps
   CUtensorMap m_fc_all, m_c1_all, m_c2, m_h[5], m_wconv1, m_wconv2, m_w[5], m_u[5], m_wgb, m_wrb;
@@ -850,15 +955,18 @@ static void pack_gru(const float *W, int K, int H, float scale, const int order[
         }
       }
 }
-// dense/conv weights: W[k*N + n] -> [n][k], two bf16 terms
-static void pack_dense_b2(const float *W, int K, int N, std::vector<__nv_bfloat16> &out) {
-  out.assign((size_t)2 * N * K, __float2bfloat16(0.f));
+// dense/conv weights: W[k*N + n] -> [n][k], three bf16 terms
+static void pack_dense_b3(const float *W, int K, int N, std::vector<__nv_bfloat16> &out) {
+  out.assign((size_t)3 * N * K, __float2bfloat16(0.f));
   for (int n = 0; n < N; n++)
     for (int k = 0; k < K; k++) {
       float w = W[(size_t)k * N + n];
       __nv_bfloat16 t0 = __float2bfloat16_rn(w);
+      float r = w - __bfloat162float(t0);
+      __nv_bfloat16 t1 = __float2bfloat16_rn(r);
       out[(size_t)n * K + k] = t0;
-      out[((size_t)N + n) * K + k] = __float2bfloat16_rn(w - __bfloat162float(t0));
+      out[((size_t)N + n) * K + k] = t1;
+      out[((size_t)2 * N + n) * K + k] = __float2bfloat16_rn(r - __bfloat162float(t1));
     }
 }
 
@@ -936,17 +1044,18 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
   e->tc = t;
   const size_t S = e->S;
   const size_t Fm = e->Fmax;
-  TCK(dev_zeros(&t->fc_all, 2 * (Fm + 4) * S * 128));
-  TCK(dev_zeros(&t->c1_all, 2 * (Fm + 2) * S * 512));
+  TCK(dev_zeros(&t->fc_all, kConvTerms * (Fm + 4) * S * 128));
+  TCK(dev_zeros(&t->c1_all, kConvTerms * (Fm + 2) * S * 512));
+  TCK(dev_zeros(&t->wide, 1));
   TCK(dev_zeros(&t->c2_h, 2 * Fm * S * 512));
   for (int i = 0; i < 5; i++) TCK(dev_zeros(&t->h_all[i], 2 * (Fm + 1) * S * e->gru[i].H));
   t->tiles_mp = (int)((S + 2 * TM - 1) / (2 * TM));
   TCK(dev_zeros(&t->cnt, (size_t)5 * t->tiles_mp));
   {
     std::vector<__nv_bfloat16> p;
-    pack_dense_b2(model->conv1->input_weights, 640, 512, p);
+    pack_dense_b3(model->conv1->input_weights, 640, 512, p);
     TCK(dev_upload(&t->w_conv1, p));
-    pack_dense_b2(model->conv2->input_weights, 1536, 512, p);
+    pack_dense_b3(model->conv2->input_weights, 1536, 512, p);
     TCK(dev_upload(&t->w_conv2, p));
   }
   for (int i = 0; i < 5; i++) {
@@ -987,13 +1096,13 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
   int bad = 0;
   bad |= make_map(&t->m_wgb, t->w_gb, false, 2 * SMALL_BN, 2560, SMALL_BN / 2);
   bad |= make_map(&t->m_wrb, t->w_rb, false, 2 * SMALL_BN, 128, SMALL_BN / 2);
-  bad |= make_map(&t->m_fc_all, t->fc_all, true, 2 * (Fm + 4) * S, 128, TM);
-  bad |= make_map(&t->m_c1_all, t->c1_all, true, 2 * (Fm + 2) * S, 512, TM);
+  bad |= make_map(&t->m_fc_all, t->fc_all, true, kConvTerms * (Fm + 4) * S, 128, TM);
+  bad |= make_map(&t->m_c1_all, t->c1_all, true, kConvTerms * (Fm + 2) * S, 512, TM);
   bad |= make_map(&t->m_c2, t->c2_h, false, 2 * Fm * S, 512, TM);
   for (int i = 0; i < 5; i++)
     bad |= make_map(&t->m_h[i], t->h_all[i], false, 2 * (Fm + 1) * S, e->gru[i].H, TM);
-  bad |= make_map(&t->m_wconv1, t->w_conv1, true, 2 * 512, 640, DENSE_BN / 2);
-  bad |= make_map(&t->m_wconv2, t->w_conv2, true, 2 * 512, 1536, DENSE_BN / 2);
+  bad |= make_map(&t->m_wconv1, t->w_conv1, true, kConvTerms * 512, 640, DENSE_BN / 2);
+  bad |= make_map(&t->m_wconv2, t->w_conv2, true, kConvTerms * 512, 1536, DENSE_BN / 2);
   for (int i = 0; i < 5; i++) {
     const int rows = (e->gru[i].H / HT) * GRU_BN;
     bad |= make_map(&t->m_w[i], t->w_gru[i], false, 2 * rows, e->gru[i].M, GRU_BN / 2);
@@ -1001,18 +1110,18 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
   }
   if (bad) return tc_fail(PNB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   TCK(cudaFuncSetAttribute(gru_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)tc_smem_bytes<GRU_STAGES, StageLayout<GRU_BN>::kBytes>()));
-  TCK(cudaFuncSetAttribute(tc_gemm_kernel<DENSE_BN, DENSE_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)tc_smem_bytes<DENSE_STAGES, StageLayout<DENSE_BN>::kBytes>()));
-  TCK(cudaFuncSetAttribute(tc_gemm_kernel<SMALL_BN, SMALL_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)tc_smem_bytes<SMALL_STAGES, StageLayout<SMALL_BN>::kBytes>()));
+                           (int)tc_smem_bytes<GRU_STAGES, GRU_STAGES * StageLayout<GRU_BN>::kBytes>()));
+  TCK(cudaFuncSetAttribute(tc_gemm_kernel<DENSE_BN, DENSE_STAGES, DENSE_STAGES3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)dense_smem_bytes<DENSE_BN, DENSE_STAGES, DENSE_STAGES3>()));
+  TCK(cudaFuncSetAttribute(tc_gemm_kernel<SMALL_BN, SMALL_STAGES, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)dense_smem_bytes<SMALL_BN, SMALL_STAGES, 0>()));
   return PNB_OK;
 }
 
 void tc_release(pnb_engine *e) {
   pnb_tc_state *t = e->tc;
   if (!t) return;
-  void *ptrs[] = {t->fc_all, t->c1_all, t->c2_h, t->w_conv1, t->w_conv2, t->w_gb, t->w_rb, t->bias_pad, t->cnt};
+  void *ptrs[] = {t->fc_all, t->c1_all, t->c2_h, t->w_conv1, t->w_conv2, t->w_gb, t->w_rb, t->bias_pad, t->cnt, t->wide};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 5; i++) {
     if (t->h_all[i]) cudaFree(t->h_all[i]);
@@ -1029,8 +1138,9 @@ int tc_reset(pnb_engine *e) {
   if (!t) return PNB_OK;
   const size_t S = e->S;
   const size_t Fm = e->Fmax;
-  TCK(cudaMemset(t->fc_all, 0, 2 * (Fm + 4) * S * 128 * 2));
-  TCK(cudaMemset(t->c1_all, 0, 2 * (Fm + 2) * S * 512 * 2));
+  TCK(cudaMemset(t->fc_all, 0, kConvTerms * (Fm + 4) * S * 128 * 2));
+  TCK(cudaMemset(t->c1_all, 0, kConvTerms * (Fm + 2) * S * 512 * 2));
+  TCK(cudaMemset(t->wide, 0, sizeof(int)));
   TCK(cudaMemset(t->c2_h, 0, 2 * Fm * S * 512 * 2));
   for (int i = 0; i < 5; i++) TCK(cudaMemset(t->h_all[i], 0, 2 * (Fm + 1) * S * e->gru[i].H * 2));
   TCK(cudaMemset(t->cnt, 0, (size_t)5 * t->tiles_mp * sizeof(unsigned)));
@@ -1039,40 +1149,63 @@ int tc_reset(pnb_engine *e) {
 
 // One stream's conv input history (the last 4 fc outputs, the last 2 conv1 outputs; oldest first) as fp32, for
 // pnb_get_state / pnb_set_state.  Between calls the history sits in hop slots 0..3 / 0..1 as two bf16 terms.
-int tc_get_stream_hist(pnb_engine *e, int s, float *fc_hist, float *c1_hist) {
+int tc_get_stream_hist(pnb_engine *e, int s, float *fc_hist, float *c1_hist, unsigned short *fc_terms, unsigned short *c1_terms) {
   pnb_tc_state *t = e->tc;
   const size_t S = e->S, Fm = e->Fmax;
-  std::vector<__nv_bfloat16> a(128), b(128), c(512), d(512);
-  for (int i = 0; i < 4; i++) {
-    const __nv_bfloat16 *p0 = t->fc_all + ((size_t)i * S + s) * 128;
-    TCK(cudaMemcpy(a.data(), p0, 128 * 2, cudaMemcpyDeviceToHost));
-    TCK(cudaMemcpy(b.data(), p0 + (Fm + 4) * S * 128, 128 * 2, cudaMemcpyDeviceToHost));
-    for (int k = 0; k < 128; k++) fc_hist[i * 128 + k] = __bfloat162float(a[k]) + __bfloat162float(b[k]);
-  }
-  for (int i = 0; i < 2; i++) {
-    const __nv_bfloat16 *p0 = t->c1_all + ((size_t)i * S + s) * 512;
-    TCK(cudaMemcpy(c.data(), p0, 512 * 2, cudaMemcpyDeviceToHost));
-    TCK(cudaMemcpy(d.data(), p0 + (Fm + 2) * S * 512, 512 * 2, cudaMemcpyDeviceToHost));
-    for (int k = 0; k < 512; k++) c1_hist[i * 512 + k] = __bfloat162float(c[k]) + __bfloat162float(d[k]);
-  }
+  static_assert(sizeof(__nv_bfloat16) == sizeof(unsigned short), "raw bf16 terms travel as 16-bit words");
+  auto get = [&](const __nv_bfloat16 *base, size_t plane, int slots, int width, float *sum, unsigned short *terms) -> cudaError_t {
+    for (int i = 0; i < slots; i++) {
+      for (int k = 0; k < width; k++) sum[i * width + k] = 0.f;
+      for (int tm = kConvTerms - 1; tm >= 0; tm--) {  // smallest term first: the fp32 sum is then exact up to its last bit
+        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(terms + ((size_t)tm * slots + i) * width);
+        cudaError_t r = cudaMemcpy(dst, base + (size_t)tm * plane + ((size_t)i * S + s) * width, (size_t)width * 2, cudaMemcpyDeviceToHost);
+        if (r != cudaSuccess) return r;
+        for (int k = 0; k < width; k++) sum[i * width + k] += __bfloat162float(dst[k]);
+      }
+    }
+    return cudaSuccess;
+  };
+  TCK(get(t->fc_all, (Fm + 4) * S * 128, 4, 128, fc_hist, fc_terms));
+  TCK(get(t->c1_all, (Fm + 2) * S * 512, 2, 512, c1_hist, c1_terms));
   return PNB_OK;
 }
-// h: the five GRU states of the stream, concatenated (4 x 512 + 128), already stored as fp32 by the caller
-int tc_set_stream_hist(pnb_engine *e, int s, const float *fc_hist, const float *c1_hist, const float *h) {
+// h: the five GRU states of the stream, concatenated (4 x 512 + 128), already stored as fp32 by the caller.
+// fc_terms / c1_terms (from a tensor-mode engine) are restored verbatim; without them the fp32 values are split.
+int tc_set_stream_hist(pnb_engine *e, int s, const float *fc_hist, const float *c1_hist, const float *h,
+                       const unsigned short *fc_terms, const unsigned short *c1_terms) {
   pnb_tc_state *t = e->tc;
   const size_t S = e->S, Fm = e->Fmax;
-  auto put_b2 = [&](const float *v, int n, __nv_bfloat16 *p0, size_t term_stride) -> cudaError_t {
-    std::vector<__nv_bfloat16> a(n), b(n);
-    for (int k = 0; k < n; k++) {
-      a[k] = __float2bfloat16_rn(v[k]);
-      b[k] = __float2bfloat16_rn(v[k] - __bfloat162float(a[k]));
-    }
-    cudaError_t r = cudaMemcpy(p0, a.data(), n * 2, cudaMemcpyHostToDevice);
-    if (r != cudaSuccess) return r;
-    return cudaMemcpy(p0 + term_stride, b.data(), n * 2, cudaMemcpyHostToDevice);
+  auto put = [&](__nv_bfloat16 *base, size_t plane, int slots, int width, const float *sum, const unsigned short *terms) -> cudaError_t {
+    std::vector<__nv_bfloat16> buf(width);
+    for (int i = 0; i < slots; i++)
+      for (int tm = 0; tm < kConvTerms; tm++) {
+        for (int k = 0; k < width; k++) {
+          if (terms) {
+            buf[k] = reinterpret_cast<const __nv_bfloat16 *>(terms + ((size_t)tm * slots + i) * width)[k];
+          } else {
+            float r = sum[i * width + k];
+            __nv_bfloat16 b = __float2bfloat16_rn(r);
+            for (int q = 0; q < tm; q++) { r -= __bfloat162float(b); b = __float2bfloat16_rn(r); }
+            buf[k] = b;
+          }
+        }
+        cudaError_t r = cudaMemcpy(base + (size_t)tm * plane + ((size_t)i * S + s) * width, buf.data(), (size_t)width * 2, cudaMemcpyHostToDevice);
+        if (r != cudaSuccess) return r;
+      }
+    return cudaSuccess;
   };
-  for (int i = 0; i < 4; i++) TCK(put_b2(fc_hist + i * 128, 128, t->fc_all + ((size_t)i * S + s) * 128, (Fm + 4) * S * 128));
-  for (int i = 0; i < 2; i++) TCK(put_b2(c1_hist + i * 512, 512, t->c1_all + ((size_t)i * S + s) * 512, (Fm + 2) * S * 512));
+  TCK(put(t->fc_all, (Fm + 4) * S * 128, 4, 128, fc_hist, fc_terms));
+  TCK(put(t->c1_all, (Fm + 2) * S * 512, 2, 512, c1_hist, c1_terms));
+  {  // a loud history keeps the conv layers in their three-term mode for the next call, as it would have at the source
+    bool big = false;
+    for (int k = 0; k < 4 * 128; k++) big |= !(fc_hist[k] < kWideThreshold);
+    if (big) {
+      int w = 0;
+      TCK(cudaMemcpy(&w, t->wide, sizeof w, cudaMemcpyDeviceToHost));
+      w |= 1;
+      TCK(cudaMemcpy(t->wide, &w, sizeof w, cudaMemcpyHostToDevice));
+    }
+  }
   size_t off = 0;
   for (int li = 0; li < 5; li++) {
     const size_t H = e->gru[li].H;
@@ -1090,11 +1223,11 @@ int tc_set_stream_hist(pnb_engine *e, int s, const float *fc_hist, const float *
   return PNB_OK;
 }
 
-int tc_launches_per_call(const pnb_engine *) { return 7; }  // fc, conv1, conv2, GRU chain, fc_gb, fc_rb, carry
+int tc_launches_per_chunk(const pnb_engine *) { return 6; }  // fc, conv1, conv2, GRU chain, fc_gb, fc_rb (+ 1 carry per call)
 
 template <typename K, typename A>
 static int tc_launch(pnb_engine *e, K kernel, const A &a, int pairs, size_t smem, cudaStream_t st) {
-  int clusters = pairs < e->sm_count / 2 ? pairs : e->sm_count / 2;
+  int clusters = pairs < e->tc_sms / 2 ? pairs : e->tc_sms / 2;  // persistent: one CTA per SM of the network's share
   if (clusters < 1) clusters = 1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -1110,14 +1243,14 @@ static int tc_launch(pnb_engine *e, K kernel, const A &a, int pairs, size_t smem
   TCK(cudaLaunchKernelEx(&cfg, kernel, a));
   return PNB_OK;
 }
-template <int BN, int STAGES>
+template <int BN, int ST2, int ST3>
 static int tc_launch_dense(pnb_engine *e, TcArgs &a, int rows, int tiles_n, cudaStream_t st) {
   a.M = rows;
   a.tiles_m = (rows + TM - 1) / TM;
   a.tiles_n = tiles_n;
   a.status = e->d_status;
   const int pairs = ((a.tiles_m + 1) / 2) * a.tiles_n;
-  return tc_launch(e, tc_gemm_kernel<BN, STAGES>, a, pairs, tc_smem_bytes<STAGES, StageLayout<BN>::kBytes>(), st);
+  return tc_launch(e, tc_gemm_kernel<BN, ST2, ST3>, a, pairs, dense_smem_bytes<BN, ST2, ST3>(), st);
 }
 
 static TcSeg mkseg(int a_map, int b_map, int K, int a_k0, int b_k0, int a_row0, int a_term_rows) {
@@ -1127,62 +1260,64 @@ static TcSeg mkseg(int a_map, int b_map, int K, int a_k0, int b_k0, int a_row0, 
   return s;
 }
 
-// The non-recurrent front of the network for all F hops of the call at once (rnn.cpp:50-52 on F S rows):
-// fc -> conv1 -> conv2.  Returns the number of launches or a negative error.
-int tc_begin_call(pnb_engine *e, int F, cudaStream_t st) {
+// ---- the network of hops [h0, h0 + n) of a call of F hops, in three phases -----------------------------------
+// The non-recurrent front (rnn.cpp:50-52 on n S rows): fc -> conv1 -> conv2.  Hop t of the call lives in slot t of the
+// per-call buffers, so a phase can be run for any hop range once the earlier hops' phases are enqueued.
+// Returns the number of launches or a negative error.
+int tc_front(pnb_engine *e, int h0, int n, int F, cudaStream_t st) {
   pnb_tc_state *t = e->tc;
   const int S = e->S, Fm = e->Fmax;
   const float *tbl = e->tansig();
-  const int rows = F * S;
-  int n = 0, rc;
-  // fc (fp32 FMA) for every hop -> bf16 terms at slots 4 .. F+3
+  const int rows = n * S;
+  int nl = 0, rc;
+  // fc (fp32 FMA) -> bf16 terms at slots 4 + h0 ..
   {
     ProfScope ps(e, PNB_K_TC_AUX, st);
-    fc_split_kernel<<<(rows + 3) / 4, 128, 0, st>>>(e->d_feat, e->fc.W, e->fc.b, t->fc_all + (size_t)4 * S * 128, rows,
-                                                    (size_t)(Fm + 4) * S);
-    n++;
+    fc_split_kernel<<<(rows + 3) / 4, 128, 0, st>>>(e->d_feat + (size_t)h0 * S * kFeat, e->fc.W, e->fc.b,
+                                                    t->fc_all + (size_t)(4 + h0) * S * 128, rows, (size_t)(Fm + 4) * S, t->wide);
+    nl++;
   }
   TcArgs a;
-  // conv1: tap q of hop t reads fc slot t + q (oldest first, nnet.cpp:182-200); output -> c1 slots 2 .. F+1
+  // conv1: tap q of hop t reads fc slot t + q (oldest first, nnet.cpp:182-200); output -> c1 slots 2 + t
   memset(&a, 0, sizeof a);
   a.maps[0] = t->m_fc_all;
   a.maps[1] = t->m_wconv1;
-  for (int q = 0; q < 5; q++) a.seg[q] = mkseg(0, 1, 128, 0, q * 128, q * S, (Fm + 4) * S);
+  for (int q = 0; q < 5; q++) a.seg[q] = mkseg(0, 1, 128, 0, q * 128, (h0 + q) * S, (Fm + 4) * S);
   a.n_seg = 5; a.b_term_rows = 512; a.fmt = 1; a.out_scale = 1.f; a.tansig = tbl;
   a.bias = t->bias_pad; a.act = PNB_ACT_RELU; a.N = 512;
-  a.out_b = t->c1_all; a.out_row0 = 2 * S; a.out_plane_rows = (Fm + 2) * S;
+  a.out_b = t->c1_all; a.out_row0 = (2 + h0) * S; a.out_plane_rows = (Fm + 2) * S; a.out_terms = kConvTerms; a.wide = t->wide;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    if ((rc = tc_launch_dense<DENSE_BN, DENSE_STAGES>(e, a, rows, 512 / DENSE_BN, st))) return rc;
-    n++;
+    if ((rc = tc_launch_dense<DENSE_BN, DENSE_STAGES, DENSE_STAGES3>(e, a, rows, 512 / DENSE_BN, st))) return rc;
+    nl++;
   }
-  // conv2: three taps -> tanh -> fp16 terms for every hop (gru1 / gru_rb / fc_gb inputs); fp32 copy of the last hop
+  // conv2: three taps -> tanh -> fp16 terms (gru1 / gru_rb / fc_gb inputs); fp32 copy of the call's last hop
   memset(&a, 0, sizeof a);
   a.maps[0] = t->m_c1_all;
   a.maps[1] = t->m_wconv2;
-  for (int q = 0; q < 3; q++) a.seg[q] = mkseg(0, 1, 512, 0, q * 512, q * S, (Fm + 2) * S);
+  for (int q = 0; q < 3; q++) a.seg[q] = mkseg(0, 1, 512, 0, q * 512, (h0 + q) * S, (Fm + 2) * S);
   a.n_seg = 3; a.b_term_rows = 512; a.fmt = 1; a.out_scale = 1.f; a.tansig = tbl;
   a.bias = t->bias_pad + 512; a.act = PNB_ACT_TANH; a.N = 512;
-  a.out_f32 = e->c2; a.ldc = 512; a.f32_row0 = (F - 1) * S;
-  a.out_h = t->c2_h; a.out_row0 = 0; a.out_plane_rows = Fm * S;
+  if (h0 + n == F) { a.out_f32 = e->c2; a.ldc = 512; a.f32_row0 = (n - 1) * S; }
+  a.out_h = t->c2_h; a.out_row0 = h0 * S; a.out_plane_rows = Fm * S; a.wide = t->wide;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    if ((rc = tc_launch_dense<DENSE_BN, DENSE_STAGES>(e, a, rows, 512 / DENSE_BN, st))) return rc;
-    n++;
+    if ((rc = tc_launch_dense<DENSE_BN, DENSE_STAGES, DENSE_STAGES3>(e, a, rows, 512 / DENSE_BN, st))) return rc;
+    nl++;
   }
-  return n;
+  return nl;
 }
 
-// The recurrent part of all F hops: five GRUs per hop (rnn.cpp:58-71) in one persistent launch.
-// State slot t holds the state BEFORE hop t.
-int tc_gru_chain(pnb_engine *e, int F, cudaStream_t st) {
+// The recurrent part: five GRUs per hop (rnn.cpp:58-71) in one persistent launch.  State slot t holds the state
+// BEFORE hop t of the call; the fp32 state ping-pongs by hop, starting from e->par (the call's first hop).
+int tc_gru_chain(pnb_engine *e, int h0, int n, cudaStream_t st) {
   pnb_tc_state *t = e->tc;
   const int S = e->S, Fm = e->Fmax;
   ChainArgs a;
   memset(&a, 0, sizeof a);
   a.maps[0] = t->m_c2;
   for (int i = 0; i < 5; i++) { a.maps[1 + i] = t->m_h[i]; a.maps[6 + i] = t->m_w[i]; a.maps[11 + i] = t->m_u[i]; }
-  a.S = S; a.F = F; a.tiles_mp = t->tiles_mp; a.cnt = t->cnt; a.tansig = e->tansig();
+  a.S = S; a.F = n; a.t0 = h0; a.tiles_mp = t->tiles_mp; a.cnt = t->cnt; a.tansig = e->tansig();
   const int c2_terms = Fm * S, h_terms = (Fm + 1) * S;
   int unit0 = 0;
   for (int li = 0; li < 5; li++) {
@@ -1212,79 +1347,76 @@ int tc_gru_chain(pnb_engine *e, int F, cudaStream_t st) {
   a.units_per_hop = unit0;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    int rc = tc_launch(e, gru_chain_kernel, a, F * unit0, tc_smem_bytes<GRU_STAGES, StageLayout<GRU_BN>::kBytes>(), st);
+    int rc = tc_launch(e, gru_chain_kernel, a, n * unit0, tc_smem_bytes<GRU_STAGES, GRU_STAGES * StageLayout<GRU_BN>::kBytes>(), st);
     if (rc) return rc;
   }
-  if (F & 1)
-    for (int li = 0; li < 5; li++) e->par[li] ^= 1;
   return 1;
 }
 
-// The two 34-wide output layers for all F hops at once (rnn.cpp:73-80; N padded to 48, fp16 two-term split,
-// sigmoid epilogue), then the carry of the last slots to the front for the next call.
-int tc_end_call(pnb_engine *e, int F, cudaStream_t st) {
+// The two 34-wide output layers (rnn.cpp:73-80; N padded to 48, fp16 two-term split, sigmoid epilogue).
+int tc_out(pnb_engine *e, int h0, int n, cudaStream_t st) {
   pnb_tc_state *t = e->tc;
   const int S = e->S, Fm = e->Fmax;
   const float *tbl = e->tansig();
-  const int rows = F * S, h_terms = (Fm + 1) * S;
-  int n = 0, rc;
+  const int rows = n * S, h_terms = (Fm + 1) * S;
+  int nl = 0, rc;
   TcArgs a;
   memset(&a, 0, sizeof a);
   a.maps[0] = t->m_c2;
   for (int q = 0; q < 4; q++) a.maps[1 + q] = t->m_h[q];
   a.maps[5] = t->m_wgb;
-  a.seg[0] = mkseg(0, 5, 512, 0, 0, 0, Fm * S);
-  for (int q = 1; q < 5; q++) a.seg[q] = mkseg(q, 5, 512, 0, q * 512, S, h_terms);  // state after hop t = slot t+1
+  a.seg[0] = mkseg(0, 5, 512, 0, 0, h0 * S, Fm * S);
+  for (int q = 1; q < 5; q++) a.seg[q] = mkseg(q, 5, 512, 0, q * 512, (h0 + 1) * S, h_terms);  // state after hop t = slot t+1
   a.n_seg = 5; a.b_term_rows = SMALL_BN; a.fmt = 0; a.out_scale = t->scale_gb; a.tansig = tbl;
-  a.bias = t->bias_pad + 1024; a.act = PNB_ACT_SIGMOID; a.N = 34; a.ldc = 68; a.out_f32 = e->d_gr;
+  a.bias = t->bias_pad + 1024; a.act = PNB_ACT_SIGMOID; a.N = 34; a.ldc = 68; a.out_f32 = e->d_gr + (size_t)h0 * S * 68;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    if ((rc = tc_launch_dense<SMALL_BN, SMALL_STAGES>(e, a, rows, 1, st))) return rc;
-    n++;
+    if ((rc = tc_launch_dense<SMALL_BN, SMALL_STAGES, 0>(e, a, rows, 1, st))) return rc;
+    nl++;
   }
   memset(&a, 0, sizeof a);
   a.maps[0] = t->m_h[4];
   a.maps[1] = t->m_wrb;
-  a.seg[0] = mkseg(0, 1, 128, 0, 0, S, h_terms);
+  a.seg[0] = mkseg(0, 1, 128, 0, 0, (h0 + 1) * S, h_terms);
   a.n_seg = 1; a.b_term_rows = SMALL_BN; a.fmt = 0; a.out_scale = t->scale_rb; a.tansig = tbl;
-  a.bias = t->bias_pad + 1072; a.act = PNB_ACT_SIGMOID; a.N = 34; a.ldc = 68; a.out_f32 = e->d_gr + 34;
+  a.bias = t->bias_pad + 1072; a.act = PNB_ACT_SIGMOID; a.N = 34; a.ldc = 68; a.out_f32 = e->d_gr + (size_t)h0 * S * 68 + 34;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
-    if ((rc = tc_launch_dense<SMALL_BN, SMALL_STAGES>(e, a, rows, 1, st))) return rc;
-    n++;
+    if ((rc = tc_launch_dense<SMALL_BN, SMALL_STAGES, 0>(e, a, rows, 1, st))) return rc;
+    nl++;
   }
-  // carry: the last 4 fc / 2 conv1 hop slots and the last state slot move to the front; counters back to zero.
-  // Source and destination ranges are disjoint when F >= 4; shorter calls copy slot by slot, ascending.
+  return nl;
+}
+
+// End of a call of F hops: the last 4 fc / 2 conv1 hop slots and the last state slot move to the front, the chain's
+// dependency counters return to zero (one launch), and the fp32 state parity advances by F.
+int tc_carry(pnb_engine *e, int F, cudaStream_t st) {
+  pnb_tc_state *t = e->tc;
+  const int S = e->S, Fm = e->Fmax;
+  const int h_terms = (Fm + 1) * S;
   CarryArgs ca;
   memset(&ca, 0, sizeof ca);
-  ca.cnt = t->cnt; ca.n_cnt = 5 * t->tiles_mp;
+  ca.cnt = t->cnt; ca.n_cnt = 5 * t->tiles_mp; ca.wide = t->wide;
   int ns = 0;
-  const bool disjoint = F >= 4;
-  for (int tm = 0; tm < 2; tm++) {
+  for (int tm = 0; tm < kConvTerms; tm++) {
     __nv_bfloat16 *bf = t->fc_all + (size_t)tm * (Fm + 4) * S * 128;
     __nv_bfloat16 *bc = t->c1_all + (size_t)tm * (Fm + 2) * S * 512;
-    if (disjoint) {
-      ca.seg[ns++] = CarrySeg{reinterpret_cast<uint4 *>(bf), reinterpret_cast<const uint4 *>(bf + (size_t)F * S * 128), (size_t)4 * S * 128 * 2 / 16};
-      ca.seg[ns++] = CarrySeg{reinterpret_cast<uint4 *>(bc), reinterpret_cast<const uint4 *>(bc + (size_t)F * S * 512), (size_t)2 * S * 512 * 2 / 16};
-    } else {
-      for (int i = 0; i < 4; i++)
-        TCK(cudaMemcpyAsync(bf + (size_t)i * S * 128, bf + (size_t)(F + i) * S * 128, (size_t)S * 128 * 2, cudaMemcpyDeviceToDevice, st));
-      for (int i = 0; i < 2; i++)
-        TCK(cudaMemcpyAsync(bc + (size_t)i * S * 512, bc + (size_t)(F + i) * S * 512, (size_t)S * 512 * 2, cudaMemcpyDeviceToDevice, st));
-    }
+    ca.seg[ns++] = CarrySeg{reinterpret_cast<uint4 *>(bf), (size_t)S * 128 * 2 / 16, 4, F};
+    ca.seg[ns++] = CarrySeg{reinterpret_cast<uint4 *>(bc), (size_t)S * 512 * 2 / 16, 2, F};
   }
   for (int li = 0; li < 5; li++) {
     const size_t H = e->gru[li].H;
     for (int tm = 0; tm < 2; tm++) {
       __half *base = t->h_all[li] + (size_t)tm * h_terms * H;
-      ca.seg[ns++] = CarrySeg{reinterpret_cast<uint4 *>(base), reinterpret_cast<const uint4 *>(base + (size_t)F * S * H), (size_t)S * H * 2 / 16};
+      ca.seg[ns++] = CarrySeg{reinterpret_cast<uint4 *>(base), (size_t)S * H * 2 / 16, 1, F};
     }
   }
   ca.n_seg = ns;
   {
     ProfScope ps(e, PNB_K_TC_AUX, st);
-    tc_carry_kernel<<<2 * e->sm_count, 256, 0, st>>>(ca);
-    n++;
+    tc_carry_kernel<<<2 * e->tc_sms, 256, 0, st>>>(ca);
   }
-  return n;
+  if (F & 1)
+    for (int li = 0; li < 5; li++) e->par[li] ^= 1;
+  return 1;
 }

@@ -15,7 +15,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <unistd.h>
 
 #include "../../include/percepnet_b200.h"
 
@@ -31,19 +30,8 @@ extern const RNNModel percepnet_model_orig __attribute__((weak));
 // binary weight file of pnb_model_load_blob, so a host can run without compiling nnet_data.cpp.
 RNNModel *rnnoise_model_from_file(FILE *f) {
   if (!f) return NULL;
-  // the C-ABI loader takes a path; copy the stream to a temporary file so that any FILE* works
-  char tmpl[] = "/tmp/pnb_model_XXXXXX";
-  int fd = mkstemp(tmpl);
-  if (fd < 0) return NULL;
-  FILE *t = fdopen(fd, "wb");
-  char buf[1 << 16];
-  size_t n;
-  while ((n = fread(buf, 1, sizeof buf, f)) > 0) fwrite(buf, 1, n, t);
-  fclose(t);
   pnb_model *m = NULL;
-  int rc = pnb_model_load_blob(tmpl, &m);
-  remove(tmpl);
-  if (rc != PNB_OK) {
+  if (pnb_model_load_stream(f, &m) != PNB_OK) {
     fprintf(stderr, "rnnoise_model_from_file: %s\n", pnb_last_error());
     return NULL;
   }
@@ -65,7 +53,9 @@ int rnnoise_init(DenoiseState *st, RNNModel *model) {
   // outside tansig_approx's defined range
   const char *nn = getenv("PNB_SHIM_NN");
   const unsigned flags = (nn && strcmp(nn, "tensor") == 0) ? PNB_NN_TENSOR : PNB_NN_FP32;
-  int rc = pnb_create(&st->engine, 1, 1, reinterpret_cast<const pnb_model *>(m), flags, 0);
+  // PNB_DEVICE=<ordinal> picks the GPU; otherwise the calling thread's current CUDA device (device 0 in a fresh process)
+  const char *dv = getenv("PNB_DEVICE");
+  int rc = pnb_create(&st->engine, 1, 1, reinterpret_cast<const pnb_model *>(m), flags, dv ? atoi(dv) : -1);
   if (rc != PNB_OK) {
     fprintf(stderr, "rnnoise_init: %s\n", pnb_last_error());
     return rc;
@@ -76,10 +66,10 @@ int rnnoise_init(DenoiseState *st, RNNModel *model) {
 DenoiseState *rnnoise_create(RNNModel *model) {
   DenoiseState *st = (DenoiseState *)malloc(rnnoise_get_size());
   if (!st) return NULL;
-  if (rnnoise_init(st, model) != 0) {  // no CPU fallback: fail loudly
+  if (rnnoise_init(st, model) != 0) {  // no CPU fallback: the caller gets NULL and the reason on stderr
     free(st);
-    fprintf(stderr, "rnnoise_create: cannot create the CUDA engine\n");
-    abort();
+    fprintf(stderr, "rnnoise_create: cannot create the CUDA engine (there is no CPU path)\n");
+    return NULL;
   }
   return st;
 }
@@ -91,6 +81,10 @@ void rnnoise_destroy(DenoiseState *st) {
 }
 
 float rnnoise_process_frame(DenoiseState *st, float *out, const float *in, FILE *f_feature) {
+  if (!st || !st->engine) {
+    fprintf(stderr, "rnnoise_process_frame: no engine (rnnoise_create failed?)\n");
+    abort();  // the reference would dereference NULL here; a frame cannot be skipped silently
+  }
   int rc = pnb_process_host_f32(st->engine, in, PNB_FRAME, out, PNB_FRAME, 1, st->gr);
   if (rc != PNB_OK) {
     fprintf(stderr, "rnnoise_process_frame: %s\n", pnb_last_error());

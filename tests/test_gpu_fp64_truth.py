@@ -61,6 +61,33 @@ def test_tensor_path_vs_double_precision(api, oracle, model0, scale):
     assert e_pair < GR_RTOL
 
 
+def test_error_against_truth_over_amplitude_scales(api, oracle, model0, capsys):
+    """Report (and bound) how the tensor path's and the reference's distance from the double-precision network move with
+    the input amplitude; also prints the largest fc output, the quantity the conv layers' operand precision hangs on."""
+    from percepnet_b200.synth import synth_pcm
+    F = 12
+    base = synth_pcm(6, F, seed=99)
+    rows = []
+    for scale in (1.0, 4.0, 16.0, 64.0, 256.0, 4096.0, 32768.0):
+        x = (base * np.float32(scale)).astype(np.float32)
+        gr32, g64, mp = _truth(oracle, model0, x)
+        if not (mp < DOMAIN).all():
+            continue
+        _, _, taps = _oracle_run(oracle, model0, x[:1])
+        feats = np.stack([t.np("features") for t in taps[0]])
+        W, b = model0.arrays["fc_weights"], model0.arrays["fc_bias"]
+        fc = np.maximum(feats @ W.reshape(70, 128) + b, 0)
+        eng = api.Engine(x.shape[0], F, model0, api.NN_TENSOR)
+        _, gr = eng.process(x, want_gr=True)
+        eng.close()
+        den = np.maximum(np.abs(g64), 1e-6)
+        rows.append((scale, (np.abs(gr - g64) / den).max(), (np.abs(gr32 - g64) / den).max(), float(fc.max())))
+    with capsys.disabled():
+        for r in rows:
+            print(f"  scale {r[0]:>7g}: tensor {r[1]:.2e}  reference {r[2]:.2e}  max fc out {r[3]:.3g}")
+    assert all(r[1] < GR_RTOL for r in rows)
+
+
 def test_domain_flag_is_raised_outside_the_tanh_domain(api, oracle, model0):
     """Input that drives a pre-activation past 8.6e7 (full-scale periodic signals at int16 scale: feature 69, the raw
     pitch xcorr, reaches 1e10): the tensor engine reports PNB_ERR_DOMAIN; the fp32 engine follows the reference."""

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 def _migrate(api, model, flags_a, flags_b, scale):
     x = _inputs(scale, 13, n_synth=5)[:5]
-    other = _inputs(scale, 4, n_synth=3)[:3] * np.float32(0.5)
+    other = _inputs(scale, 6, n_synth=3)[:3] * np.float32(0.5)
     a = api.Engine(5, 7, model, flags_a)
     a.process(x[:, :7 * 480])
     blob = a.get_state(2)
