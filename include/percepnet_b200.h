@@ -185,6 +185,9 @@ enum {
 };
 int pnb_profile_enable(pnb_engine *e, int on);
 int pnb_profile_read(pnb_engine *e, double *ms, long long *counts);
+/* The same records as a timeline: launch i of the profiled calls as (class, start ms, end ms) relative to the first
+ * launch, in launch order (launches on different internal streams overlap).  Returns the count written (<= cap). */
+int pnb_profile_timeline(pnb_engine *e, int *cls, double *t0_ms, double *t1_ms, int cap);
 const char *pnb_kernel_class_name(int cls);
 
 /* Number of kernels this library has launched on behalf of e since creation. */
@@ -199,6 +202,9 @@ int pnb_launches_per_call(const pnb_engine *e, int n_frames);
  * after the other on all SMs.  Environment: PNB_OVERLAP=0 disables, =2 forces it for small batches; PNB_NET_SMS,
  * PNB_CHUNK tune it (read by pnb_create).  Results do not depend on the schedule. */
 int pnb_overlap_info(const pnb_engine *e, int *net_sms, int *dsp_sms, int *chunk_hops);
+/* on = 0: run every call serially on all SMs (e.g. to time one kernel class alone); on = 1: back to the partition the
+ * engine was created with.  Waits for the engine to be idle. */
+int pnb_set_overlap(pnb_engine *e, int on);
 int pnb_n_streams(const pnb_engine *e);
 int pnb_max_frames(const pnb_engine *e);
 const char *pnb_last_error(void);

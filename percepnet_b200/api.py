@@ -70,9 +70,11 @@ def load_library() -> C.CDLL:
     L.pnb_launches_per_call.argtypes = [vp, i]
     L.pnb_n_streams.argtypes = [vp]
     L.pnb_overlap_info.argtypes = [vp, vp, vp, vp]
+    L.pnb_set_overlap.argtypes = [vp, i]
     L.pnb_max_frames.argtypes = [vp]
     L.pnb_profile_enable.argtypes = [vp, i]
     L.pnb_profile_read.argtypes = [vp, vp, vp]
+    L.pnb_profile_timeline.argtypes = [vp, vp, vp, vp, i]
     L.pnb_kernel_class_name.argtypes = [i]
     L.pnb_kernel_class_name.restype = C.c_char_p
     L.pnb_last_error.restype = C.c_char_p
@@ -84,7 +86,7 @@ def load_library() -> C.CDLL:
 EXPORTS = ("pnb_create", "pnb_destroy", "pnb_reset", "pnb_process_host_f32", "pnb_process_host_i16",
            "pnb_model_load_blob", "pnb_model_load_stream", "pnb_model_free", "pnb_train_records_host", "pnb_train_records_device", "pnb_submit_train_records", "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_wait", "pnb_check",
            "pnb_read_tap", "pnb_state_size", "pnb_get_state", "pnb_set_state", "pnb_pitch_only_device", "pnb_pitch_only_host", "pnb_launch_count",
-           "pnb_launches_per_call", "pnb_profile_enable", "pnb_profile_read", "pnb_kernel_class_name", "pnb_n_streams", "pnb_overlap_info", "pnb_max_frames", "pnb_last_error", "pnb_version")
+           "pnb_launches_per_call", "pnb_profile_enable", "pnb_profile_read", "pnb_profile_timeline", "pnb_kernel_class_name", "pnb_n_streams", "pnb_overlap_info", "pnb_set_overlap", "pnb_max_frames", "pnb_last_error", "pnb_version")
 
 
 def pitch_only_device(d_buf: int, stride: int, n_units: int, d_period: int, d_corr: int, d_gain: int, d_lag: int = 0,
@@ -264,6 +266,19 @@ class Engine:
         cnt = (C.c_longlong * n)()
         self._ck(self.L.pnb_profile_read(self.h, ms, cnt), "pnb_profile_read")
         return {self.L.pnb_kernel_class_name(k).decode(): (ms[k], int(cnt[k])) for k in range(n) if cnt[k]}
+
+    def profile_timeline(self, cap: int = 4096):
+        """[(class name, start ms, end ms)] of every launch since profiling was enabled / last read."""
+        cls = (C.c_int * cap)()
+        t0 = (C.c_double * cap)()
+        t1 = (C.c_double * cap)()
+        n = self.L.pnb_profile_timeline(self.h, cls, t0, t1, cap)
+        if n < 0:
+            self._ck(n, "pnb_profile_timeline")
+        return [(self.L.pnb_kernel_class_name(cls[k]).decode(), t0[k], t1[k]) for k in range(n)]
+
+    def set_overlap(self, on: bool):
+        self._ck(self.L.pnb_set_overlap(self.h, 1 if on else 0), "pnb_set_overlap")
 
     def overlap_info(self) -> dict:
         a, b, c = C.c_int(), C.c_int(), C.c_int()

@@ -97,8 +97,24 @@ def build_timing() -> str:
     return out
 
 
+def build_chain_timing() -> str:
+    """libpercepnet_b200_chain_timing.so: the library with -DPNB_CHAIN_TIMING in pnb_nn_tc.cu (per-role cycle accounting
+    of gru_chain_kernel, read by tools/chain_roles.py).  Debug aid, not loaded by the product."""
+    build()
+    nvcc = _nvcc()
+    obj = os.path.join(OBJ, "pnb_nn_tc_timing.o")
+    out = os.path.join(HERE, "libpercepnet_b200_chain_timing.so")
+    subprocess.run([nvcc, *ARCH, *COMMON, "-DPNB_CHAIN_TIMING", "-c", os.path.join(CSRC, "pnb_nn_tc.cu"), "-o", obj],
+                   check=True, capture_output=True)
+    others = [os.path.join(OBJ, f.replace(".cu", ".o")) for f in SOURCES if f != "pnb_nn_tc.cu"]
+    subprocess.run([nvcc, *ARCH, "-shared", "-cudart", "static", "-o", out, obj, *others], check=True, capture_output=True)
+    return out
+
+
 if __name__ == "__main__":
-    if "--timing" in sys.argv:
+    if "--chain-timing" in sys.argv:
+        print(build_chain_timing())
+    elif "--timing" in sys.argv:
         print(build_timing())
     else:
         build(force="--force" in sys.argv, verbose=True)

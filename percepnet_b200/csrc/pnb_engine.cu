@@ -481,6 +481,27 @@ extern "C" int pnb_profile_read(pnb_engine *e, double *ms, long long *counts) {
   }
   return PNB_OK;
 }
+// Every launch of the profiled calls as (class, start, end) in ms relative to the first launch, in launch order;
+// consumes the pending records like pnb_profile_read.  Returns the number of records written (<= cap) or a negative error.
+extern "C" int pnb_profile_timeline(pnb_engine *e, int *cls, double *t0_ms, double *t1_ms, int cap) {
+  if (!e || !cls || !t0_ms || !t1_ms) return fail(PNB_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  int n = 0;
+  for (auto &r : e->prof_pending) {
+    if (n < cap) {
+      float a = 0.f, b = 0.f;
+      CK(cudaEventElapsedTime(&a, e->prof_pending[0].a, r.a));
+      CK(cudaEventElapsedTime(&b, e->prof_pending[0].a, r.b));
+      cls[n] = r.cls; t0_ms[n] = a; t1_ms[n] = b;
+      n++;
+    }
+    e->prof_pool.push_back(r.a);
+    e->prof_pool.push_back(r.b);
+  }
+  e->prof_pending.clear();
+  return n;
+}
 extern "C" const char *pnb_kernel_class_name(int cls) {
   static const char *names[PNB_NUM_KERNEL_CLASSES] = {"stage_in_kernel", "analysis_kernel", "fc_f32_kernel",
       "gemm_f32_kernel", "gru_gates_kernel", "synthesis_kernel", "slide_history_kernel", "tc_gemm_kernel", "tc_aux_kernel", "train_labels_kernel"};
@@ -637,12 +658,17 @@ static int process_device_enqueue(pnb_engine *e, const float *d_in, const short 
     CK(cudaEventRecord(e->ev_fork, st));
     CK(cudaStreamWaitEvent(sd, e->ev_fork, 0));
     CK(cudaStreamWaitEvent(sn, e->ev_fork, 0));
-    { ProfScope ps(e, PNB_K_STAGE_IN, sd); n += launch_stage_in(line, e->pcm_stride, d_in, d_in16, in_stride, S, F * kFrame, sd); }
     e->tc_sms = e->net_sms;
     int h0 = 0, p0 = 0, pn = 0;  // current chunk; previous chunk (start, length)
     for (int k = 0; k < C; k++) {
       const int nh = len[k];
+      {
+        ProfScope ps(e, PNB_K_STAGE_IN, sd);
+        n += launch_stage_in(line + (size_t)h0 * kFrame, e->pcm_stride, d_in ? d_in + (size_t)h0 * kFrame : nullptr,
+                             d_in16 ? d_in16 + (size_t)h0 * kFrame : nullptr, in_stride, S, nh * kFrame, sd);
+      }
       { ProfScope ps(e, PNB_K_ANALYSIS, sd); n += launch_analysis(analysis_args(e, h0, nh), sd); }
+      n += tc_fc(e, h0, nh, sd);  // CUDA-core work: with the DSP kernels
       CK(cudaEventRecord(e->ev_ana[k], sd));
       CK(cudaStreamWaitEvent(sn, e->ev_ana[k], 0));
       int q = tc_front(e, h0, nh, F, sn);
@@ -680,6 +706,7 @@ static int process_device_enqueue(pnb_engine *e, const float *d_in, const short 
     { ProfScope ps(e, PNB_K_ANALYSIS, st); n += launch_analysis(analysis_args(e, 0, F), st); }
     CK(cudaGetLastError());
     if (tensor) {
+      n += tc_fc(e, 0, F, st);
       int k = tc_front(e, 0, F, F, st);
       if (k < 0) return k;
       n += k;
@@ -1267,6 +1294,21 @@ extern "C" int pnb_launches_per_call(const pnb_engine *e, int n_frames) {
     return 1 + C * (2 + tc_launches_per_chunk(e)) + 1;  // stage_in + per chunk (analysis, network, synthesis) + carry
   }
   return 3 + 25 * n_frames;
+}
+// Runtime switch for the chunked overlap schedule (an engine created without it cannot turn it on): profiling a
+// kernel class alone on all SMs needs the serial schedule.
+extern "C" int pnb_set_overlap(pnb_engine *e, int on) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  if (!e->s_net) return on ? fail(PNB_ERR_ARG, "this engine was created without an SM partition") : PNB_OK;
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  if (on) {
+    if (e->net_sms == 0) { e->net_sms = e->saved_net_sms; }
+  } else if (e->net_sms) {
+    e->saved_net_sms = e->net_sms;
+    e->net_sms = 0;
+  }
+  return PNB_OK;
 }
 extern "C" int pnb_overlap_info(const pnb_engine *e, int *net_sms, int *dsp_sms, int *chunk_hops) {
   if (!e) return fail(PNB_ERR_ARG, "engine is NULL");

@@ -73,7 +73,7 @@ struct pnb_engine {
   // limit (it clocks down to ~1.4 GHz) while the DSP phase leaves that budget unused; side by side they even out.
   void *green_net = nullptr, *green_dsp = nullptr;  // CUgreenCtx
   cudaStream_t s_net = nullptr, s_dsp = nullptr;
-  int net_sms = 0, dsp_sms = 0, chunk = 8;
+  int net_sms = 0, dsp_sms = 0, chunk = 8, saved_net_sms = 0;
   cudaEvent_t ev_fork = nullptr, ev_join_net = nullptr, ev_join_dsp = nullptr;
   std::vector<cudaEvent_t> ev_ana, ev_net;
   int last_frames = 0;
@@ -103,6 +103,7 @@ int tc_prepare(pnb_engine *e, const pnb_model *model);
 void tc_release(pnb_engine *e);
 int tc_reset(pnb_engine *e);
 // the network of hops [h0, h0+n) of a call of F hops: hop-parallel front, the GRU chain, hop-parallel output layers
+int tc_fc(pnb_engine *e, int h0, int n, cudaStream_t st);
 int tc_front(pnb_engine *e, int h0, int n, int F, cudaStream_t st);
 int tc_gru_chain(pnb_engine *e, int h0, int n, cudaStream_t st);
 int tc_out(pnb_engine *e, int h0, int n, cudaStream_t st);

@@ -19,7 +19,7 @@
 //                    own layer at the previous hop), so the recurrence is a per-(layer, row-pair) counter that
 //                    the epilogue warps bump (release) and the TMA producer polls (acquire) -- no grid barrier,
 //                    no launch boundary between layers or hops.
-// Warp roles per CTA: warp 0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_64B boxes of 32 k into a 7-stage
+// Warp roles per CTA: warp 0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B boxes of 64 k into a 4-stage
 // ring; its own 128 activation rows and HALF of the weight rows of the tile), warp 1 (leader CTA) = MMA issuer,
 // warp 2 = TMEM allocator, warps 4-11 = epilogue (tcgen05.ld, one stream per thread).  Two accumulator buffers in
 // TMEM: the epilogue of tile i overlaps the MMAs of tile i+1.  The issue loops run warp-converged on uniform
@@ -48,7 +48,8 @@ using namespace pnb;
 namespace {
 
 constexpr int TM = 128;   // streams per CTA tile (UMMA M = 256 per pair)
-constexpr int BK = 32;    // k per pipeline stage: 64-byte rows, SWIZZLE_64B
+constexpr int BK = 64;    // k per pipeline stage: 128-byte rows, SWIZZLE_128B (64-byte rows made the TMA unit the pacing stage:
+                          // one L2 request per row, 448 request cycles per 576 MMA cycles)
 constexpr int HT = 64;    // hidden units per GRU tile
 constexpr int GRU_BN = 3 * HT;  // weight rows per GRU tile (z|r|n)
 // Epilogue warps per CTA: warp 4 + q + 4 k reads TMEM lane quadrant q; the kEpiSets warps of a quadrant share its
@@ -165,11 +166,12 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// Shared-memory matrix descriptor, K-major operand, SWIZZLE_64B: rows of 64 bytes, 8-row groups 512 bytes apart
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO [16,30), SBO [32,46), version=1 [46,48), layout [61,64) with 4 = SW64).
-// The high word is a constant; the low word is (address >> 4) | LBO and advances by plain addition (the shared
-// window is < 256 KB, so the 14-bit field never carries).
-constexpr uint32_t kDescHi = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
+// Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO [16,30), SBO [32,46), version=1 [46,48), layout [61,64) with 2 = SW128).
+// The high word is a constant; the low word is (address >> 4) | LBO and advances by plain addition, 32 bytes per
+// 16-wide k-step inside the 128-byte row (the shared window is < 256 KB, so the 14-bit field never carries).
+// Tiles are 1024-byte aligned (the swizzle is a function of the address bits).
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFF) | (1u << 16); }
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 // instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, A/B format (0 fp16, 1 bf16), both K-major
@@ -263,7 +265,7 @@ struct SmemCarve {
 };
 template <int STAGES, int REGION_BYTES>  // REGION_BYTES: the stage ring (the barriers sit behind it)
 __device__ __forceinline__ SmemCarve carve(uint8_t *smem_raw) {
-  // the swizzled tiles need 512-byte (SW64) alignment; align the carve-up to 1024 by hand
+  // the swizzled tiles need 1024-byte (SW128) alignment; align the carve-up by hand
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   SmemCarve c;
   c.stages = smem;
@@ -626,7 +628,19 @@ __device__ __forceinline__ void wait_layer(const ChainArgs &a, int layer, int mp
     if (++spins > (1u << 26)) __trap();  // tens of seconds: a broken schedule becomes a launch error, not a hang
 }
 
-constexpr int GRU_STAGES = 7;
+constexpr int GRU_STAGES = 4;
+
+// Per-role cycle accounting of the chain kernel (debug builds only: -DPNB_CHAIN_TIMING, tools/chain_roles.py).
+#ifdef PNB_CHAIN_TIMING
+__device__ unsigned long long g_chain_cycles[16];
+#define CT_DECL long long ct_t = clock64(); unsigned long long ct_acc[6] = {0, 0, 0, 0, 0, 0}
+#define CT_TICK(k) do { long long _n = clock64(); ct_acc[k] += (unsigned long long)(_n - ct_t); ct_t = _n; } while (0)
+#define CT_FLUSH(base, n) do { for (int _i = 0; _i < (n); _i++) atomicAdd(&g_chain_cycles[(base) + _i], ct_acc[_i]); } while (0)
+#else
+#define CT_DECL do { } while (0)
+#define CT_TICK(k) do { } while (0)
+#define CT_FLUSH(base, n) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_constant__ ChainArgs args) {
   using SL = StageLayout<GRU_BN>;
@@ -645,15 +659,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_c
   if (warp == 0) {
     // ===== TMA producer: waits for the rows it is about to read, then streams the tile's operands =====
     Pipe p;
+    CT_DECL;
     for (int u = pair_id; u < total_units; u += n_pairs_cta) {
       const Unit un = decode_unit(args, u);
       const ChainLayer &L = args.L[un.l];
+      CT_TICK(0);  // 0: decode + issue
       if (elect_one()) {  // the same lane issues the TMA loads below
         if (L.dep >= 0) wait_layer(args, L.dep, un.mp, un.t + 1);  // input: layer below, this hop
         if (un.t > 0) wait_layer(args, un.l, un.mp, un.t);        // own state after the previous hop
         fence_proxy_async();  // the rows were written with st.global by other SMs; TMA reads them through the async proxy
       }
       __syncwarp();
+      CT_TICK(1);  // 1: dependency wait
       const int m0 = (2 * un.mp + crank) * TM;
       const int brow = un.nt * GRU_BN + crank * (GRU_BN / 2);
       for (int s = 0; s <= L.n_x; s++) {
@@ -664,7 +681,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_c
         const int aterm = rec ? L.h_term_rows : L.x_term_rows[s];
         const int bk0 = rec ? 0 : L.x_bk0[s];
         for (int kb = 0; kb < nkb; kb++) {
+          CT_TICK(0);
           mbar_wait(c.empty + 8 * p.st, p.ph ^ 1);
+          CT_TICK(2);  // 2: waiting for a free stage
           if (elect_one()) {
             const uint32_t fb = c.full + 8 * p.st;
             if (crank == 0) mbar_expect_tx(fb, 2 * SL::kBytes);
@@ -679,6 +698,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_c
         }
       }
     }
+    CT_TICK(0);
+    if (lane == 0 && crank == 0) CT_FLUSH(0, 3);
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA) =====
     if (crank == 0) {
@@ -686,25 +707,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_c
       const uint32_t a_lo0 = desc_lo(stage0);
       Pipe p;
       int j = 0;
+      CT_DECL;
       for (int u = pair_id; u < total_units; u += n_pairs_cta, j++) {
         const Unit un = decode_unit(args, u);
         const ChainLayer &L = args.L[un.l];
         const int buf = j & 1;
+        CT_TICK(0);  // 0: decode + issue
         mbar_wait(c.acc_empty + 8 * buf, ((j >> 1) & 1) ^ 1);
+        CT_TICK(1);  // 1: waiting for the epilogue to hand the accumulator back
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * kAccCols;
         // accumulator columns [nx | z | r | nh]: input part (rows [n|z|r]) at column 0, recurrent part (rows [z|r|n]) at 64
         int nkb = 0;
         for (int s = 0; s < L.n_x; s++) nkb += L.x_kb[s];
         for (int kb = 0; kb < nkb; kb++) {
+          CT_TICK(0);
           mbar_wait(c.full + 8 * p.st, p.ph);
+          CT_TICK(2);  // 2: waiting for operands
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + p.st * (SL::kBytes >> 4);
           mma_kblock<GRU_BN, 2>(acc, a_lo, idesc, c.empty + 8 * p.st);
           p.advance(STAGES);
         }
         for (int kb = 0; kb < L.h_kb; kb++) {
+          CT_TICK(0);
           mbar_wait(c.full + 8 * p.st, p.ph);
+          CT_TICK(2);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + p.st * (SL::kBytes >> 4);
           mma_kblock<GRU_BN, 2>(acc + HT, a_lo, idesc, c.empty + 8 * p.st);
@@ -713,16 +741,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_c
         if (elect_one()) umma_commit(c.acc_full + 8 * buf);
         __syncwarp();
       }
+      CT_TICK(0);
+      if (lane == 0) CT_FLUSH(4, 3);
     }
   } else if (warp >= 4) {
     // ===== epilogue: gate math of nnet.cpp:136-178 (reset_after) on this thread's stream, 16 units at a time =====
     const int wq = warp & 3, eset = (warp - 4) >> 2;
     const float *tbl = c.tbl;
     int j = 0;
+    CT_DECL;
     for (int u = pair_id; u < total_units; u += n_pairs_cta, j++) {
       const Unit un = decode_unit(args, u);
       const ChainLayer &L = args.L[un.l];
       const int H = L.H, buf = j & 1;
+      CT_TICK(0);  // 0: work
       const int row = (2 * un.mp + crank) * TM + wq * 32 + lane;
       const bool row_ok = row < S;
       const int pold = (L.par0 + un.t) & 1;
@@ -739,7 +771,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_c
 #pragma unroll
         for (int q = 0; q < 4; q++)
           hold[b][q] = row_ok ? __ldcg(reinterpret_cast<const float4 *>(h_old + 16 * eset + 32 * b) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      CT_TICK(1);  // 1: dependency wait + state prefetch issue
       mbar_wait(c.acc_full + 8 * buf, (j >> 1) & 1);
+      CT_TICK(2);  // 2: waiting for the accumulator
       tc_fence_after();
       const uint32_t tlane = tmem_base + buf * kAccCols + ((uint32_t)(wq * 32) << 16);
       const float sc = L.scale;
@@ -785,17 +819,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_c
         }
       }
       // publish: every store of this warp for this tile is ordered before the counter bump
+      CT_TICK(0);
       __syncwarp();
       if (lane == 0) {
         __threadfence();
         red_release_gpu_add(args.cnt + un.l * args.tiles_mp + un.mp, 1u);
       }
+      CT_TICK(3);  // 3: publish (fence + counter)
     }
+    if (warp == 4 && lane == 0 && crank == 0) CT_FLUSH(8, 4);
   }
   tc_teardown<kTmemCols>(tmem_base, warp);
 }
 
-constexpr int DENSE_STAGES = 6, DENSE_STAGES3 = 4, SMALL_BN = 48, SMALL_STAGES = 8;
+constexpr int DENSE_STAGES = 3, DENSE_STAGES3 = 2, SMALL_BN = 48, SMALL_STAGES = 5;
 // conv layers: fc / conv1 outputs are stored as THREE bf16 terms.  Two terms (16 bits, three products) reproduce the
 // network to 1e-5 while activations are O(10) -- every input at the CLI's amplitude scale; louder input (fc outputs
 // in the thousands at x256) needs the third term (six products) to stay inside 1e-4 of the double-precision network
@@ -905,7 +942,7 @@ static int make_map(CUtensorMap *m, const void *base, bool bf16, uint64_t rows, 
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                         const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
@@ -1223,6 +1260,18 @@ int tc_set_stream_hist(pnb_engine *e, int s, const float *fc_hist, const float *
   return PNB_OK;
 }
 
+#ifdef PNB_CHAIN_TIMING
+extern "C" int pnb_debug_chain_cycles(unsigned long long *out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, g_chain_cycles, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_chain_cycles, z, sizeof z);
+  }
+  return 0;
+}
+#endif
+
 int tc_launches_per_chunk(const pnb_engine *) { return 6; }  // fc, conv1, conv2, GRU chain, fc_gb, fc_rb (+ 1 carry per call)
 
 template <typename K, typename A>
@@ -1261,22 +1310,24 @@ static TcSeg mkseg(int a_map, int b_map, int K, int a_k0, int b_k0, int a_row0, 
 }
 
 // ---- the network of hops [h0, h0 + n) of a call of F hops, in three phases -----------------------------------
-// The non-recurrent front (rnn.cpp:50-52 on n S rows): fc -> conv1 -> conv2.  Hop t of the call lives in slot t of the
+// The non-recurrent front (rnn.cpp:50-52 on n S rows): fc (tc_fc) -> conv1 -> conv2 (tc_front).  Hop t of the call lives in slot t of the
 // per-call buffers, so a phase can be run for any hop range once the earlier hops' phases are enqueued.
 // Returns the number of launches or a negative error.
+int tc_fc(pnb_engine *e, int h0, int n, cudaStream_t st) {
+  // fc (fp32 FMA on the CUDA cores: it runs with the DSP kernels when the schedule is split) -> bf16 terms at slots 4 + h0 ..
+  pnb_tc_state *t = e->tc;
+  const int S = e->S, Fm = e->Fmax, rows = n * S;
+  ProfScope ps(e, PNB_K_TC_AUX, st);
+  fc_split_kernel<<<(rows + 3) / 4, 128, 0, st>>>(e->d_feat + (size_t)h0 * S * kFeat, e->fc.W, e->fc.b,
+                                                  t->fc_all + (size_t)(4 + h0) * S * 128, rows, (size_t)(Fm + 4) * S, t->wide);
+  return 1;
+}
 int tc_front(pnb_engine *e, int h0, int n, int F, cudaStream_t st) {
   pnb_tc_state *t = e->tc;
   const int S = e->S, Fm = e->Fmax;
   const float *tbl = e->tansig();
   const int rows = n * S;
   int nl = 0, rc;
-  // fc (fp32 FMA) -> bf16 terms at slots 4 + h0 ..
-  {
-    ProfScope ps(e, PNB_K_TC_AUX, st);
-    fc_split_kernel<<<(rows + 3) / 4, 128, 0, st>>>(e->d_feat + (size_t)h0 * S * kFeat, e->fc.W, e->fc.b,
-                                                    t->fc_all + (size_t)(4 + h0) * S * 128, rows, (size_t)(Fm + 4) * S, t->wide);
-    nl++;
-  }
   TcArgs a;
   // conv1: tap q of hop t reads fc slot t + q (oldest first, nnet.cpp:182-200); output -> c1 slots 2 + t
   memset(&a, 0, sizeof a);
