@@ -63,6 +63,12 @@ enum {
   PNB_NN_TENSOR = 1,     /* network contraction on tcgen05 tensor cores, split-fp16 operands, fp32 accumulate */
   PNB_POSTFILTER = 2,    /* apply the envelope post-filter (src/denoise.cpp:216-250) to g; off in the reference */
   PNB_KEEP_TAPS = 4,     /* keep per-frame intermediates of the last call readable through pnb_read_tap    */
+  PNB_CONV_WIDE = 16,    /* PNB_NN_TENSOR only: conv1 / conv2 with three bf16 terms per operand (six tensor-core products)
+                            instead of two (three).  Two terms reproduce the double-precision network to 7e-6 on g/r for
+                            input at the CLI's amplitude scale (PCM / 32768, |x| <= 1) and to 4e-4 at worst for float
+                            input hundreds to thousands of times louder (the reference's own fp32 arithmetic: 3e-5 there);
+                            three terms stay within 2.1e-5 at every scale and cost 8 % of the throughput.  The mode is
+                            per engine, never per input, so a stream's result does not depend on its neighbours.          */
   PNB_TRAIN_DATA = 8     /* training-data generator (pnb_train_records_*): n_streams = 2 x pairs, no network,
                             no synthesis; model may be NULL; the pnb_process_* entry points are refused      */
 };

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpercepnet_b200.so")
 
 FRAME = 480
-NN_FP32, NN_TENSOR, POSTFILTER, KEEP_TAPS, TRAIN_DATA = 0, 1, 2, 4, 8
+NN_FP32, NN_TENSOR, POSTFILTER, KEEP_TAPS, TRAIN_DATA, CONV_WIDE = 0, 1, 2, 4, 8, 16
 RECORD = 138
 TAPS = {"features": (0, np.float32, 70), "pitch": (1, np.int32, 4), "pitchf": (2, np.float32, 2),
         "X": (3, np.float32, 800), "P": (4, np.float32, 800), "Ex": (5, np.float32, 34), "gr": (6, np.float32, 68),

@@ -181,7 +181,11 @@ static void setup_overlap(pnb_engine *e, int want_net_sms) {
   CUstream s_net = nullptr, s_dsp = nullptr;
   if (G.DeviceGet(&dev, e->device) != CUDA_SUCCESS) return;
   if (G.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return;
-  if (G.DevSmResourceSplitByCount(&grp, &ngrp, &all, &rem, 0, (unsigned)want_net_sms) != CUDA_SUCCESS || ngrp != 1) return;
+  // default granularity: 8 SMs (keeps whole GPCs' cluster scheduling); PNB_SPLIT_FINE=1 asks for 2-SM (TPC) granularity,
+  // enough for the CTA pairs of the network kernels
+  const char *fine = getenv("PNB_SPLIT_FINE");
+  const unsigned split_flags = (fine && atoi(fine) != 0) ? CU_DEV_SM_RESOURCE_SPLIT_IGNORE_SM_COSCHEDULING : 0;
+  if (G.DevSmResourceSplitByCount(&grp, &ngrp, &all, &rem, split_flags, (unsigned)want_net_sms) != CUDA_SUCCESS || ngrp != 1) return;
   if (grp.sm.smCount < 8 || rem.sm.smCount < 8) return;
   if (G.DevResourceGenerateDesc(&d_net, &grp, 1) != CUDA_SUCCESS || G.DevResourceGenerateDesc(&d_dsp, &rem, 1) != CUDA_SUCCESS) return;
   if (G.GreenCtxCreate(&g_net, d_net, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
@@ -217,6 +221,7 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
     return fail(PNB_ERR_ARG, "n_streams x max_frames_per_call above 2^24 rows per call: split the batch across engines");
   const bool train_mode = (flags & PNB_TRAIN_DATA) != 0;
   if (train_mode && (n_streams & 1)) return fail(PNB_ERR_ARG, "PNB_TRAIN_DATA needs n_streams = 2 x pairs");
+  if ((flags & PNB_CONV_WIDE) && !(flags & PNB_NN_TENSOR)) return fail(PNB_ERR_ARG, "PNB_CONV_WIDE applies to PNB_NN_TENSOR engines");
   if (train_mode && (flags & (PNB_NN_TENSOR | PNB_POSTFILTER)))
     return fail(PNB_ERR_ARG, "PNB_TRAIN_DATA runs no network: combine it only with PNB_KEEP_TAPS");
   int rc = train_mode ? 0 : check_model(model);

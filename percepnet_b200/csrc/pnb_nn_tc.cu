@@ -69,9 +69,6 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -333,10 +330,12 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem_base, int warp) {
 // One k-block of a tile on the MMA side: the significant products of both 16-wide k-steps, then the stage is released.
 // Runs warp-converged; `a_lo` is the descriptor low word of the stage's first A term (B terms follow the A terms).
 // Two terms per operand: hi hi, hi lo, lo hi.  Three terms (t0 t1 t2, each 8 bits below the previous): the six
-// products of total order <= 2, issued in three passes over K, smallest products first (PASS 0: order 2, PASS 1:
-// order 1, PASS 2: t0 t0).  The tensor core adds into the fp32 accumulator with truncation at the accumulator's
-// magnitude, so correction products added to an already large sum lose exactly the bits they were meant to supply;
-// summed among themselves first, they do not.
+// products of total order <= 2.
+// PASS < 0: all products of the k-block at once (GRU chain: operands bounded by 1, sums of a few units).
+// PASS >= 0 (dense layers, whose ReLU inputs are unbounded): the K loop runs once per product order, smallest products
+// first (three terms: PASS 0 order 2, PASS 1 order 1, PASS 2 t0 t0; two terms: PASS 1, PASS 2).  The tensor core adds
+// into the fp32 accumulator with truncation at the accumulator's magnitude, so correction products added to an already
+// large sum lose exactly the bits they were meant to supply; summed among themselves first, they do not.
 template <int BN, int NT, int PASS = -1>
 __device__ __forceinline__ void mma_kblock(uint32_t dcol, uint32_t a_lo, uint32_t idesc, uint32_t empty_bar) {
   using SL = StageLayout<BN, NT>;
@@ -346,10 +345,15 @@ __device__ __forceinline__ void mma_kblock(uint32_t dcol, uint32_t a_lo, uint32_
 #pragma unroll
     for (int ks = 0; ks < BK / 16; ks++) {
       const uint32_t a = a_lo + ks * 2, b = b_lo + ks * 2;
-      if (NT == 2) {
+      if (NT == 2 && PASS < 0) {
         umma_f16(dcol, desc64(a), desc64(b), idesc);
         umma_f16(dcol, desc64(a), desc64(b + B), idesc);
         umma_f16(dcol, desc64(a + A), desc64(b), idesc);
+      } else if (NT == 2 && PASS == 1) {
+        umma_f16(dcol, desc64(a), desc64(b + B), idesc);
+        umma_f16(dcol, desc64(a + A), desc64(b), idesc);
+      } else if (NT == 2) {
+        umma_f16(dcol, desc64(a), desc64(b), idesc);
       } else if (PASS == 0) {
         umma_f16(dcol, desc64(a + A), desc64(b + B), idesc);
         umma_f16(dcol, desc64(a), desc64(b + 2 * B), idesc);
@@ -410,9 +414,10 @@ __device__ __forceinline__ void dense_producer(const TcArgs &args, const SmemCar
   Pipe p;
   for (int pair = pair_id; pair < total_pairs; pair += n_pairs_cta) {
     const int n_tile = pair % args.tiles_n, m0 = (2 * (pair / args.tiles_n) + crank) * TM;
-    // three-term operands: three passes over K (see mma_kblock); pass q needs the terms below 3 - q of either operand
-    for (int pass = 0; pass < (NT == 3 ? 3 : 1); pass++) {
-      const int nt = NT == 3 ? 3 - pass : NT;
+    // one pass over K per product order (see mma_kblock); with q passes still to go after this one, the pass needs
+    // the first q + 1 terms of either operand
+    for (int pass = 0; pass < NT; pass++) {
+      const int nt = NT - pass;
       for (int s = 0; s < args.n_seg; s++) {
         const TcSeg &sg = args.seg[s];
         const CUtensorMap *ma = &args.maps[sg.a_map], *mb = &args.maps[sg.b_map];
@@ -461,12 +466,12 @@ __device__ __forceinline__ void dense_mma(const TcArgs &args, const SmemCarve &c
         mma_kblock<BN, NT, 0>(acc, a_lo0 + p.st * (SL::kBytes >> 4), idesc, c.empty + 8 * p.st);
         p.advance(STAGES);
       }
-      for (int kb = 0; kb < nkb; kb++) {
-        mbar_wait(c.full + 8 * p.st, p.ph);
-        tc_fence_after();
-        mma_kblock<BN, NT, 1>(acc, a_lo0 + p.st * (SL::kBytes >> 4), idesc, c.empty + 8 * p.st);
-        p.advance(STAGES);
-      }
+    }
+    for (int kb = 0; kb < nkb; kb++) {
+      mbar_wait(c.full + 8 * p.st, p.ph);
+      tc_fence_after();
+      mma_kblock<BN, NT, 1>(acc, a_lo0 + p.st * (SL::kBytes >> 4), idesc, c.empty + 8 * p.st);
+      p.advance(STAGES);
     }
     for (int kb = 0; kb < nkb; kb++) {
       mbar_wait(c.full + 8 * p.st, p.ph);
@@ -833,20 +838,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_kernel(const __grid_c
 }
 
 constexpr int DENSE_STAGES = 3, DENSE_STAGES3 = 2, SMALL_BN = 48, SMALL_STAGES = 5;
-// conv layers: fc / conv1 outputs are stored as THREE bf16 terms.  Two terms (16 bits, three products) reproduce the
-// network to 1e-5 while activations are O(10) -- every input at the CLI's amplitude scale; louder input (fc outputs
-// in the thousands at x256) needs the third term (six products) to stay inside 1e-4 of the double-precision network
-// (tests/test_gpu_fp64_truth.py).  fc_split_kernel raises the engine's `wide` word when an fc output reaches
-// kWideThreshold; the conv launches read it.
+// conv layers: fc / conv1 outputs and the conv weights are stored as THREE bf16 terms.  The launches use the first
+// two (three products, corrections summed before the main product) unless the engine's `wide` word is set
+// (PNB_CONV_WIDE at pnb_create: all three terms, six products).  The mode is the same for every row of every call,
+// so a stream's result never depends on what its neighbours in the batch carry.
 constexpr int kConvTerms = 3;
-constexpr float kWideThreshold = 128.f;
 
 // fc 70 -> 128 relu in fp32 FMA (0.1 % of the MACs; K = 70 is no tensor-core shape), emitting the three bf16
-// terms conv1 consumes.  One block per 4 rows, one thread per output.  Raises bit 1 of *wide when an output
-// reaches kWideThreshold (see kConvTerms).
+// terms conv1 consumes.  One block per 4 rows, one thread per output.
 __global__ void __launch_bounds__(128) fc_split_kernel(const float *__restrict__ feat, const float *__restrict__ W,
                                                        const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out,
-                                                       int M, size_t plane_rows, int *__restrict__ wide) {
+                                                       int M, size_t plane_rows) {
   __shared__ float f[4][72];
   const int r0 = blockIdx.x * 4;
   for (int i = threadIdx.x; i < 4 * 70; i += blockDim.x) {
@@ -862,11 +864,9 @@ __global__ void __launch_bounds__(128) fc_split_kernel(const float *__restrict__
     for (int rr = 0; rr < 4; rr++) a[rr] = fmaf(w, f[rr][k], a[rr]);
   }
   const size_t plane = plane_rows * 128;
-  bool big = false;
   for (int rr = 0; rr < 4; rr++) {
     if (r0 + rr >= M) break;
     float v = a[rr] < 0.f ? 0.f : a[rr];
-    big |= !(v < kWideThreshold);  // also NaN
     __nv_bfloat16 t0 = __float2bfloat16_rn(v);
     float r = v - __bfloat162float(t0);
     __nv_bfloat16 t1 = __float2bfloat16_rn(r);
@@ -874,7 +874,6 @@ __global__ void __launch_bounds__(128) fc_split_kernel(const float *__restrict__
     size_t o = (size_t)(r0 + rr) * 128 + n;
     out[o] = t0; out[plane + o] = t1; out[2 * plane + o] = t2;
   }
-  if (__any_sync(0xffffffffu, big) && (threadIdx.x & 31) == 0) atomicOr(wide, 2);
 }
 
 // End-of-call bookkeeping in one launch: the hop slots the next call reads first (last 4 fc / 2 conv1 outputs,
@@ -888,7 +887,6 @@ struct CarryArgs {
   int n_seg;
   unsigned *cnt;
   int n_cnt;
-  int *wide;  // bit 1 = this call saw a large fc output, bit 0 = the previous call did (its hops are still in the conv taps)
 };
 __global__ void __launch_bounds__(256) tc_carry_kernel(const __grid_constant__ CarryArgs a) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
@@ -898,7 +896,6 @@ __global__ void __launch_bounds__(256) tc_carry_kernel(const __grid_constant__ C
       for (int k = 0; k < sg.n_slots; k++) sg.base[(size_t)k * sg.slot16 + i] = sg.base[(size_t)(k + sg.shift) * sg.slot16 + i];
   }
   for (size_t i = tid; i < (size_t)a.n_cnt; i += nth) a.cnt[i] = 0u;
-  if (tid == 0) *a.wide = (*a.wide >> 1) & 1;
 }
 
 }  // namespace
@@ -1084,6 +1081,11 @@ int tc_prepare(pnb_engine *e, const pnb_model *model) {
   TCK(dev_zeros(&t->fc_all, kConvTerms * (Fm + 4) * S * 128));
   TCK(dev_zeros(&t->c1_all, kConvTerms * (Fm + 2) * S * 512));
   TCK(dev_zeros(&t->wide, 1));
+  {
+    int w = (e->flags & PNB_CONV_WIDE) ? 1 : 0;
+    if (const char *ct = getenv("PNB_CONV_TERMS")) w = atoi(ct) == 3 ? 1 : atoi(ct) == 2 ? 0 : w;  // experiments
+    TCK(cudaMemcpy(t->wide, &w, sizeof w, cudaMemcpyHostToDevice));
+  }
   TCK(dev_zeros(&t->c2_h, 2 * Fm * S * 512));
   for (int i = 0; i < 5; i++) TCK(dev_zeros(&t->h_all[i], 2 * (Fm + 1) * S * e->gru[i].H));
   t->tiles_mp = (int)((S + 2 * TM - 1) / (2 * TM));
@@ -1177,7 +1179,6 @@ int tc_reset(pnb_engine *e) {
   const size_t Fm = e->Fmax;
   TCK(cudaMemset(t->fc_all, 0, kConvTerms * (Fm + 4) * S * 128 * 2));
   TCK(cudaMemset(t->c1_all, 0, kConvTerms * (Fm + 2) * S * 512 * 2));
-  TCK(cudaMemset(t->wide, 0, sizeof(int)));
   TCK(cudaMemset(t->c2_h, 0, 2 * Fm * S * 512 * 2));
   for (int i = 0; i < 5; i++) TCK(cudaMemset(t->h_all[i], 0, 2 * (Fm + 1) * S * e->gru[i].H * 2));
   TCK(cudaMemset(t->cnt, 0, (size_t)5 * t->tiles_mp * sizeof(unsigned)));
@@ -1233,16 +1234,6 @@ int tc_set_stream_hist(pnb_engine *e, int s, const float *fc_hist, const float *
   };
   TCK(put(t->fc_all, (Fm + 4) * S * 128, 4, 128, fc_hist, fc_terms));
   TCK(put(t->c1_all, (Fm + 2) * S * 512, 2, 512, c1_hist, c1_terms));
-  {  // a loud history keeps the conv layers in their three-term mode for the next call, as it would have at the source
-    bool big = false;
-    for (int k = 0; k < 4 * 128; k++) big |= !(fc_hist[k] < kWideThreshold);
-    if (big) {
-      int w = 0;
-      TCK(cudaMemcpy(&w, t->wide, sizeof w, cudaMemcpyDeviceToHost));
-      w |= 1;
-      TCK(cudaMemcpy(t->wide, &w, sizeof w, cudaMemcpyHostToDevice));
-    }
-  }
   size_t off = 0;
   for (int li = 0; li < 5; li++) {
     const size_t H = e->gru[li].H;
@@ -1319,7 +1310,7 @@ int tc_fc(pnb_engine *e, int h0, int n, cudaStream_t st) {
   const int S = e->S, Fm = e->Fmax, rows = n * S;
   ProfScope ps(e, PNB_K_TC_AUX, st);
   fc_split_kernel<<<(rows + 3) / 4, 128, 0, st>>>(e->d_feat + (size_t)h0 * S * kFeat, e->fc.W, e->fc.b,
-                                                  t->fc_all + (size_t)(4 + h0) * S * 128, rows, (size_t)(Fm + 4) * S, t->wide);
+                                                  t->fc_all + (size_t)(4 + h0) * S * 128, rows, (size_t)(Fm + 4) * S);
   return 1;
 }
 int tc_front(pnb_engine *e, int h0, int n, int F, cudaStream_t st) {
@@ -1447,7 +1438,7 @@ int tc_carry(pnb_engine *e, int F, cudaStream_t st) {
   const int h_terms = (Fm + 1) * S;
   CarryArgs ca;
   memset(&ca, 0, sizeof ca);
-  ca.cnt = t->cnt; ca.n_cnt = 5 * t->tiles_mp; ca.wide = t->wide;
+  ca.cnt = t->cnt; ca.n_cnt = 5 * t->tiles_mp;
   int ns = 0;
   for (int tm = 0; tm < kConvTerms; tm++) {
     __nv_bfloat16 *bf = t->fc_all + (size_t)tm * (Fm + 4) * S * 128;

@@ -3,9 +3,11 @@
 single-precision arithmetic judged the same way.
 
 Both the reference (sequential fp32 sums, /root/reference/src/nnet.cpp:59-72) and the GPU path (fp32 operands split
-into two 16-bit terms, three tensor-core products, fp32 accumulation) are approximations of that double-precision
-network; the parity bar of 1e-4 relative on g/r is asserted at every amplitude scale, and the tensor path's distance
-from the truth is reported beside the reference's own.
+into 16-bit terms, tensor-core products, fp32 accumulation) are approximations of that double-precision network.
+The parity bar of 1e-4 relative on g/r is asserted
+  * at the CLI's amplitude scale with the default engine (conv operands in two bf16 terms),
+  * at x256 and at int16 scale with PNB_CONV_WIDE (three terms) -- the mode for float input far above full scale;
+the default engine's distance at those scales is reported and bounded (5e-4), next to the reference's own.
 
 Domain.  The reference's tansig_approx converts floor(.5f + 25 x) to int (src/vec.h:63): undefined for |x| >= 8.6e7
 (on x86 "tanh" then returns its argument).  Frames whose pre-activations get there are outside what the tensor path
@@ -46,12 +48,19 @@ def test_tensor_path_vs_double_precision(api, oracle, model0, scale):
     print(f"scale {scale:g}: {inside.sum()} of {len(mp)} streams stay inside the tanh domain (max |pre| {mp.max():.3g})")
     assert inside.sum() >= 6
     xi = np.ascontiguousarray(x[inside])
-    eng = api.Engine(xi.shape[0], 8, model0, api.NN_TENSOR)
+    t64 = g64[:, inside]
+    den = np.maximum(np.abs(t64), 1e-6)
+    if scale != 1.0:                                          # the default (two-term) engine on loud input: reported, bounded
+        eng = api.Engine(xi.shape[0], 8, model0, api.NN_TENSOR)
+        _, gr2 = eng.process_stream_chunks(xi, want_gr=True)
+        eng.close()
+        e2 = (np.abs(gr2 - t64) / den).max()
+        print(f"  default engine (two conv terms): {e2:.3e}")
+        assert e2 < 5e-4
+    eng = api.Engine(xi.shape[0], 8, model0, api.NN_TENSOR | (api.CONV_WIDE if scale != 1.0 else 0))
     _, gr = eng.process_stream_chunks(xi, want_gr=True)
     eng.check()                                               # no domain flag for in-domain input
     eng.close()
-    t64 = g64[:, inside]
-    den = np.maximum(np.abs(t64), 1e-6)
     e_tc = (np.abs(gr - t64) / den).max()
     e_ref = (np.abs(gr32[:, inside] - t64) / den).max()
     e_pair = (np.abs(gr - gr32[:, inside]) / den).max()
@@ -77,15 +86,20 @@ def test_error_against_truth_over_amplitude_scales(api, oracle, model0, capsys):
         feats = np.stack([t.np("features") for t in taps[0]])
         W, b = model0.arrays["fc_weights"], model0.arrays["fc_bias"]
         fc = np.maximum(feats @ W.reshape(70, 128) + b, 0)
-        eng = api.Engine(x.shape[0], F, model0, api.NN_TENSOR)
-        _, gr = eng.process(x, want_gr=True)
-        eng.close()
         den = np.maximum(np.abs(g64), 1e-6)
-        rows.append((scale, (np.abs(gr - g64) / den).max(), (np.abs(gr32 - g64) / den).max(), float(fc.max())))
+        errs = []
+        for flags in (api.NN_TENSOR, api.NN_TENSOR | api.CONV_WIDE):
+            eng = api.Engine(x.shape[0], F, model0, flags)
+            _, gr = eng.process(x, want_gr=True)
+            eng.close()
+            errs.append((np.abs(gr - g64) / den).max())
+        rows.append((scale, errs[0], errs[1], (np.abs(gr32 - g64) / den).max(), float(fc.max())))
     with capsys.disabled():
         for r in rows:
-            print(f"  scale {r[0]:>7g}: tensor {r[1]:.2e}  reference {r[2]:.2e}  max fc out {r[3]:.3g}")
-    assert all(r[1] < GR_RTOL for r in rows)
+            print(f"  scale {r[0]:>7g}: tensor {r[1]:.2e} (two conv terms) {r[2]:.2e} (PNB_CONV_WIDE)  reference {r[3]:.2e}  max fc out {r[4]:.3g}")
+    assert all(r[2] < GR_RTOL for r in rows)            # three terms: inside the bar at every scale
+    assert all(r[1] < GR_RTOL for r in rows if r[0] <= 16)   # two terms: inside the bar up to 16 x full scale
+    assert all(r[1] < 5e-4 for r in rows)
 
 
 def test_domain_flag_is_raised_outside_the_tanh_domain(api, oracle, model0):
