@@ -602,11 +602,11 @@ def main():
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if nn_mode == "tensor" and os.path.exists(tp):   # dram__bytes_read+write of the dominant instance, from the last ncu capture
             tj = json.load(open(tp)).get(nn_cls, {})
-            if tj:
-                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            if tj:                                       # per launch, like `achieved`: bytes per frame x frames per launch
+                traffic = int(tj["dram_bytes_per_frame"] * S * F / nn_n)
         roof = {"bound": "tensor" if nn_mode == "tensor" else "fp32", "kernel": nn_cls, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "traffic_note": "DRAM bytes of the network kernels of one step (ncu, profiles/ncu_traffic.json)",
+                "traffic_note": "DRAM bytes per average launch of the network kernels: ncu dram__bytes_read+write per frame (profiles/ncu_traffic.json, 8-hop capture) x frames per launch",
                 "peak_source": (peaks["source"] + " (sustained bf16 cuBLAS; the timed region lasts seconds)") if nn_mode == "tensor"
                                else "nominal fp32 FMA pipe: 148 SMs x 128 lanes x 2 x 1.965 GHz",
                 "frac_of_burst_peak": achieved / peaks["bf16_tflops"] if nn_mode == "tensor" else None,
