@@ -267,7 +267,8 @@ def run_traindata(args):
     launches0 = eng.launches
     ev0.record(stream)
     for i in range(K):
-        step(W + i)
+        step(W + i, submit)
+    eng.flush(stream.cuda_stream)
     ev1.record(stream)
     torch.cuda.synchronize()
     launches = eng.launches - launches0
@@ -374,7 +375,8 @@ def run_xcorr(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for i in range(K):
-        step(W + i)
+        step(W + i, submit)
+    eng.flush(stream.cuda_stream)
     ev1.record(stream)
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
@@ -486,6 +488,8 @@ def main():
     ap.add_argument("--path", default="enhance", choices=["enhance", "traindata", "xcorr"],
                     help="enhance = the headline hot path; traindata = SURVEY.md 8 row f1, the training-record generator; "
                          "xcorr = BASELINE.json config 5, the pitch analysis alone (use --streams 65536)")
+    ap.add_argument("--plain-calls", action="store_true", help="time pnb_process_device_* (joined into the stream after every "
+                    "call) instead of pnb_submit_device_* + pnb_flush")
     ap.add_argument("--no-int16-run", action="store_true", help="skip the second timed run at int16 amplitude scale")
     args = ap.parse_args()
     if not args.frames:
@@ -539,10 +543,14 @@ def main():
     outs = [torch.empty_like(b) for b in bufs]
     stream = torch.cuda.current_stream()
 
-    def step(i):
+    submit = not args.plain_calls
+
+    def step(i, submitted=False):
+        # timed region: pnb_submit_device_* (a call is not joined back into the stream, so the next call's analysis overlaps
+        # this call's network tail; pnb_flush before the closing event makes the stream wait for all of them)
         b = i % n_buf
-        eng.process_device(bufs[b].data_ptr(), bufs[b].stride(0), outs[b].data_ptr(), outs[b].stride(0), F,
-                           stream=stream.cuda_stream)
+        f = eng.submit_device if submitted else eng.process_device
+        f(bufs[b].data_ptr(), bufs[b].stride(0), outs[b].data_ptr(), outs[b].stride(0), F, stream=stream.cuda_stream)
 
     def barrier():
         if world > 1:
@@ -550,7 +558,8 @@ def main():
         torch.cuda.synchronize()
 
     for i in range(W):
-        step(i)
+        step(i, submit)
+    eng.flush(stream.cuda_stream)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -560,7 +569,8 @@ def main():
     launches0 = eng.launches
     ev0.record(stream)
     for i in range(K):
-        step(W + i)
+        step(W + i, submit)
+    eng.flush(stream.cuda_stream)
     ev1.record(stream)
     barrier()
     launches = (eng.launches - launches0) * world           # kernels launched inside the timed region (library counter; every rank issues the same schedule)
@@ -682,12 +692,14 @@ def main():
         for b in bufs:
             b.mul_(32768.0)
         for i in range(W):
-            step(i)
+            step(i, submit)
+        eng.flush(stream.cuda_stream)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for i in range(K):
-            step(W + i)
+            step(W + i, submit)
+        eng.flush(stream.cuda_stream)
         e1.record(stream)
         barrier()
         _, ms16, v16 = aggregate_throughput(S * F * K, e0.elapsed_time(e1), device=device)
@@ -721,6 +733,8 @@ def main():
                                    f"(BASELINE.json config {'2' if S == 1024 else '3/4'}), network={nn_mode}",
                        "streams_per_gpu": S, "frames_per_step": F, "nn": nn_mode, "parallelism": f"streams sharded x{world}, no collective",
                        "l2_policy": f"{n_buf} rotating input buffers of {S * F * FRAME * 4 / 1e6:.0f} MB each (> 126 MB L2 in total)",
+                       "device_api": "pnb_process_device_f32 per step" if args.plain_calls else
+                                     "pnb_submit_device_f32 per step + one pnb_flush before the closing event (calls overlap each other)",
                        "inputs": "every stream its own synthetic signal (harmonic source + noise, generated on the device)",
                        "weights": "random-init, reference architecture (7,962,564 params)"},
             "x_realtime": value / 100.0, "samples_per_sec": value * FRAME,

@@ -121,6 +121,16 @@ int pnb_process_device_f32(pnb_engine *e, const float *d_in, size_t in_stride, f
 int pnb_process_device_i16(pnb_engine *e, const short *d_in, size_t in_stride, short *d_out, size_t out_stride,
                            int n_frames, float *d_gr, void *cuda_stream);
 
+/* Submitted twins of pnb_process_device_*: the call starts when cuda_stream reaches this point (its inputs are ready in
+ * that stream's order) but is NOT joined back into it, so a following call's analysis overlaps this call's network and
+ * synthesis (the engine orders what they share).  d_out is complete once pnb_flush(e, stream) has made `stream` wait for
+ * everything submitted so far, or after pnb_wait / pnb_check on the host.  Calls of one engine are issued in order. */
+int pnb_submit_device_f32(pnb_engine *e, const float *d_in, size_t in_stride, float *d_out, size_t out_stride,
+                          int n_frames, void *cuda_stream);
+int pnb_submit_device_i16(pnb_engine *e, const short *d_in, size_t in_stride, short *d_out, size_t out_stride,
+                          int n_frames, void *cuda_stream);
+int pnb_flush(pnb_engine *e, void *cuda_stream);
+
 /* Training-data generator: the per-frame loop of the reference's train() (src/denoise.cpp:600-787, as shipped:
  * gains fixed at 1, no biquads, the second file is the finished noisy mixture, TEST defined so g is post-filtered).
  * The engine must have been created with PNB_TRAIN_DATA and n_streams = 2 x n_pairs.  speech/noisy hold n_pairs

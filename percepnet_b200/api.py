@@ -57,6 +57,9 @@ def load_library() -> C.CDLL:
     L.pnb_process_device_i16.argtypes = [vp, vp, sz, vp, sz, i, vp, vp]
     L.pnb_submit_host_f32.argtypes = [vp, vp, sz, vp, sz, i]
     L.pnb_submit_host_i16.argtypes = [vp, vp, sz, vp, sz, i]
+    L.pnb_submit_device_f32.argtypes = [vp, vp, sz, vp, sz, i, vp]
+    L.pnb_submit_device_i16.argtypes = [vp, vp, sz, vp, sz, i, vp]
+    L.pnb_flush.argtypes = [vp, vp]
     L.pnb_wait.argtypes = [vp]
     L.pnb_check.argtypes = [vp, vp]
     L.pnb_read_tap.argtypes = [vp, i, vp, sz]
@@ -84,7 +87,7 @@ def load_library() -> C.CDLL:
 
 
 EXPORTS = ("pnb_create", "pnb_destroy", "pnb_reset", "pnb_process_host_f32", "pnb_process_host_i16",
-           "pnb_model_load_blob", "pnb_model_load_stream", "pnb_model_free", "pnb_train_records_host", "pnb_train_records_device", "pnb_submit_train_records", "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_wait", "pnb_check",
+           "pnb_model_load_blob", "pnb_model_load_stream", "pnb_model_free", "pnb_train_records_host", "pnb_train_records_device", "pnb_submit_train_records", "pnb_process_device_f32", "pnb_process_device_i16", "pnb_submit_host_f32", "pnb_submit_host_i16", "pnb_submit_device_f32", "pnb_submit_device_i16", "pnb_flush", "pnb_wait", "pnb_check",
            "pnb_read_tap", "pnb_state_size", "pnb_get_state", "pnb_set_state", "pnb_pitch_only_device", "pnb_pitch_only_host", "pnb_launch_count",
            "pnb_launches_per_call", "pnb_profile_enable", "pnb_profile_read", "pnb_profile_timeline", "pnb_kernel_class_name", "pnb_n_streams", "pnb_overlap_info", "pnb_set_overlap", "pnb_max_frames", "pnb_last_error", "pnb_version")
 
@@ -196,6 +199,15 @@ class Engine:
         f = self.L.pnb_process_device_i16 if int16 else self.L.pnb_process_device_f32
         self._ck(f(self.h, d_in, in_stride, d_out, out_stride, n_frames, d_gr or None, stream or None),
                  "pnb_process_device")
+
+    def submit_device(self, d_in: int, in_stride: int, d_out: int, out_stride: int, n_frames: int, stream: int = 0,
+                      int16: bool = False):
+        """pnb_submit_device_*: like process_device but not joined into `stream`; flush(stream) or wait() completes it."""
+        f = self.L.pnb_submit_device_i16 if int16 else self.L.pnb_submit_device_f32
+        self._ck(f(self.h, d_in, in_stride, d_out, out_stride, n_frames, stream or None), "pnb_submit_device")
+
+    def flush(self, stream: int = 0):
+        self._ck(self.L.pnb_flush(self.h, stream or None), "pnb_flush")
 
     def submit(self, x: np.ndarray, out: np.ndarray):
         """Pipelined host call (pnb_submit_host_*): returns at once; x/out ([S, F*480] float32 or int16, ideally

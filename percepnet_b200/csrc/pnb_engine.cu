@@ -178,7 +178,7 @@ static void setup_overlap(pnb_engine *e, int want_net_sms) {
   unsigned int ngrp = 1;
   CUdevResourceDesc d_net = nullptr, d_dsp = nullptr;
   CUgreenCtx g_net = nullptr, g_dsp = nullptr;
-  CUstream s_net = nullptr, s_dsp = nullptr;
+  CUstream s_net = nullptr, s_dsp = nullptr, s_syn = nullptr;
   if (G.DeviceGet(&dev, e->device) != CUDA_SUCCESS) return;
   if (G.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return;
   // default granularity: 8 SMs (keeps whole GPCs' cluster scheduling); PNB_SPLIT_FINE=1 asks for 2-SM (TPC) granularity,
@@ -191,22 +191,29 @@ static void setup_overlap(pnb_engine *e, int want_net_sms) {
   if (G.GreenCtxCreate(&g_net, d_net, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
   if (G.GreenCtxCreate(&g_dsp, d_dsp, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { G.GreenCtxDestroy(g_net); return; }
   if (G.GreenCtxStreamCreate(&s_net, g_net, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
-      G.GreenCtxStreamCreate(&s_dsp, g_dsp, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+      G.GreenCtxStreamCreate(&s_dsp, g_dsp, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
+      G.GreenCtxStreamCreate(&s_syn, g_dsp, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
     if (s_net) cudaStreamDestroy((cudaStream_t)s_net);
+    if (s_dsp) cudaStreamDestroy((cudaStream_t)s_dsp);
     G.GreenCtxDestroy(g_net); G.GreenCtxDestroy(g_dsp);
     return;
   }
   bool ev_ok = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
                cudaEventCreateWithFlags(&e->ev_join_net, cudaEventDisableTiming) == cudaSuccess &&
-               cudaEventCreateWithFlags(&e->ev_join_dsp, cudaEventDisableTiming) == cudaSuccess;
+               cudaEventCreateWithFlags(&e->ev_join_dsp, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&e->ev_join_syn, cudaEventDisableTiming) == cudaSuccess;
   const int nchunks = (e->Fmax + e->chunk - 1) / e->chunk + 5;  // + the short chunks at both ends of a call
   e->ev_ana.assign(nchunks, nullptr);
   e->ev_net.assign(nchunks, nullptr);
+  e->ev_syn[0].assign(nchunks, nullptr);
+  e->ev_syn[1].assign(nchunks, nullptr);
   for (int k = 0; k < nchunks && ev_ok; k++)
     ev_ok = cudaEventCreateWithFlags(&e->ev_ana[k], cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&e->ev_net[k], cudaEventDisableTiming) == cudaSuccess;
+            cudaEventCreateWithFlags(&e->ev_net[k], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_syn[0][k], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_syn[1][k], cudaEventDisableTiming) == cudaSuccess;
   e->green_net = g_net; e->green_dsp = g_dsp;
-  e->s_net = (cudaStream_t)s_net; e->s_dsp = (cudaStream_t)s_dsp;
+  e->s_net = (cudaStream_t)s_net; e->s_dsp = (cudaStream_t)s_dsp; e->s_syn = (cudaStream_t)s_syn;
   if (!ev_ok) return;  // net_sms stays 0: the serial schedule; pnb_destroy releases what was created
   e->net_sms = (int)grp.sm.smCount;
   e->dsp_sms = (int)rem.sm.smCount;
@@ -332,14 +339,21 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
   }
   // network state; the conv rings and gate sums are scratch of the fp32 path only
   CKD(dalloc(&e->c2, S * 512));
-  for (int i = 0; i < 5; i++)
-    for (int p = 0; p < 2; p++) CKD(dalloc(&e->h[i][p], S * e->gru[i].H));
-  if (!(flags & PNB_NN_TENSOR)) {
-    CKD(dalloc(&e->ring_fc, 5 * S * 128));
-    CKD(dalloc(&e->ring_c1, 3 * S * 512));
-    CKD(dalloc(&e->zr, S * 1024));
-    CKD(dalloc(&e->nx, S * 512));
-    CKD(dalloc(&e->nh, S * 512));
+  if (flags & PNB_NN_TENSOR) {
+    for (int i = 0; i < 5; i++)
+      for (int p = 0; p < 2; p++) CKD(dalloc(&e->h[i][p], S * e->gru[i].H));
+  } else {
+    // fp32 path: hop-slot buffers of one chunk of at most kF32ChainMaxHops hops.  Slot 0.. of the fc / conv1 buffers hold
+    // the conv histories (oldest first), slot 0 of every state buffer the state before the chunk's first hop; the
+    // chunk's carry moves the last slots back there, so between calls the state lives at the front (par stays 0).
+    const size_t C = kF32ChainMaxHops;
+    e->f32_rt = S <= 64 ? 1 : 8;
+    e->f32_rb = (int)((S + 16 * e->f32_rt - 1) / (16 * e->f32_rt));
+    CKD(dalloc(&e->ring_fc, (C + 4) * S * 128));
+    CKD(dalloc(&e->ring_c1, (C + 2) * S * 512));
+    CKD(dalloc(&e->c2_all, C * S * 512));
+    for (int i = 0; i < 5; i++) CKD(dalloc(&e->h[i][0], (C + 1) * S * e->gru[i].H));
+    CKD(dalloc(&e->f32_cnt, (size_t)5 * e->f32_rb));
   }
   e->tc_sms = e->sm_count;
   if (flags & PNB_NN_TENSOR) {
@@ -365,7 +379,7 @@ extern "C" void pnb_destroy(pnb_engine *e) {
   tc_release(e);
   float *fl[] = {e->fc.W, e->fc.b, e->conv1.W, e->conv1.b, e->conv2.W, e->conv2.b, e->fc_gb.W, e->fc_gb.b,
                  e->fc_rb.W, e->fc_rb.b, e->d_pcm, e->d_synth, e->d_last_gain, e->d_feat, e->d_Ex, e->d_gr,
-                 e->d_tap_pitchf, e->d_tap_g, e->ring_fc, e->ring_c1, e->c2, e->zr, e->nx, e->nh, e->d_hin, e->d_hout,
+                 e->d_tap_pitchf, e->d_tap_g, e->ring_fc, e->ring_c1, e->c2, e->c2_all, e->d_hin, e->d_hout,
                  e->d_raw, e->d_records};
   for (float *p : fl) if (p) cudaFree(p);
   for (int i = 0; i < 5; i++) {
@@ -374,6 +388,7 @@ extern "C" void pnb_destroy(pnb_engine *e) {
     if (e->gru[i].b) cudaFree(e->gru[i].b);
     for (int p = 0; p < 2; p++) if (e->h[i][p]) cudaFree(e->h[i][p]);
   }
+  if (e->f32_cnt) cudaFree(e->f32_cnt);
   if (e->d_zring) cudaFree(e->d_zring);
   if (e->d_ering) cudaFree(e->d_ering);
   if (e->d_P) cudaFree(e->d_P);
@@ -396,11 +411,15 @@ extern "C" void pnb_destroy(pnb_engine *e) {
   if (e->s_out) cudaStreamDestroy(e->s_out);
   for (cudaEvent_t ev : e->ev_ana) if (ev) cudaEventDestroy(ev);
   for (cudaEvent_t ev : e->ev_net) if (ev) cudaEventDestroy(ev);
+  for (int p = 0; p < 2; p++)
+    for (cudaEvent_t ev : e->ev_syn[p]) if (ev) cudaEventDestroy(ev);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join_net) cudaEventDestroy(e->ev_join_net);
   if (e->ev_join_dsp) cudaEventDestroy(e->ev_join_dsp);
+  if (e->ev_join_syn) cudaEventDestroy(e->ev_join_syn);
   if (e->s_net) cudaStreamDestroy(e->s_net);
   if (e->s_dsp) cudaStreamDestroy(e->s_dsp);
+  if (e->s_syn) cudaStreamDestroy(e->s_syn);
   if (e->green_net) green_api().GreenCtxDestroy((CUgreenCtx)e->green_net);
   if (e->green_dsp) green_api().GreenCtxDestroy((CUgreenCtx)e->green_dsp);
   for (auto &r : e->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -426,15 +445,19 @@ extern "C" int pnb_reset(pnb_engine *e) {
   *e->h_status = 0;
   e->hop = 0;
   e->poisoned = false;
+  e->unjoined = false;      // the device was synchronised above (green-context streams included)
+  e->prev_start.clear();
   if (e->flags & PNB_TRAIN_DATA) {
     CK(cudaDeviceSynchronize());
     return PNB_OK;
   }
-  if (e->ring_fc) CK(cudaMemset(e->ring_fc, 0, 5 * S * 128 * sizeof(float)));
-  if (e->ring_c1) CK(cudaMemset(e->ring_c1, 0, 3 * S * 512 * sizeof(float)));
+  if (e->ring_fc) CK(cudaMemset(e->ring_fc, 0, (kF32ChainMaxHops + 4) * S * 128 * sizeof(float)));
+  if (e->ring_c1) CK(cudaMemset(e->ring_c1, 0, (kF32ChainMaxHops + 2) * S * 512 * sizeof(float)));
+  if (e->f32_cnt) CK(cudaMemset(e->f32_cnt, 0, (size_t)5 * e->f32_rb * sizeof(unsigned)));
   CK(cudaMemset(e->c2, 0, S * 512 * sizeof(float)));
   for (int i = 0; i < 5; i++)
-    for (int p = 0; p < 2; p++) CK(cudaMemset(e->h[i][p], 0, S * e->gru[i].H * sizeof(float)));
+    for (int p = 0; p < 2; p++)
+      if (e->h[i][p]) CK(cudaMemset(e->h[i][p], 0, ((e->flags & PNB_NN_TENSOR) ? 1 : kF32ChainMaxHops + 1) * S * e->gru[i].H * sizeof(float)));
   for (int i = 0; i < 5; i++) e->par[i] = 0;
   int trc = tc_reset(e);
   if (trc) return trc;
@@ -509,7 +532,7 @@ extern "C" int pnb_profile_timeline(pnb_engine *e, int *cls, double *t0_ms, doub
 }
 extern "C" const char *pnb_kernel_class_name(int cls) {
   static const char *names[PNB_NUM_KERNEL_CLASSES] = {"stage_in_kernel", "analysis_kernel", "fc_f32_kernel",
-      "gemm_f32_kernel", "gru_gates_kernel", "synthesis_kernel", "slide_history_kernel", "tc_gemm_kernel", "tc_aux_kernel", "train_labels_kernel"};
+      "gemm_f32_kernel", "f32_carry_kernel", "synthesis_kernel", "slide_history_kernel", "tc_gemm_kernel", "tc_aux_kernel", "train_labels_kernel"};
   return (cls >= 0 && cls < PNB_NUM_KERNEL_CLASSES) ? names[cls] : "?";
 }
 
@@ -522,79 +545,88 @@ static GemmSeg seg(const float *A, int lda, const float *B, int ldb, int K) {
   return s;
 }
 
-static int gru_step_f32(pnb_engine *e, int li, const GemmSeg *xs, int nx_seg, cudaStream_t st) {
-  // xs: the input segments with B pointing at the start of the matching rows of W (column 0)
-  const int S = e->S, H = e->gru[li].H, ld = 3 * H;
-  const float *h_old = e->h[li][e->par[li]];
-  float *h_new = e->h[li][e->par[li] ^ 1];
+// The network of hops [h0, h0 + n) of a call (n <= kF32ChainMaxHops) in fp32 FMA (rnn.cpp:42-81): the non-recurrent layers
+// once over all n S rows, the five GRUs of all n hops in one persistent launch, the output layers over n S rows, and the
+// carry that moves the conv histories and the states back to the front of their slot buffers.
+static int nn_chunk_f32(pnb_engine *e, int h0, int n, cudaStream_t st) {
+  const int S = e->S, rows = n * S;
   const float *tbl = e->tansig();
-  int n = 0;
+  int nl = 0;
+  // fc -> slots 4.. (slots 0..3 hold the last four hops' outputs)
+  { ProfScope ps(e, PNB_K_FC, st); nl += launch_fc_f32(e->d_feat + (size_t)h0 * S * kFeat, e->fc.W, e->fc.b, e->ring_fc + (size_t)4 * S * 128, rows, 70, 128, st); }
   GemmArgs g;
   memset(&g, 0, sizeof g);
-  g.M = S; g.tansig = tbl; g.bias = nullptr; g.act = 0;
-  // z and r sums over input and recurrent parts
-  for (int i = 0; i < nx_seg; i++) g.seg[i] = xs[i];
-  g.seg[nx_seg] = seg(h_old, H, e->gru[li].U, ld, H);
-  g.n_seg = nx_seg + 1; g.N = 2 * H; g.C = e->zr; g.ldc = 2 * H;
-  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
-  // candidate: input part
-  for (int i = 0; i < nx_seg; i++) { g.seg[i] = xs[i]; g.seg[i].B = xs[i].B + 2 * H; }
-  g.n_seg = nx_seg; g.N = H; g.C = e->nx; g.ldc = H;
-  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
-  // candidate: recurrent part
-  g.seg[0] = seg(h_old, H, e->gru[li].U + 2 * H, ld, H);
-  g.n_seg = 1; g.N = H; g.C = e->nh; g.ldc = H;
-  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
-  GruGateArgs gg;
-  gg.zr = e->zr; gg.nx = e->nx; gg.nh = e->nh; gg.bias = e->gru[li].b; gg.h_old = h_old; gg.h_new = h_new;
-  gg.M = S; gg.H = H; gg.tansig = tbl;
-  { ProfScope ps(e, PNB_K_GRU_GATES, st); n += launch_gru_gates(gg, st); }
-  e->par[li] ^= 1;
-  return n;
-}
+  g.M = rows; g.tansig = tbl;
+  // conv1: tap q of hop t reads fc slot t + q (oldest first, nnet.cpp:182-200; weights [tap][c][n]) -> c1 slots 2..
+  for (int q = 0; q < 5; q++) g.seg[q] = seg(e->ring_fc + (size_t)q * S * 128, 128, e->conv1.W + (size_t)q * 128 * 512, 512, 128);
+  g.n_seg = 5; g.N = 512; g.C = e->ring_c1 + (size_t)2 * S * 512; g.ldc = 512; g.bias = e->conv1.b; g.act = e->act_conv1;
+  { ProfScope ps(e, PNB_K_GEMM_F32, st); nl += launch_gemm_f32(g, st); }
+  for (int q = 0; q < 3; q++) g.seg[q] = seg(e->ring_c1 + (size_t)q * S * 512, 512, e->conv2.W + (size_t)q * 512 * 512, 512, 512);
+  g.n_seg = 3; g.N = 512; g.C = e->c2_all; g.ldc = 512; g.bias = e->conv2.b; g.act = e->act_conv2;
+  { ProfScope ps(e, PNB_K_GEMM_F32, st); nl += launch_gemm_f32(g, st); }
 
-static int nn_step_f32(pnb_engine *e, int t, cudaStream_t st) {
-  const int S = e->S;
-  const long c = e->hop + t;
-  const float *tbl = e->tansig();
-  int n = 0;
-  float *fc_out = e->ring_fc + (size_t)(c % 5) * S * 128;
-  { ProfScope ps(e, PNB_K_FC, st); n += launch_fc_f32(e->d_feat + (size_t)t * S * kFeat, e->fc.W, e->fc.b, fc_out, S, 70, 128, st); }
-  GemmArgs g;
-  memset(&g, 0, sizeof g);
-  g.M = S; g.tansig = tbl;
-  // conv1: taps oldest..newest are ring slots c-4..c (nnet.cpp:182-200; weights [tap][c][n])
-  for (int q = 0; q < 5; q++)
-    g.seg[q] = seg(e->ring_fc + (size_t)(((c - 4 + q) % 5 + 5) % 5) * S * 128, 128, e->conv1.W + (size_t)q * 128 * 512, 512, 128);
-  float *c1_out = e->ring_c1 + (size_t)(c % 3) * S * 512;
-  g.n_seg = 5; g.N = 512; g.C = c1_out; g.ldc = 512; g.bias = e->conv1.b; g.act = e->act_conv1;
-  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
-  for (int q = 0; q < 3; q++)
-    g.seg[q] = seg(e->ring_c1 + (size_t)(((c - 2 + q) % 3 + 3) % 3) * S * 512, 512, e->conv2.W + (size_t)q * 512 * 512, 512, 512);
-  g.n_seg = 3; g.N = 512; g.C = e->c2; g.ldc = 512; g.bias = e->conv2.b; g.act = e->act_conv2;
-  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
   // stacked GRUs: each consumes the freshly updated state of the one below
-  GemmSeg xs[2];
-  xs[0] = seg(e->c2, 512, e->gru[0].W, 1536, 512);
-  n += gru_step_f32(e, 0, xs, 1, st);
-  for (int li = 1; li < 4; li++) {
-    xs[0] = seg(e->h[li - 1][e->par[li - 1]], 512, e->gru[li].W, 1536, 512);
-    n += gru_step_f32(e, li, xs, 1, st);
+  F32ChainArgs a;
+  memset(&a, 0, sizeof a);
+  a.S = S; a.n_rb = e->f32_rb; a.cnt = e->f32_cnt; a.tansig = tbl;
+  for (int li = 0; li < 5; li++) {
+    F32ChainLayer &L = a.L[li];
+    const int H = e->gru[li].H;
+    L.H = H; L.W = e->gru[li].W; L.U = e->gru[li].U; L.bias = e->gru[li].b; L.ldw = 3 * H; L.h = e->h[li][0];
+    if (li == 0) {          // gru1 <- conv2 out
+      L.n_x = 1; L.dep = -1; L.x[0] = e->c2_all; L.x_ld[0] = 512; L.x_K[0] = 512; L.x_slot1[0] = 0; L.x_slot_stride[0] = (size_t)S * 512;
+    } else if (li < 4) {    // gru2 <- gru1, gru3 <- gru2, gru_gb <- gru3
+      L.n_x = 1; L.dep = li - 1; L.x[0] = e->h[li - 1][0]; L.x_ld[0] = 512; L.x_K[0] = 512; L.x_slot1[0] = 1; L.x_slot_stride[0] = (size_t)S * 512;
+    } else {                // gru_rb <- [gru3 state, conv2 out] (rnn.cpp:69-71)
+      L.n_x = 2; L.dep = 2;
+      L.x[0] = e->h[2][0]; L.x_ld[0] = 512; L.x_K[0] = 512; L.x_slot1[0] = 1; L.x_slot_stride[0] = (size_t)S * 512; L.w_row0[0] = 0;
+      L.x[1] = e->c2_all;  L.x_ld[1] = 512; L.x_K[1] = 512; L.x_slot1[1] = 0; L.x_slot_stride[1] = (size_t)S * 512; L.w_row0[1] = 512;
+    }
   }
-  // gru_rb input = [gru3 state, conv2 out] (rnn.cpp:69-71)
-  xs[0] = seg(e->h[2][e->par[2]], 512, e->gru[4].W, 384, 512);
-  xs[1] = seg(e->c2, 512, e->gru[4].W + (size_t)512 * 384, 384, 512);
-  n += gru_step_f32(e, 4, xs, 2, st);
-  // fc_gb on [conv2, gru1, gru2, gru3, gru_gb] (rnn.cpp:73-78), fc_rb on gru_rb (rnn.cpp:80)
-  float *gr = e->d_gr + (size_t)t * S * 68;
-  const float *cat[5] = {e->c2, e->h[0][e->par[0]], e->h[1][e->par[1]], e->h[2][e->par[2]], e->h[3][e->par[3]]};
-  for (int q = 0; q < 5; q++) g.seg[q] = seg(cat[q], 512, e->fc_gb.W + (size_t)q * 512 * 34, 34, 512);
+  {
+    // anti-diagonal order: (t, l) sits on diagonal t + depth(l); everything it needs is on an earlier one
+    static const int depth[5] = {0, 1, 2, 3, 3};
+    int k = 0, unit = 0;
+    for (int d = 0; d < n + 3; d++)
+      for (int li = 0; li < 5; li++) {
+        const int t = d - depth[li];
+        if (t < 0 || t >= n) continue;
+        a.lh[k] = (unsigned char)((t << 3) | li);
+        a.lh_unit0[k] = unit;
+        unit += e->f32_rb * (e->gru[li].H / 32);
+        k++;
+      }
+    a.lh_unit0[k] = unit;
+    a.n_lh = k; a.n_units = unit;
+  }
+  {
+    ProfScope ps(e, PNB_K_GEMM_F32, st);
+    if (launch_gru_chain_f32(a, e->f32_rt, e->sm_count, st) < 0) return fail(PNB_ERR_CUDA, "cannot configure the fp32 GRU chain kernel");
+    nl++;
+  }
+  // fc_gb on [conv2, gru1, gru2, gru3, gru_gb] (rnn.cpp:73-78), fc_rb on gru_rb (rnn.cpp:80); state after hop t = slot t+1
+  float *gr = e->d_gr + (size_t)h0 * S * 68;
+  g.seg[0] = seg(e->c2_all, 512, e->fc_gb.W, 34, 512);
+  for (int q = 1; q < 5; q++) g.seg[q] = seg(e->h[q - 1][0] + (size_t)S * 512, 512, e->fc_gb.W + (size_t)q * 512 * 34, 34, 512);
   g.n_seg = 5; g.N = 34; g.C = gr; g.ldc = 68; g.bias = e->fc_gb.b; g.act = e->act_gb;
-  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
-  g.seg[0] = seg(e->h[4][e->par[4]], 128, e->fc_rb.W, 34, 128);
+  { ProfScope ps(e, PNB_K_GEMM_F32, st); nl += launch_gemm_f32(g, st); }
+  g.seg[0] = seg(e->h[4][0] + (size_t)S * 128, 128, e->fc_rb.W, 34, 128);
   g.n_seg = 1; g.N = 34; g.C = gr + 34; g.ldc = 68; g.bias = e->fc_rb.b; g.act = e->act_rb;
-  { ProfScope ps(e, PNB_K_GEMM_F32, st); n += launch_gemm_f32(g, st); }
-  return n;
+  { ProfScope ps(e, PNB_K_GEMM_F32, st); nl += launch_gemm_f32(g, st); }
+  // carry
+  F32CarryArgs c;
+  memset(&c, 0, sizeof c);
+  int ns = 0;
+  auto cseg = [&](float *base, size_t slot_floats, int n_slots, int from) {
+    c.seg[ns++] = F32CarrySeg{reinterpret_cast<float4 *>(base), reinterpret_cast<const float4 *>(base + (size_t)from * slot_floats), slot_floats / 4, n_slots};
+  };
+  cseg(e->ring_fc, (size_t)S * 128, 4, n);
+  cseg(e->ring_c1, (size_t)S * 512, 2, n);
+  for (int li = 0; li < 5; li++) cseg(e->h[li][0], (size_t)S * e->gru[li].H, 1, n);
+  c.seg[ns++] = F32CarrySeg{reinterpret_cast<float4 *>(e->c2), reinterpret_cast<const float4 *>(e->c2_all + (size_t)(n - 1) * S * 512), (size_t)S * 512 / 4, 1};
+  c.n_seg = ns; c.cnt = e->f32_cnt; c.n_cnt = 5 * e->f32_rb;
+  { ProfScope ps(e, PNB_K_GRU_GATES, st); nl += launch_f32_carry(c, st); }
+  return nl;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -637,20 +669,52 @@ static SynthesisArgs synthesis_args(pnb_engine *e, int h0, int n, float *d_out, 
   return s;
 }
 
+// How a call is tied to the caller: a plain call forks from the caller's stream and joins back into it; a submitted
+// call (pnb_submit_*) starts when `ready` fires (or at the current end of the caller's stream when it is null), records
+// `done` behind its last synthesis and is NOT joined into any stream, so that the next call's analysis can start
+// while this call's network and synthesis are still running.
+struct CallLink {
+  bool submitted = false;
+  cudaEvent_t ready = nullptr, done = nullptr;
+};
+
+// The caller's stream (or the host, st == nullptr ... not used) catches up with work left in flight by submitted calls.
+static int join_engine_streams(pnb_engine *e, cudaStream_t st) {
+  if (!e->unjoined) return PNB_OK;
+  CK(cudaEventRecord(e->ev_join_net, e->s_net));
+  CK(cudaEventRecord(e->ev_join_dsp, e->s_dsp));
+  CK(cudaEventRecord(e->ev_join_syn, e->s_syn));
+  CK(cudaStreamWaitEvent(st, e->ev_join_net, 0));
+  CK(cudaStreamWaitEvent(st, e->ev_join_dsp, 0));
+  CK(cudaStreamWaitEvent(st, e->ev_join_syn, 0));
+  e->unjoined = false;
+  return PNB_OK;
+}
+static int drain_engine_streams(pnb_engine *e) {  // host-side
+  if (!e->unjoined) return PNB_OK;
+  CK(cudaStreamSynchronize(e->s_dsp));
+  CK(cudaStreamSynchronize(e->s_net));
+  CK(cudaStreamSynchronize(e->s_syn));
+  e->unjoined = false;
+  return PNB_OK;
+}
+
 // Enqueues one call.  Host-side stream state (hop counter, line offset, GRU buffer parity) is committed only after
 // every launch was accepted; a failure in between leaves work half-enqueued, so the engine is poisoned until pnb_reset.
 static int process_device_enqueue(pnb_engine *e, const float *d_in, const short *d_in16, size_t in_stride, float *d_out,
-                                  short *d_out16, size_t out_stride, int F, float *d_gr, cudaStream_t st, long long *n_out) {
+                                  short *d_out16, size_t out_stride, int F, float *d_gr, cudaStream_t st, const CallLink &lk,
+                                  long long *n_out) {
   const int S = e->S;
   long long n = 0;
   float *line = e->d_pcm + e->line_off;
   const bool tensor = (e->flags & PNB_NN_TENSOR) != 0;
   if (tensor && e->net_sms > 0 && F >= 2 * e->chunk) {
-    // ---- chunked two-stream schedule: s_dsp runs analysis k+1 and synthesis k-1 while s_net runs the network of chunk k
-    cudaStream_t sd = e->s_dsp, sn = e->s_net;
+    // ---- chunked schedule: s_dsp runs stage-in + analysis + fc of chunk k+1 and s_syn the synthesis of chunk k-1 (both
+    // on the DSP partition) while s_net runs the network of chunk k on its own SMs
+    cudaStream_t sd = e->s_dsp, sn = e->s_net, ss = e->s_syn;
     // chunk lengths: short at both ends (the first analysis and the last network chunk run with the other partition
-    // idle), e->chunk in between
-    int len[kMaxChunks], C = 0;
+    // idle unless calls overlap), e->chunk in between
+    int len[kMaxChunks], start[kMaxChunks + 1], C = 0;
     {
       int left = F, head[2] = {e->chunk / 4 > 0 ? e->chunk / 4 : 1, e->chunk / 2 > 0 ? e->chunk / 2 : 1};
       const int tail_total = head[0] + head[1];
@@ -659,14 +723,32 @@ static int process_device_enqueue(pnb_engine *e, const float *d_in, const short 
       if (left > tail_total) { len[C++] = left - tail_total; left = tail_total; }
       if (left > head[0]) { len[C++] = left - head[0]; left = head[0]; }
       if (left > 0) len[C++] = left;
+      start[0] = 0;
+      for (int k = 0; k < C; k++) start[k + 1] = start[k] + len[k];
     }
-    CK(cudaEventRecord(e->ev_fork, st));
-    CK(cudaStreamWaitEvent(sd, e->ev_fork, 0));
-    CK(cudaStreamWaitEvent(sn, e->ev_fork, 0));
+    // start of the call: the caller's stream unless a ready event was given; when the previous call did not run on the
+    // engine's streams (first call, serial schedule) the caller's stream is what orders this call behind it
+    if (!lk.ready || e->prev_start.empty()) {
+      CK(cudaEventRecord(e->ev_fork, st));
+      CK(cudaStreamWaitEvent(sd, e->ev_fork, 0));
+      CK(cudaStreamWaitEvent(sn, e->ev_fork, 0));
+      CK(cudaStreamWaitEvent(ss, e->ev_fork, 0));
+    }
+    if (lk.ready) CK(cudaStreamWaitEvent(sd, lk.ready, 0));
+    const int cur = e->syn_par ^ 1, prv = e->syn_par;
+    const int pC = (int)e->prev_start.size();
     e->tc_sms = e->net_sms;
-    int h0 = 0, p0 = 0, pn = 0;  // current chunk; previous chunk (start, length)
     for (int k = 0; k < C; k++) {
-      const int nh = len[k];
+      const int h0 = start[k], nh = len[k], h1 = h0 + nh;
+      if (pC) {
+        // What this chunk overwrites was last read by the previous call: hop slots [h0, h1) of the per-call buffers and
+        // the ring slots behind them by its synthesis of the same hops, fc slots [h0+4, h1+4) by its conv1 of hops
+        // < h1+4 (and by its carry, which runs before the last chunk's network-done event).  The synthesis of the last
+        // previous chunk that starts before hop h1+4 is behind all of them.
+        int j = 0;
+        while (j + 1 < pC && e->prev_start[j + 1] < h1 + 4) j++;
+        CK(cudaStreamWaitEvent(sd, e->ev_syn[prv][j], 0));
+      }
       {
         ProfScope ps(e, PNB_K_STAGE_IN, sd);
         n += launch_stage_in(line + (size_t)h0 * kFrame, e->pcm_stride, d_in ? d_in + (size_t)h0 * kFrame : nullptr,
@@ -683,30 +765,34 @@ static int process_device_enqueue(pnb_engine *e, const float *d_in, const short 
       n += q;
       if ((q = tc_out(e, h0, nh, sn)) < 0) { e->tc_sms = e->sm_count; return q; }
       n += q;
-      CK(cudaEventRecord(e->ev_net[k], sn));
-      if (k >= 1) {  // one chunk behind, so that the next analysis is never queued behind a wait for the network
-        CK(cudaStreamWaitEvent(sd, e->ev_net[k - 1], 0));
-        ProfScope ps(e, PNB_K_SYNTHESIS, sd);
-        n += launch_synthesis(synthesis_args(e, p0, pn, d_out, d_out16, out_stride), sd);
+      if (k == C - 1) {  // the carry reads the call's last fc / conv1 / state slots: before the event the next call waits for
+        if ((q = tc_carry(e, F, sn)) < 0) { e->tc_sms = e->sm_count; return q; }
+        n += q;
       }
-      p0 = h0; pn = nh; h0 += nh;
+      CK(cudaEventRecord(e->ev_net[k], sn));
+      CK(cudaStreamWaitEvent(ss, e->ev_net[k], 0));
+      {
+        ProfScope ps(e, PNB_K_SYNTHESIS, ss);
+        n += launch_synthesis(synthesis_args(e, h0, nh, d_out, d_out16, out_stride), ss);
+      }
+      CK(cudaEventRecord(e->ev_syn[cur][k], ss));
     }
-    {
-      CK(cudaStreamWaitEvent(sd, e->ev_net[C - 1], 0));
-      ProfScope ps(e, PNB_K_SYNTHESIS, sd);
-      n += launch_synthesis(synthesis_args(e, p0, pn, d_out, d_out16, out_stride), sd);
-    }
-    int q = tc_carry(e, F, sn);
     e->tc_sms = e->sm_count;
-    if (q < 0) return q;
-    n += q;
     n += advance_line(e, F, sd);
-    CK(cudaEventRecord(e->ev_join_net, sn));
-    CK(cudaEventRecord(e->ev_join_dsp, sd));
-    CK(cudaStreamWaitEvent(st, e->ev_join_net, 0));
-    CK(cudaStreamWaitEvent(st, e->ev_join_dsp, 0));
+    e->prev_start.assign(start, start + C);
+    e->syn_par = cur;
+    e->unjoined = true;
+    if (lk.submitted) {
+      if (lk.done) CK(cudaEventRecord(lk.done, ss));
+    } else {
+      int rc = join_engine_streams(e, st);
+      if (rc) return rc;
+    }
   } else {
     // ---- serial schedule on the caller's stream
+    if (lk.ready) CK(cudaStreamWaitEvent(st, lk.ready, 0));
+    { int rc = join_engine_streams(e, st); if (rc) return rc; }
+    e->prev_start.clear();
     { ProfScope ps(e, PNB_K_STAGE_IN, st); n += launch_stage_in(line, e->pcm_stride, d_in, d_in16, in_stride, S, F * kFrame, st); }
     { ProfScope ps(e, PNB_K_ANALYSIS, st); n += launch_analysis(analysis_args(e, 0, F), st); }
     CK(cudaGetLastError());
@@ -722,10 +808,15 @@ static int process_device_enqueue(pnb_engine *e, const float *d_in, const short 
       if ((k = tc_carry(e, F, st)) < 0) return k;
       n += k;
     } else {
-      for (int t = 0; t < F; t++) n += nn_step_f32(e, t, st);
+      for (int h0 = 0; h0 < F; h0 += kF32ChainMaxHops) {
+        const int q = nn_chunk_f32(e, h0, F - h0 < kF32ChainMaxHops ? F - h0 : kF32ChainMaxHops, st);
+        if (q < 0) return q;
+        n += q;
+      }
     }
     { ProfScope ps(e, PNB_K_SYNTHESIS, st); n += launch_synthesis(synthesis_args(e, 0, F, d_out, d_out16, out_stride), st); }
     n += advance_line(e, F, st);
+    if (lk.submitted && lk.done) CK(cudaEventRecord(lk.done, st));
   }
   if (d_gr) CK(cudaMemcpyAsync(d_gr, e->d_gr, (size_t)F * S * 68 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   CK(cudaGetLastError());
@@ -734,7 +825,8 @@ static int process_device_enqueue(pnb_engine *e, const float *d_in, const short 
 }
 
 static int process_device(pnb_engine *e, const float *d_in, const short *d_in16, size_t in_stride, float *d_out,
-                          short *d_out16, size_t out_stride, int F, float *d_gr, cudaStream_t st) {
+                          short *d_out16, size_t out_stride, int F, float *d_gr, cudaStream_t st,
+                          const CallLink &lk = CallLink()) {
   if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
   if (e->flags & PNB_TRAIN_DATA) return fail(PNB_ERR_ARG, "engine was created with PNB_TRAIN_DATA: use pnb_train_records_*");
   if (e->poisoned) return fail(PNB_ERR_CUDA, "an earlier call failed while enqueuing work; the streams' state is undefined until pnb_reset");
@@ -744,7 +836,8 @@ static int process_device(pnb_engine *e, const float *d_in, const short *d_in16,
     return fail(PNB_ERR_ARG, "row stride smaller than n_frames*480");
   CK(cudaSetDevice(e->device));
   long long n = 0;
-  const int rc = process_device_enqueue(e, d_in, d_in16, in_stride, d_out, d_out16, out_stride, F, d_gr, st, &n);
+  if (lk.submitted && d_gr) return fail(PNB_ERR_ARG, "submitted calls do not copy g/r out");
+  const int rc = process_device_enqueue(e, d_in, d_in16, in_stride, d_out, d_out16, out_stride, F, d_gr, st, lk, &n);
   if (rc) {
     e->poisoned = true;
     return rc;
@@ -917,14 +1010,14 @@ static int submit_host(pnb_engine *e, const T *in, size_t in_stride, T *out, siz
   const size_t w = (size_t)F * kFrame * sizeof(T);
   CK(cudaMemcpy2DAsync(e->pipe_in[k], row * sizeof(T), in, in_stride * sizeof(T), w, S, cudaMemcpyHostToDevice, e->s_in));
   CK(cudaEventRecord(e->ev_in[k], e->s_in));
-  CK(cudaStreamWaitEvent(e->stream, e->ev_in[k], 0));
+  CallLink lk;  // starts when the copy has landed, not joined into any stream: the next call's analysis may overlap this call's tail
+  lk.submitted = true; lk.ready = e->ev_in[k]; lk.done = e->ev_cmp[k];
   int rc;
   if (sizeof(T) == 4)
-    rc = process_device(e, (const float *)e->pipe_in[k], nullptr, row, (float *)e->pipe_out[k], nullptr, row, F, nullptr, e->stream);
+    rc = process_device(e, (const float *)e->pipe_in[k], nullptr, row, (float *)e->pipe_out[k], nullptr, row, F, nullptr, e->stream, lk);
   else
-    rc = process_device(e, nullptr, (const short *)e->pipe_in[k], row, nullptr, (short *)e->pipe_out[k], row, F, nullptr, e->stream);
+    rc = process_device(e, nullptr, (const short *)e->pipe_in[k], row, nullptr, (short *)e->pipe_out[k], row, F, nullptr, e->stream, lk);
   if (rc) return rc;
-  CK(cudaEventRecord(e->ev_cmp[k], e->stream));
   CK(cudaStreamWaitEvent(e->s_out, e->ev_cmp[k], 0));
   CK(cudaMemcpy2DAsync(out, out_stride * sizeof(T), e->pipe_out[k], row * sizeof(T), w, S, cudaMemcpyDeviceToHost, e->s_out));
   CK(cudaEventRecord(e->ev_out[k], e->s_out));
@@ -986,10 +1079,31 @@ extern "C" int pnb_submit_train_records(pnb_engine *e, const short *speech, size
   return PNB_OK;
 }
 
+// Device-buffer twins of pnb_submit_host_*: the call starts when `cuda_stream` reaches this point (the inputs are ready in
+// its order) and is not joined back; pnb_flush makes a stream wait for everything submitted, pnb_wait the host.
+extern "C" int pnb_submit_device_f32(pnb_engine *e, const float *d_in, size_t in_stride, float *d_out, size_t out_stride,
+                                     int n_frames, void *cuda_stream) {
+  CallLink lk;
+  lk.submitted = true;
+  return process_device(e, d_in, nullptr, in_stride, d_out, nullptr, out_stride, n_frames, nullptr, (cudaStream_t)cuda_stream, lk);
+}
+extern "C" int pnb_submit_device_i16(pnb_engine *e, const short *d_in, size_t in_stride, short *d_out, size_t out_stride,
+                                     int n_frames, void *cuda_stream) {
+  CallLink lk;
+  lk.submitted = true;
+  return process_device(e, nullptr, d_in, in_stride, nullptr, d_out, out_stride, n_frames, nullptr, (cudaStream_t)cuda_stream, lk);
+}
+extern "C" int pnb_flush(pnb_engine *e, void *cuda_stream) {
+  if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
+  CK(cudaSetDevice(e->device));
+  return join_engine_streams(e, (cudaStream_t)cuda_stream);
+}
+
 extern "C" int pnb_wait(pnb_engine *e) {
   if (!e) return fail(PNB_ERR_ARG, "engine is NULL");
   CK(cudaSetDevice(e->device));
   if (e->s_in) CK(cudaStreamSynchronize(e->s_in));
+  { int rc = drain_engine_streams(e); if (rc) return rc; }
   CK(cudaMemcpyAsync(e->h_status, e->d_status, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   if (e->s_out) CK(cudaStreamSynchronize(e->s_out));
@@ -1110,14 +1224,10 @@ extern "C" int pnb_get_state(pnb_engine *e, int stream, void *dst, size_t bytes)
     st->has_terms = 1;
     return tc_get_stream_hist(e, stream, &st->fc_hist[0][0], &st->c1_hist[0][0], &st->fc_terms[0][0][0], &st->c1_terms[0][0][0]);
   }
-  for (int k = 0; k < 4; k++) {
-    const long c = e->hop - 4 + k;
-    CK(cudaMemcpy(st->fc_hist[k], e->ring_fc + ((size_t)((c % 5 + 5) % 5) * S + s) * 128, 128 * 4, cudaMemcpyDeviceToHost));
-  }
-  for (int k = 0; k < 2; k++) {
-    const long c = e->hop - 2 + k;
-    CK(cudaMemcpy(st->c1_hist[k], e->ring_c1 + ((size_t)((c % 3 + 3) % 3) * S + s) * 512, 512 * 4, cudaMemcpyDeviceToHost));
-  }
+  for (int k = 0; k < 4; k++)   // slots 0..3 / 0..1: the histories, oldest first (nn_chunk_f32's carry)
+    CK(cudaMemcpy(st->fc_hist[k], e->ring_fc + ((size_t)k * S + s) * 128, 128 * 4, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 2; k++)
+    CK(cudaMemcpy(st->c1_hist[k], e->ring_c1 + ((size_t)k * S + s) * 512, 512 * 4, cudaMemcpyDeviceToHost));
   return PNB_OK;
 }
 
@@ -1153,14 +1263,10 @@ extern "C" int pnb_set_state(pnb_engine *e, int stream, const void *src, size_t 
   if (e->flags & PNB_NN_TENSOR)
     return tc_set_stream_hist(e, stream, &st->fc_hist[0][0], &st->c1_hist[0][0], st->h,
                               st->has_terms ? &st->fc_terms[0][0][0] : nullptr, st->has_terms ? &st->c1_terms[0][0][0] : nullptr);
-  for (int k = 0; k < 4; k++) {
-    const long c = e->hop - 4 + k;
-    CK(cudaMemcpy(e->ring_fc + ((size_t)((c % 5 + 5) % 5) * S + s) * 128, st->fc_hist[k], 128 * 4, cudaMemcpyHostToDevice));
-  }
-  for (int k = 0; k < 2; k++) {
-    const long c = e->hop - 2 + k;
-    CK(cudaMemcpy(e->ring_c1 + ((size_t)((c % 3 + 3) % 3) * S + s) * 512, st->c1_hist[k], 512 * 4, cudaMemcpyHostToDevice));
-  }
+  for (int k = 0; k < 4; k++)
+    CK(cudaMemcpy(e->ring_fc + ((size_t)k * S + s) * 128, st->fc_hist[k], 128 * 4, cudaMemcpyHostToDevice));
+  for (int k = 0; k < 2; k++)
+    CK(cudaMemcpy(e->ring_c1 + ((size_t)k * S + s) * 512, st->c1_hist[k], 512 * 4, cudaMemcpyHostToDevice));
   return PNB_OK;
 }
 
@@ -1298,7 +1404,7 @@ extern "C" int pnb_launches_per_call(const pnb_engine *e, int n_frames) {
     const int C = (e->net_sms > 0 && n_frames >= 2 * e->chunk) ? (n_frames + e->chunk - 1) / e->chunk + 4 : 1;  // upper bound
     return 1 + C * (2 + tc_launches_per_chunk(e)) + 1;  // stage_in + per chunk (analysis, network, synthesis) + carry
   }
-  return 3 + 25 * n_frames;
+  return 3 + 7 * ((n_frames + kF32ChainMaxHops - 1) / kF32ChainMaxHops);  // stage_in, analysis, synthesis + per chunk: fc, conv1, conv2, GRU chain, fc_gb, fc_rb, carry
 }
 // Runtime switch for the chunked overlap schedule (an engine created without it cannot turn it on): profiling a
 // kernel class alone on all SMs needs the serial schedule.

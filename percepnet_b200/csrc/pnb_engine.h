@@ -46,12 +46,14 @@ struct pnb_engine {
   float *d_tap_g = nullptr;   // [F][S][34] gains as applied (PNB_KEEP_TAPS)
 
   // network state (fp32 path): conv rings, GRU states (ping-pong), scratch sums
-  float *ring_fc = nullptr;  // [5][S][128] outputs of fc for hops c-4..c
-  float *ring_c1 = nullptr;  // [3][S][512] outputs of conv1 for hops c-2..c
+  float *ring_fc = nullptr;  // [chunk+4][S][128] fc outputs: slots 0..3 the last four hops (oldest first), 4.. the chunk's
+  float *ring_c1 = nullptr;  // [chunk+2][S][512] conv1 outputs, likewise
   float *c2 = nullptr;       // [S][512]
   float *h[5][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   int par[5] = {0, 0, 0, 0, 0};
-  float *zr = nullptr, *nx = nullptr, *nh = nullptr;
+  float *c2_all = nullptr;   // fp32 path: [chunk][S][512] conv2 outputs of a chunk of hops
+  unsigned *f32_cnt = nullptr;  // fp32 path: [5][f32_rb] dependency counters of the persistent GRU chain
+  int f32_rt = 8, f32_rb = 0;   // rows per thread of the chain kernel (8: 128-stream blocks, 1: 16-stream blocks); stream blocks
   long hop = 0;  // hops processed since reset
 
   // staging for the host-buffer entry points
@@ -72,10 +74,17 @@ struct pnb_engine {
   // in its own green context = its own disjoint set of SMs.  The network phase alone is capped by the board's power
   // limit (it clocks down to ~1.4 GHz) while the DSP phase leaves that budget unused; side by side they even out.
   void *green_net = nullptr, *green_dsp = nullptr;  // CUgreenCtx
-  cudaStream_t s_net = nullptr, s_dsp = nullptr;
+  cudaStream_t s_net = nullptr, s_dsp = nullptr, s_syn = nullptr;  // s_syn: synthesis, in the DSP partition
   int net_sms = 0, dsp_sms = 0, chunk = 8, saved_net_sms = 0;
-  cudaEvent_t ev_fork = nullptr, ev_join_net = nullptr, ev_join_dsp = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join_net = nullptr, ev_join_dsp = nullptr, ev_join_syn = nullptr;
   std::vector<cudaEvent_t> ev_ana, ev_net;
+  // Calls overlap each other as well (pnb_submit_*): the analysis of call i+1 starts while the network and synthesis
+  // of call i are still running.  What call i+1 overwrites (hop-slot buffers, spectrum ring, fc slots) is guarded by
+  // the synthesis-done events of call i, kept per chunk and double-buffered by call parity.
+  std::vector<cudaEvent_t> ev_syn[2];
+  std::vector<int> prev_start;   // first hop of every chunk of the previous chunked call (empty: it was not chunked)
+  int syn_par = 0;               // which ev_syn[] the previous chunked call recorded into
+  bool unjoined = false;         // submitted work is in flight on the engine's own streams, not joined into any caller stream
   int last_frames = 0;
   long long launches = 0;
   // status word on the device: bit 0 = an activation left the domain in which the reference's tansig_approx is

@@ -103,16 +103,29 @@ int launch_gemm_f32(const GemmArgs &g, cudaStream_t st);
 int launch_fc_f32(const float *feat, const float *W, const float *bias, float *out, int M, int K, int N,
                   cudaStream_t st);
 
-// GRU gate math (nnet.cpp:120-180, reset_after) on pre-computed sums:
-//   zr [M x 2H] = W_zr x + U_zr h,  nx [M x H] = W_n x,  nh [M x H] = U_n h
-struct GruGateArgs {
-  const float *zr, *nx, *nh;
-  const float *bias;   // [6H]
-  const float *h_old;  // [M x H]
-  float *h_new;        // [M x H]
-  int M, H;
+// The five GRUs of a chunk of hops in one persistent fp32 launch (pnb_nn_f32.cu).  Slot buffers: hop t of the chunk
+// reads state slot t and writes slot t+1; inputs are conv2's output slot t or the layer below's slot t+1.
+struct F32ChainLayer {
+  int H, n_x, dep;            // hidden size; input segments (1 or 2); layer whose fresh state is the input (-1: conv2 out)
+  const float *x[2];          // input buffers [slots][S][x_ld]
+  int x_ld[2], x_K[2], x_slot1[2];
+  size_t x_slot_stride[2];    // floats per hop slot of the input buffer
+  const float *W, *U, *bias;  // reference layout: W [K_in][3H], U [H][3H], bias [6H]
+  int ldw, w_row0[2];         // 3H; first row of W for each input segment
+  float *h;                   // [(n+1) slots][S][H]
+};
+constexpr int kF32ChainMaxHops = 8;
+struct F32ChainArgs {
+  F32ChainLayer L[5];
+  int S, n_rb, n_units, n_lh;
+  unsigned char lh[5 * kF32ChainMaxHops];      // (hop << 3) | layer in anti-diagonal order
+  int lh_unit0[5 * kF32ChainMaxHops + 1];      // first unit of every entry; [n_lh] = n_units
+  unsigned *cnt;                               // [5][n_rb] finished tiles per (layer, stream block), zero at launch
   const float *tansig;
 };
-int launch_gru_gates(const GruGateArgs &g, cudaStream_t st);
+int launch_gru_chain_f32(const F32ChainArgs &a, int rows_per_thread, int sm_count, cudaStream_t st);
+struct F32CarrySeg { float4 *dst; const float4 *src; size_t slot4; int n_slots; };  // n_slots slots of slot4 float4s
+struct F32CarryArgs { F32CarrySeg seg[12]; int n_seg; unsigned *cnt; int n_cnt; };
+int launch_f32_carry(const F32CarryArgs &a, cudaStream_t st);
 
 }  // namespace pnb

@@ -170,33 +170,240 @@ int launch_fc_f32(const float *feat, const float *W, const float *bias, float *o
   return 1;
 }
 
-// GRU gates (nnet.cpp:120-180 with reset_after):
-//   z = sig(b_z + b'_z + zsum)   r = sig(b_r + b'_r + rsum)
-//   n = tanh(b_n + (b'_n + nh) * r + nx)   h' = z h + (1 - z) n
-__global__ void gru_gates_kernel(GruGateArgs g) {
-  const int H = g.H;
-  const size_t total = (size_t)g.M * H;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    int m = (int)(idx / H), j = (int)(idx % H);
-    const float *b = g.bias;
-    float zs = g.zr[(size_t)m * 2 * H + j], rs = g.zr[(size_t)m * 2 * H + H + j];
-    float z = sigmoid_approx((__ldg(b + j) + __ldg(b + 3 * H + j)) + zs, g.tansig);
-    float r = sigmoid_approx((__ldg(b + H + j) + __ldg(b + 4 * H + j)) + rs, g.tansig);
-    float tmp = __ldg(b + 5 * H + j) + g.nh[idx];
-    float c = __ldg(b + 2 * H + j) + tmp * r;
-    c = c + g.nx[idx];
-    float n = tansig_approx(c, g.tansig);
-    float h = g.h_old[idx];
-    g.h_new[idx] = z * h + (1.f - z) * n;
+// ------------------------------------------------------------------------------------------------------------------
+// The five GRUs of a chunk of hops in ONE persistent fp32 launch (BASELINE.json config 2: "persistent-kernel GRU, fp32").
+//
+// Unit of work = (hop t, layer l, block of BM streams, tile of 32 hidden units): the four gate sums z, r, W_n x, U_n h of
+// 32 hidden units for BM streams (nnet.cpp:120-180 keeps the last two apart), as one register-tiled FMA contraction over
+// [x ; h], then the gate math and the state update in the same thread -- no pre-activation ever goes to memory.
+// State slot t of h_all[l] is the state BEFORE hop t of the chunk, slot t+1 the state after it: a layer reads slot t of
+// its own buffer and slot t+1 of the layer below (the freshly updated state, rnn.cpp:58-71), so nothing is overwritten
+// inside a launch.  A unit depends only on units of the same stream block: all tiles of (t, l-1) and of (t-1, l).  Each
+// (layer, stream block) has a completion counter (red.release / ld.acquire); units are walked in anti-diagonal order
+// (t + l ascending), where every dependency lies on an earlier diagonal, by a grid that is fully co-resident -- so the
+// waits are short, there is no grid barrier and no launch boundary between layers or hops.
+// The accumulation order of every sum (ascending k, x segments first, then h, one FMA per term) is the one the
+// per-layer kernels above use.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int CH_BK = 16, CH_HT = 32, CH_BN = 3 * CH_HT, CH_STAGES = 4, CH_THREADS = 256;
+constexpr int CH_APAD = CH_BK + 4;  // row stride of the A tile in floats: 16-byte aligned rows, conflict-free 128-bit reads
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int n = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add_u32(unsigned *p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int RT>  // rows per thread: 8 (128-stream blocks) or 1 (16-stream blocks, for a handful of streams)
+struct ChainSmem {
+  static constexpr int BM = 16 * RT;
+  float A[CH_STAGES][BM][CH_APAD];
+  float B[CH_STAGES][CH_BK][CH_BN];
+};
+
+// one k-tile of FMAs: acc_z/acc_r/acc_n[i][c] += A[row i][k] * B[k][gate][col c]
+template <int RT>
+__device__ __forceinline__ void chain_tile_fma(const float (*As)[CH_APAD], const float (*Bs)[CH_BN], int ty, int tx,
+                                               float (&az)[RT][2], float (&ar)[RT][2], float (&an)[RT][2]) {
+#pragma unroll
+  for (int kk = 0; kk < CH_BK; kk += 4) {
+    float4 a[RT];
+#pragma unroll
+    for (int i = 0; i < RT; i++) a[i] = *reinterpret_cast<const float4 *>(&As[ty + 16 * i][kk]);  // rows ty, ty+16, ..: a warp's two rows are neighbours (different banks)
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const float2 bz = *reinterpret_cast<const float2 *>(&Bs[kk + q][2 * tx]);
+      const float2 br = *reinterpret_cast<const float2 *>(&Bs[kk + q][CH_HT + 2 * tx]);
+      const float2 bn = *reinterpret_cast<const float2 *>(&Bs[kk + q][2 * CH_HT + 2 * tx]);
+#pragma unroll
+      for (int i = 0; i < RT; i++) {
+        const float av = q == 0 ? a[i].x : q == 1 ? a[i].y : q == 2 ? a[i].z : a[i].w;
+        az[i][0] = fmaf(av, bz.x, az[i][0]); az[i][1] = fmaf(av, bz.y, az[i][1]);
+        ar[i][0] = fmaf(av, br.x, ar[i][0]); ar[i][1] = fmaf(av, br.y, ar[i][1]);
+        an[i][0] = fmaf(av, bn.x, an[i][0]); an[i][1] = fmaf(av, bn.y, an[i][1]);
+      }
+    }
   }
 }
 
-int launch_gru_gates(const GruGateArgs &g, cudaStream_t st) {
-  size_t total = (size_t)g.M * g.H;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  gru_gates_kernel<<<blocks, 256, 0, st>>>(g);
+template <int RT>
+__global__ void __launch_bounds__(CH_THREADS, RT == 8 ? 2 : 4) gru_chain_f32_kernel(const __grid_constant__ F32ChainArgs args) {
+  using SM = ChainSmem<RT>;
+  constexpr int BM = SM::BM;
+  extern __shared__ __align__(16) unsigned char chain_smem_raw[];
+  SM &sm = *reinterpret_cast<SM *>(chain_smem_raw);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int S = args.S;
+
+  for (int u = blockIdx.x; u < args.n_units; u += gridDim.x) {
+    // ---- which unit: anti-diagonal order, the (hop, layer) entries and their first units come from the host
+    int e = 0;
+    while (u >= args.lh_unit0[e + 1]) e++;
+    const int t = args.lh[e] >> 3, l = args.lh[e] & 7;
+    const F32ChainLayer &L = args.L[l];
+    const int tiles = L.H / CH_HT;
+    const int local = u - args.lh_unit0[e];
+    const int rb = local / tiles, j0 = (local - rb * tiles) * CH_HT, m0 = rb * BM;
+
+    // ---- dependencies (one thread polls; the barrier publishes the result to the block)
+    if (tid == 0) {
+      unsigned spins = 0;
+      if (L.dep >= 0) {
+        const unsigned want = (unsigned)(t + 1) * (unsigned)(args.L[L.dep].H / CH_HT);
+        while (ld_acquire_gpu_u32(args.cnt + L.dep * args.n_rb + rb) < want)
+          if (++spins > (1u << 26)) __trap();  // a broken schedule becomes a launch error, not a hang
+      }
+      if (t > 0) {
+        const unsigned want = (unsigned)t * (unsigned)tiles;
+        while (ld_acquire_gpu_u32(args.cnt + l * args.n_rb + rb) < want)
+          if (++spins > (1u << 26)) __trap();
+      }
+    }
+    __syncthreads();
+
+    // ---- the contraction over [x segments ; h]
+    float az[RT][2], ar[RT][2], anx[RT][2], anh[RT][2];
+#pragma unroll
+    for (int i = 0; i < RT; i++)
+#pragma unroll
+      for (int c = 0; c < 2; c++) { az[i][c] = 0.f; ar[i][c] = 0.f; anx[i][c] = 0.f; anh[i][c] = 0.f; }
+
+    const int n_seg = L.n_x + 1;
+    int kt_total = 0;
+    for (int sg = 0; sg < n_seg; sg++) kt_total += (sg < L.n_x ? L.x_K[sg] : L.H) / CH_BK;
+
+    // issue the loads of k-tile `kt` (global tile index over all segments) into stage kt % CH_STAGES
+    auto issue = [&](int kt) {
+      int sg = 0, k0 = kt * CH_BK;
+      while (sg < L.n_x && k0 >= L.x_K[sg]) { k0 -= L.x_K[sg]; sg++; }
+      const bool rec = sg == L.n_x;
+      const float *Ab = rec ? L.h + (size_t)t * S * L.H : L.x[sg] + (size_t)(t + L.x_slot1[sg]) * L.x_slot_stride[sg];
+      const int lda = rec ? L.H : L.x_ld[sg];
+      const float *Bb = rec ? L.U : L.W + (size_t)L.w_row0[sg] * L.ldw;
+      const int st = kt % CH_STAGES;
+      // A: BM rows x 4 chunks of 16 bytes
+      for (int c = tid; c < BM * 4; c += CH_THREADS) {
+        const int r = c >> 2, q = c & 3;
+        const bool ok = m0 + r < S;
+        cp_async16(&sm.A[st][r][q * 4], Ab + (size_t)(ok ? m0 + r : 0) * lda + k0 + q * 4, ok);
+      }
+      // B: 16 k-rows x 3 gates x 8 chunks
+      for (int c = tid; c < CH_BK * 24; c += CH_THREADS) {
+        const int kr = c / 24, rem = c - kr * 24, g = rem >> 3, q = rem & 7;
+        cp_async16(&sm.B[st][kr][g * CH_HT + q * 4], Bb + (size_t)(k0 + kr) * L.ldw + g * L.H + j0 + q * 4, true);
+      }
+    };
+    for (int p = 0; p < CH_STAGES - 1; p++) {
+      if (p < kt_total) issue(p);
+      cp_async_commit();
+    }
+    const int kt_x = kt_total - L.H / CH_BK;  // tiles before the recurrent segment
+    for (int kt = 0; kt < kt_total; kt++) {
+      cp_async_wait<CH_STAGES - 2>();
+      __syncthreads();  // tile kt has landed for every thread; the stage read in iteration kt-1 is free again
+      if (kt + CH_STAGES - 1 < kt_total) issue(kt + CH_STAGES - 1);
+      cp_async_commit();
+      const int st = kt % CH_STAGES;
+      if (kt < kt_x) chain_tile_fma<RT>(sm.A[st], sm.B[st], ty, tx, az, ar, anx);
+      else chain_tile_fma<RT>(sm.A[st], sm.B[st], ty, tx, az, ar, anh);
+    }
+    cp_async_wait<0>();
+
+    // ---- gates and state update (nnet.cpp:120-180 with reset_after; same operation order as gru_gates_kernel)
+    {
+      const float *b = L.bias;
+      const int H = L.H;
+      const float *h_old = L.h + (size_t)t * S * H;
+      float *h_new = L.h + (size_t)(t + 1) * S * H;
+      const int j = j0 + 2 * tx;
+      float bz[2], br[2], bn[2], bnh[2];
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        bz[c] = __ldg(b + j + c) + __ldg(b + 3 * H + j + c);
+        br[c] = __ldg(b + H + j + c) + __ldg(b + 4 * H + j + c);
+        bn[c] = __ldg(b + 2 * H + j + c);
+        bnh[c] = __ldg(b + 5 * H + j + c);
+      }
+#pragma unroll
+      for (int i = 0; i < RT; i++) {
+        const int m = m0 + ty + 16 * i;
+        if (m >= S) continue;
+        const float2 ho = __ldcg(reinterpret_cast<const float2 *>(h_old + (size_t)m * H + j));
+        float out[2];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const float z = sigmoid_approx(bz[c] + az[i][c], args.tansig);
+          const float r = sigmoid_approx(br[c] + ar[i][c], args.tansig);
+          const float tmp = bnh[c] + anh[i][c];
+          float cc = bn[c] + tmp * r;
+          cc = cc + anx[i][c];
+          const float n = tansig_approx(cc, args.tansig);
+          const float h = c == 0 ? ho.x : ho.y;
+          out[c] = z * h + (1.f - z) * n;
+        }
+        *reinterpret_cast<float2 *>(h_new + (size_t)m * H + j) = make_float2(out[0], out[1]);
+      }
+    }
+    __syncthreads();  // every thread's stores are issued (and the tile buffers are free for the next unit)
+    if (tid == 0) {
+      __threadfence();
+      red_release_gpu_add_u32(args.cnt + l * args.n_rb + rb, 1u);
+    }
+  }
+}
+
+// End of a chunk of n hops: the last 4 fc / 2 conv1 slots and the last state slot move to the front, conv2's output of
+// the last hop is kept for the tap, the chain's counters return to zero.  A thread owns the same element of every slot.
+__global__ void f32_carry_kernel(F32CarryArgs a) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (int sg = 0; sg < a.n_seg; sg++) {
+    const F32CarrySeg &g = a.seg[sg];
+    for (size_t i = tid; i < g.slot4; i += stride)
+      for (int q = 0; q < g.n_slots; q++) g.dst[(size_t)q * g.slot4 + i] = g.src[(size_t)q * g.slot4 + i];
+  }
+  for (size_t i = tid; i < (size_t)a.n_cnt; i += stride) a.cnt[i] = 0u;
+}
+}  // namespace
+
+size_t f32_chain_smem(int rt) { return rt == 8 ? sizeof(ChainSmem<8>) : sizeof(ChainSmem<1>); }
+
+int launch_gru_chain_f32(const F32ChainArgs &a, int rt, int sm_count, cudaStream_t st) {
+  static int occ8 = 0, occ1 = 0;
+  int &occ = rt == 8 ? occ8 : occ1;
+  const size_t smem = f32_chain_smem(rt);
+  if (!occ) {
+    cudaError_t e1, e2;
+    if (rt == 8) {
+      e1 = cudaFuncSetAttribute(gru_chain_f32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gru_chain_f32_kernel<8>, CH_THREADS, smem);
+    } else {
+      e1 = cudaFuncSetAttribute(gru_chain_f32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gru_chain_f32_kernel<1>, CH_THREADS, smem);
+    }
+    if (e1 != cudaSuccess || e2 != cudaSuccess || occ < 1) { occ = 0; return -1; }
+  }
+  // the dependency waits need every block of the grid resident: never more blocks than fit at once
+  int grid = occ * sm_count;
+  if (grid > a.n_units) grid = a.n_units;
+  if (rt == 8) gru_chain_f32_kernel<8><<<grid, CH_THREADS, smem, st>>>(a);
+  else gru_chain_f32_kernel<1><<<grid, CH_THREADS, smem, st>>>(a);
+  return 1;
+}
+
+int launch_f32_carry(const F32CarryArgs &a, cudaStream_t st) {
+  f32_carry_kernel<<<296, 256, 0, st>>>(a);
   return 1;
 }
 
