@@ -363,6 +363,8 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
     // PNB_OVERLAP=0 keeps the serial schedule; PNB_NET_SMS / PNB_CHUNK tune the split and the chunk length.
     const char *ov = getenv("PNB_OVERLAP"), *ns = getenv("PNB_NET_SMS"), *ch = getenv("PNB_CHUNK");
     if (ch && atoi(ch) >= 1) e->chunk = atoi(ch);
+    const char *rp = getenv("PNB_RAMP");  // 0: all chunks equal (submitted calls overlap each other, so a call's ends need not be short)
+    if (rp) e->ramp = atoi(rp) != 0;
     const bool worth = (long long)n_streams >= 2048 && max_frames >= 2 * e->chunk && (max_frames + e->chunk - 1) / e->chunk + 5 <= kMaxChunks;
     if (!(ov && atoi(ov) == 0) && (worth || (ov && atoi(ov) == 2)) && max_frames >= 2 * e->chunk)
       setup_overlap(e, ns && atoi(ns) >= 8 ? atoi(ns) : (e->sm_count * 7 / 16 / 8) * 8);
@@ -717,6 +719,9 @@ static int process_device_enqueue(pnb_engine *e, const float *d_in, const short 
     int len[kMaxChunks], start[kMaxChunks + 1], C = 0;
     {
       int left = F, head[2] = {e->chunk / 4 > 0 ? e->chunk / 4 : 1, e->chunk / 2 > 0 ? e->chunk / 2 : 1};
+      if (!e->ramp) {
+        while (left > 0) { len[C] = left < e->chunk ? left : e->chunk; left -= len[C++]; }
+      }
       const int tail_total = head[0] + head[1];
       for (int i = 0; i < 2 && left > tail_total + e->chunk; i++) { len[C++] = head[i]; left -= head[i]; }
       while (left > tail_total + e->chunk) { len[C++] = e->chunk; left -= e->chunk; }

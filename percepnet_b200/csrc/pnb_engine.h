@@ -76,6 +76,7 @@ struct pnb_engine {
   void *green_net = nullptr, *green_dsp = nullptr;  // CUgreenCtx
   cudaStream_t s_net = nullptr, s_dsp = nullptr, s_syn = nullptr;  // s_syn: synthesis, in the DSP partition
   int net_sms = 0, dsp_sms = 0, chunk = 8, saved_net_sms = 0;
+  bool ramp = true;              // short chunks at both ends of a call (PNB_RAMP=0: all chunks equal)
   cudaEvent_t ev_fork = nullptr, ev_join_net = nullptr, ev_join_dsp = nullptr, ev_join_syn = nullptr;
   std::vector<cudaEvent_t> ev_ana, ev_net;
   // Calls overlap each other as well (pnb_submit_*): the analysis of call i+1 starts while the network and synthesis

@@ -605,12 +605,62 @@ struct ChainArgs {
   int t0;                // first hop of this launch inside the call (slot / counter arithmetic is per call)
   int tiles_mp;          // row pairs (256 streams each)
   int units_per_hop;
+  int diag;              // unit order: 0 = hop-major (layer by layer inside a hop), 1 = anti-diagonals (few streams)
   unsigned *cnt;         // [5][tiles_mp] epilogue-warp completions, zero at launch
   const float *tansig;
 };
 
 struct Unit { int t, l, mp, nt; };
+// Anti-diagonal unit order (small batches): (hop t, layer l) sits on diagonal t + depth(l), depth = 0,1,2,3,3 (gru_rb reads
+// gru3 like gru_gb does).  Everything a unit waits for lies on an earlier diagonal, and a diagonal holds up to five
+// layer-hops of mutually independent units -- with few streams one layer-hop alone cannot occupy the CTA pairs.
+__device__ __forceinline__ int diag_size(const ChainArgs &a, int d) {
+  int n = 0;
+#pragma unroll
+  for (int l = 0; l < 5; l++) {
+    const int t = d - (l < 4 ? l : 3);
+    n += (t >= 0 && t < a.F) ? (a.tiles_mp << a.L[l].tiles_log2) : 0;
+  }
+  return n;
+}
+__device__ __forceinline__ Unit decode_unit_diag(const ChainArgs &a, int u) {
+  int d = 0, r = u;
+  bool found = false;
+  for (; d < 3 && !found; d++) {  // ramp-up diagonals
+    const int sz = diag_size(a, d);
+    if (r < sz) { found = true; break; }
+    r -= sz;
+  }
+  if (!found && a.F > 3) {        // full diagonals 3 .. F-1 all hold units_per_hop units
+    const int q = r / a.units_per_hop;
+    if (q < a.F - 3) { d = 3 + q; r -= q * a.units_per_hop; found = true; }
+    else { r -= (a.F - 3) * a.units_per_hop; d = a.F; }
+  }
+  for (; !found; d++) {           // ramp-down diagonals
+    const int sz = diag_size(a, d);
+    if (r < sz) break;
+    r -= sz;
+  }
+  Unit x;
+  x.l = 0; x.t = 0;
+  bool hit = false;
+#pragma unroll
+  for (int l = 0; l < 5; l++) {
+    const int t = d - (l < 4 ? l : 3);
+    const int nl = (t >= 0 && t < a.F) ? (a.tiles_mp << a.L[l].tiles_log2) : 0;
+    if (!hit) {
+      if (r < nl) { x.l = l; x.t = t; hit = true; }
+      else r -= nl;
+    }
+  }
+  const int sh = a.L[x.l].tiles_log2;
+  x.t += a.t0;
+  x.mp = r >> sh;
+  x.nt = r & ((1 << sh) - 1);
+  return x;
+}
 __device__ __forceinline__ Unit decode_unit(const ChainArgs &a, int u) {
+  if (a.diag) return decode_unit_diag(a, u);
   Unit x;
   const int tl = u / a.units_per_hop;
   int r = u - tl * a.units_per_hop;
@@ -1387,6 +1437,9 @@ int tc_gru_chain(pnb_engine *e, int h0, int n, cudaStream_t st) {
     }
   }
   a.units_per_hop = unit0;
+  // with many streams one layer-hop fills the machine and hop-major order keeps a layer's fresh output in L2 for the
+  // layer above; with few, only the anti-diagonal order exposes enough independent units
+  a.diag = (t->tiles_mp * 8 < e->tc_sms) ? 1 : 0;
   {
     ProfScope ps(e, PNB_K_TC_GEMM, st);
     int rc = tc_launch(e, gru_chain_kernel, a, n * unit0, tc_smem_bytes<GRU_STAGES, GRU_STAGES * StageLayout<GRU_BN>::kBytes>(), st);

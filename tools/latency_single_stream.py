@@ -28,8 +28,14 @@ def main():
             for t in range(100, 400):
                 e.process(x[:, t * 480:(t + 1) * 480])
             dt = (time.perf_counter() - t0) / 300
+            # where the time goes: CUDA events around every launch of a few more calls
+            e.profile(True)
+            for t in range(20):
+                e.process(x[:, t * 480:(t + 1) * 480])
+            prof = {k: round(1e3 * v[0] / 20, 1) for k, v in e.profile_read().items()}
+            e.profile(False)
             res[f"S{S}_{name}"] = {"us_per_call": round(dt * 1e6, 1), "x_realtime_per_stream": round(0.01 / dt, 1),
-                                   "launches_per_call": e.launches_per_call(1)}
+                                   "launches_per_call": e.launches_per_call(1), "kernel_us_per_call": prof}
             e.close()
     print(json.dumps(res, indent=1))
 
