@@ -20,4 +20,9 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_g
   python bench.py --frames 8 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-int16-run > $O/ev2_ncu_dense.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:pitch_only_kernel --launch-skip 3 -c 1 -f -o $O/ev2_pitch \
   python bench.py --path xcorr --streams 65536 --steps 1 --warmup 3 --no-cpu-baseline > $O/ev2_ncu_pitch.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/ev2_launches_1024_fp32.csv \
+  python bench.py --streams 1024 --frames 8 --nn fp32 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-int16-run > $O/ev2_launches_1024_fp32.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gru_chain_f32_kernel --launch-skip 3 -c 1 -f -o $O/ev2_chain_f32 \
+  python bench.py --streams 1024 --frames 8 --nn fp32 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-int16-run > $O/ev2_ncu_chain_f32.log 2>&1
+python tools/latency_single_stream.py > $O/ev2_latency.json 2>/dev/null
 ls -la $O/ev2_*
