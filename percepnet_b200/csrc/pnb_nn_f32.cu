@@ -186,7 +186,7 @@ int launch_fc_f32(const float *feat, const float *W, const float *bias, float *o
 // per-layer kernels above use.
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
-constexpr int CH_BK = 16, CH_HT = 32, CH_BN = 3 * CH_HT, CH_STAGES = 4, CH_THREADS = 256;
+constexpr int CH_BK = 32, CH_HT = 32, CH_BN = 3 * CH_HT, CH_STAGES = 3, CH_THREADS = 256;  // 32-k tiles: one block barrier per 32 k
 constexpr int CH_APAD = CH_BK + 4;  // row stride of the A tile in floats: 16-byte aligned rows, conflict-free 128-bit reads
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
@@ -293,13 +293,14 @@ __global__ void __launch_bounds__(CH_THREADS, RT == 8 ? 2 : 4) gru_chain_f32_ker
       const int lda = rec ? L.H : L.x_ld[sg];
       const float *Bb = rec ? L.U : L.W + (size_t)L.w_row0[sg] * L.ldw;
       const int st = kt % CH_STAGES;
-      // A: BM rows x 4 chunks of 16 bytes
-      for (int c = tid; c < BM * 4; c += CH_THREADS) {
-        const int r = c >> 2, q = c & 3;
+      // A: BM rows x CH_BK/4 chunks of 16 bytes
+      constexpr int CPR = CH_BK / 4;
+      for (int c = tid; c < BM * CPR; c += CH_THREADS) {
+        const int r = c / CPR, q = c - r * CPR;
         const bool ok = m0 + r < S;
         cp_async16(&sm.A[st][r][q * 4], Ab + (size_t)(ok ? m0 + r : 0) * lda + k0 + q * 4, ok);
       }
-      // B: 16 k-rows x 3 gates x 8 chunks
+      // B: CH_BK k-rows x 3 gates x 8 chunks
       for (int c = tid; c < CH_BK * 24; c += CH_THREADS) {
         const int kr = c / 24, rem = c - kr * 24, g = rem >> 3, q = rem & 7;
         cp_async16(&sm.B[st][kr][g * CH_HT + q * 4], Bb + (size_t)(k0 + kr) * L.ldw + g * L.H + j0 + q * 4, true);
