@@ -35,6 +35,24 @@ __device__ __forceinline__ float activate(float v, int act, const float *__restr
   return v;
 }
 
+// Packed fp32 pairs (fma.rn.f32x2: two IEEE fp32 FMAs per instruction, bit for bit what two fmaf give).  A scalar FFMA
+// reads three registers from two register banks, so unless the allocator happens to put the accumulator and the B value
+// on opposite banks it takes two cycles -- ncu showed "dispatch stall" as the largest stall of the scalar version, with
+// half of its FFMAs conflicting.  The packed form reads aligned pairs (one register per bank each): every instruction
+// costs the same two cycles for two FMAs, and the loop needs half the issue slots.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ void ffma2(f32x2 &d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+__device__ __forceinline__ f32x2 pack2(float x, float y) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
 constexpr int BM = 128, BN = 64, BK = 16, APAD = 4;
 
 template <bool VEC_B>
@@ -44,11 +62,9 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
 
-  float acc[8][4];
+  f32x2 acc[8][2];  // 8 rows x 2 pairs of columns
 #pragma unroll
-  for (int i = 0; i < 8; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+  for (int i = 0; i < 8; i++) { acc[i][0] = 0ull; acc[i][1] = 0ull; }
 
   // global->register staging: A 2 x float4 per thread, B 1 x float4 per thread
   const int a_row = tid >> 2, a_kq = (tid & 3) * 4;  // rows a_row and a_row+64
@@ -98,13 +114,14 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
     for (int k = 0; k < BK; k++) {
       float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 8]);
       float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 8 + 4]);
-      float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4]);
+      const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(&Bs[buf][k][tx * 4]);  // columns {0,1} and {2,3} as pairs
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 8; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int i = 0; i < 8; i++) {
+        const f32x2 aa = pack2(av[i], av[i]);
+        ffma2(acc[i][0], aa, b.x);
+        ffma2(acc[i][1], aa, b.y);
+      }
     }
     if (more) stash(buf ^ 1);
     __syncthreads();
@@ -116,11 +133,13 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
   for (int i = 0; i < 8; i++) {
     int r = m0 + ty * 8 + i;
     if (r >= g.M) continue;
+    const float2 p0 = unpack2(acc[i][0]), p1 = unpack2(acc[i][1]);
+    const float accv[4] = {p0.x, p0.y, p1.x, p1.y};
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       int c = n0 + tx * 4 + j;
       if (c >= g.N) continue;
-      float v = acc[i][j];
+      float v = accv[j];
       if (g.bias) v = activate(v + __ldg(g.bias + c), g.act, g.tansig);
       g.C[(size_t)r * g.ldc + c] = v;
     }
@@ -213,10 +232,10 @@ struct ChainSmem {
   float B[CH_STAGES][CH_BK][CH_BN];
 };
 
-// one k-tile of FMAs: acc_z/acc_r/acc_n[i][c] += A[row i][k] * B[k][gate][col c]
+// one k-tile of FMAs: acc_z/acc_r/acc_n[i] (pairs of hidden units) += A[row i][k] * B[k][gate][pair]
 template <int RT>
 __device__ __forceinline__ void chain_tile_fma(const float (*As)[CH_APAD], const float (*Bs)[CH_BN], int ty, int tx,
-                                               float (&az)[RT][2], float (&ar)[RT][2], float (&an)[RT][2]) {
+                                               f32x2 (&az)[RT], f32x2 (&ar)[RT], f32x2 (&an)[RT]) {
 #pragma unroll
   for (int kk = 0; kk < CH_BK; kk += 4) {
     float4 a[RT];
@@ -224,15 +243,16 @@ __device__ __forceinline__ void chain_tile_fma(const float (*As)[CH_APAD], const
     for (int i = 0; i < RT; i++) a[i] = *reinterpret_cast<const float4 *>(&As[ty + 16 * i][kk]);  // rows ty, ty+16, ..: a warp's two rows are neighbours (different banks)
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      const float2 bz = *reinterpret_cast<const float2 *>(&Bs[kk + q][2 * tx]);
-      const float2 br = *reinterpret_cast<const float2 *>(&Bs[kk + q][CH_HT + 2 * tx]);
-      const float2 bn = *reinterpret_cast<const float2 *>(&Bs[kk + q][2 * CH_HT + 2 * tx]);
+      const f32x2 bz = *reinterpret_cast<const f32x2 *>(&Bs[kk + q][2 * tx]);
+      const f32x2 br = *reinterpret_cast<const f32x2 *>(&Bs[kk + q][CH_HT + 2 * tx]);
+      const f32x2 bn = *reinterpret_cast<const f32x2 *>(&Bs[kk + q][2 * CH_HT + 2 * tx]);
 #pragma unroll
       for (int i = 0; i < RT; i++) {
         const float av = q == 0 ? a[i].x : q == 1 ? a[i].y : q == 2 ? a[i].z : a[i].w;
-        az[i][0] = fmaf(av, bz.x, az[i][0]); az[i][1] = fmaf(av, bz.y, az[i][1]);
-        ar[i][0] = fmaf(av, br.x, ar[i][0]); ar[i][1] = fmaf(av, br.y, ar[i][1]);
-        an[i][0] = fmaf(av, bn.x, an[i][0]); an[i][1] = fmaf(av, bn.y, an[i][1]);
+        const f32x2 aa = pack2(av, av);
+        ffma2(az[i], aa, bz);
+        ffma2(ar[i], aa, br);
+        ffma2(an[i], aa, bn);
       }
     }
   }
@@ -274,11 +294,9 @@ __global__ void __launch_bounds__(CH_THREADS, RT == 8 ? 2 : 4) gru_chain_f32_ker
     __syncthreads();
 
     // ---- the contraction over [x segments ; h]
-    float az[RT][2], ar[RT][2], anx[RT][2], anh[RT][2];
+    f32x2 az[RT], ar[RT], anx[RT], anh[RT];  // pairs of neighbouring hidden units
 #pragma unroll
-    for (int i = 0; i < RT; i++)
-#pragma unroll
-      for (int c = 0; c < 2; c++) { az[i][c] = 0.f; ar[i][c] = 0.f; anx[i][c] = 0.f; anh[i][c] = 0.f; }
+    for (int i = 0; i < RT; i++) { az[i] = 0ull; ar[i] = 0ull; anx[i] = 0ull; anh[i] = 0ull; }
 
     const int n_seg = L.n_x + 1;
     int kt_total = 0;
@@ -342,14 +360,15 @@ __global__ void __launch_bounds__(CH_THREADS, RT == 8 ? 2 : 4) gru_chain_f32_ker
         const int m = m0 + ty + 16 * i;
         if (m >= S) continue;
         const float2 ho = __ldcg(reinterpret_cast<const float2 *>(h_old + (size_t)m * H + j));
+        const float2 sz = unpack2(az[i]), sr = unpack2(ar[i]), snx = unpack2(anx[i]), snh = unpack2(anh[i]);
         float out[2];
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-          const float z = sigmoid_approx(bz[c] + az[i][c], args.tansig);
-          const float r = sigmoid_approx(br[c] + ar[i][c], args.tansig);
-          const float tmp = bnh[c] + anh[i][c];
+          const float z = sigmoid_approx(bz[c] + (c == 0 ? sz.x : sz.y), args.tansig);
+          const float r = sigmoid_approx(br[c] + (c == 0 ? sr.x : sr.y), args.tansig);
+          const float tmp = bnh[c] + (c == 0 ? snh.x : snh.y);
           float cc = bn[c] + tmp * r;
-          cc = cc + anx[i][c];
+          cc = cc + (c == 0 ? snx.x : snx.y);
           const float n = tansig_approx(cc, args.tansig);
           const float h = c == 0 ? ho.x : ho.y;
           out[c] = z * h + (1.f - z) * n;

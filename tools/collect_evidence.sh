@@ -9,8 +9,9 @@ python bench.py --frames 8 --steps 20 --warmup 5 --no-cpu-baseline > $O/ev2_benc
 python bench.py --path xcorr --streams 65536 --steps 20 --warmup 5 > $O/ev2_bench_xcorr.json 2> $O/ev2_xcorr.err; cut -c1-200 $O/ev2_bench_xcorr.json
 python bench.py --streams 1024 --frames 8 --nn tensor --no-cpu-baseline > $O/ev2_bench_1024_tensor.json 2>/dev/null
 python bench.py --streams 1024 --frames 8 --nn fp32 --no-cpu-baseline > $O/ev2_bench_1024_fp32.json 2>/dev/null
+python bench.py --streams 16384 --frames 8 --nn fp32 --no-cpu-baseline --no-int16-run > $O/ev2_bench_16384_fp32.json 2>/dev/null
 python bench.py --path traindata > $O/ev2_bench_traindata.json 2>/dev/null
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/ev2_launches.csv \
+timeout 600 ncu --kernel-name-base mangled -k regex:pnb --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/ev2_launches.csv \
   python bench.py --frames 8 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-int16-run > $O/ev2_launches.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gru_chain_kernel --launch-skip 3 -c 1 -f -o $O/ev2_chain \
   python bench.py --frames 8 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-int16-run > $O/ev2_ncu_chain.log 2>&1
@@ -20,7 +21,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_g
   python bench.py --frames 8 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-int16-run > $O/ev2_ncu_dense.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:pitch_only_kernel --launch-skip 3 -c 1 -f -o $O/ev2_pitch \
   python bench.py --path xcorr --streams 65536 --steps 1 --warmup 3 --no-cpu-baseline > $O/ev2_ncu_pitch.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/ev2_launches_1024_fp32.csv \
+timeout 600 ncu --kernel-name-base mangled -k regex:pnb --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/ev2_launches_1024_fp32.csv \
   python bench.py --streams 1024 --frames 8 --nn fp32 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-int16-run > $O/ev2_launches_1024_fp32.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gru_chain_f32_kernel --launch-skip 3 -c 1 -f -o $O/ev2_chain_f32 \
   python bench.py --streams 1024 --frames 8 --nn fp32 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-int16-run > $O/ev2_ncu_chain_f32.log 2>&1
