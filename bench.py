@@ -586,66 +586,6 @@ def main():
         step(W + K)
         overlapped_breakdown = {k: round(v[0], 4) for k, v in eng.profile_read().items()}
         eng.profile(False)
-        # the serial-schedule step runs on an engine of its own, created without the SM partition (with the green contexts
-        # alive, kernels on an ordinary stream of the same process were measured a third slower in the analysis kernel)
-        old_ov = os.environ.get("PNB_OVERLAP")
-        os.environ["PNB_OVERLAP"] = "0"
-        try:
-            eng_p = api.Engine(S, F, model, flags, device=local)
-        finally:
-            if old_ov is None:
-                os.environ.pop("PNB_OVERLAP", None)
-            else:
-                os.environ["PNB_OVERLAP"] = old_ov
-    else:
-        eng_p = eng
-
-    def pstep(i):
-        b = i % n_buf
-        eng_p.process_device(bufs[b].data_ptr(), bufs[b].stride(0), outs[b].data_ptr(), outs[b].stride(0), F, stream=stream.cuda_stream)
-    pstep(W + K + 1)                          # one untimed step to settle
-    torch.cuda.synchronize()
-    eng_p.profile(True)
-    pstep(W + K + 2)
-    prof = eng_p.profile_read()
-    eng_p.profile(False)
-    if eng_p is not eng:
-        eng_p.close()
-    nn_cls = "tc_gemm_kernel" if nn_mode == "tensor" else "gemm_f32_kernel"
-    nn_ms, nn_n = prof.get(nn_cls, (0.0, 0))
-    step_ms_prof = sum(v[0] for v in prof.values())
-    peaks = measured_peaks()
-    roof = None
-    if nn_n:
-        flops_per_launch = S * F * FLOP_PER_FRAME / nn_n       # algorithmic flops of the step / contraction launches
-        achieved = flops_per_launch / (nn_ms / nn_n * 1e-3) / 1e12
-        # the kernel is timed inside a step that lasts seconds: the sustained library figure is the matching peak
-        # (the burst figure is given beside it); the fp32 path is judged against the fp32 FMA pipe, not the tensor pipe
-        fp32_peak = 2 * 128 * 148 * 1.965e9 / 1e12
-        peak = peaks["bf16_tflops_sustained"] if nn_mode == "tensor" else fp32_peak
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if nn_mode == "tensor" and os.path.exists(tp):   # dram__bytes_read+write of the dominant instance, from the last ncu capture
-            tj = json.load(open(tp)).get(nn_cls, {})
-            if tj:                                       # per launch, like `achieved`: bytes per frame x frames per launch
-                traffic = int(tj["dram_bytes_per_frame"] * S * F / nn_n)
-        roof = {"bound": "tensor" if nn_mode == "tensor" else "fp32", "kernel": nn_cls, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": traffic,
-                "traffic_note": "DRAM bytes per average launch of the network kernels: ncu dram__bytes_read+write per frame (profiles/ncu_traffic.json, 8-hop capture) x frames per launch",
-                "peak_source": (peaks["source"] + " (sustained bf16 cuBLAS; the timed region lasts seconds)") if nn_mode == "tensor"
-                               else "nominal fp32 FMA pipe: 148 SMs x 128 lanes x 2 x 1.965 GHz",
-                "frac_of_burst_peak": achieved / peaks["bf16_tflops"] if nn_mode == "tensor" else None,
-                "launches_per_step": nn_n, "avg_launch_ms": nn_ms / nn_n,
-                "share_of_step": nn_ms / step_ms_prof if step_ms_prof else None,
-                "pipe": "tcgen05 split-fp16 (3 MMA per product)" if nn_mode == "tensor" else "fp32 FMA (CUDA cores)",
-                # the fp32-accurate split issues 3 half-precision MMAs per algorithmic product: what the tensor
-                # pipe actually executes, against the same measured peak
-                "issued_tflops": achieved * 3 if nn_mode == "tensor" else None,
-                "issued_frac": achieved * 3 / peak if nn_mode == "tensor" else None,
-                "step_hbm_gbs_algorithmic": S * F * BYTES_PER_FRAME / (ms_max / K * 1e-3) / 1e9,
-                "breakdown_ms": {k: round(v[0], 4) for k, v in prof.items()},
-                "breakdown_note": "one step on the serial schedule: every kernel alone on all 148 SMs",
-                "overlapped_breakdown_ms": overlapped_breakdown}
 
     # ---- end to end through the public host-buffer call, pinned memory ---------------------
     e2e = None
@@ -696,13 +636,80 @@ def main():
         e2e["blocking_call_frames_per_s"] = world * S * F * nb / (time.perf_counter() - t0)
         e2e["blocking_calls_timed"] = nb
 
+    # ---- serial-schedule profile for the roofline.  With the overlapped schedule it runs on an engine of its own, created
+    # without the SM partition AFTER the partitioned engine is gone (with green contexts alive in the process, kernels on
+    # an ordinary stream were measured up to 40 % slower in the analysis kernel).
+    if sched["kind"] != "serial":
+        eng.close()
+        eng = None
+        old_ov = os.environ.get("PNB_OVERLAP")
+        os.environ["PNB_OVERLAP"] = "0"
+        try:
+            eng_p = api.Engine(S, F, model, flags, device=local)
+        finally:
+            if old_ov is None:
+                os.environ.pop("PNB_OVERLAP", None)
+            else:
+                os.environ["PNB_OVERLAP"] = old_ov
+    else:
+        eng_p = eng
+
+    def pstep(i):
+        b = i % n_buf
+        eng_p.process_device(bufs[b].data_ptr(), bufs[b].stride(0), outs[b].data_ptr(), outs[b].stride(0), F, stream=stream.cuda_stream)
+    pstep(W + K + 1)                          # one untimed step to settle
+    torch.cuda.synchronize()
+    eng_p.profile(True)
+    pstep(W + K + 2)
+    prof = eng_p.profile_read()
+    eng_p.profile(False)
+    if eng_p is not eng:
+        eng_p.close()
+        eng_p = None
+    nn_cls = "tc_gemm_kernel" if nn_mode == "tensor" else "gemm_f32_kernel"
+    nn_ms, nn_n = prof.get(nn_cls, (0.0, 0))
+    step_ms_prof = sum(v[0] for v in prof.values())
+    peaks = measured_peaks()
+    roof = None
+    if nn_n:
+        flops_per_launch = S * F * FLOP_PER_FRAME / nn_n       # algorithmic flops of the step / contraction launches
+        achieved = flops_per_launch / (nn_ms / nn_n * 1e-3) / 1e12
+        # the kernel is timed inside a step that lasts seconds: the sustained library figure is the matching peak
+        # (the burst figure is given beside it); the fp32 path is judged against the fp32 FMA pipe, not the tensor pipe
+        fp32_peak = 2 * 128 * 148 * 1.965e9 / 1e12
+        peak = peaks["bf16_tflops_sustained"] if nn_mode == "tensor" else fp32_peak
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if nn_mode == "tensor" and os.path.exists(tp):   # dram__bytes_read+write of the dominant instance, from the last ncu capture
+            tj = json.load(open(tp)).get(nn_cls, {})
+            if tj:                                       # per launch, like `achieved`: bytes per frame x frames per launch
+                traffic = int(tj["dram_bytes_per_frame"] * S * F / nn_n)
+        roof = {"bound": "tensor" if nn_mode == "tensor" else "fp32", "kernel": nn_cls, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "DRAM bytes per average launch of the network kernels: ncu dram__bytes_read+write per frame (profiles/ncu_traffic.json, 8-hop capture) x frames per launch",
+                "peak_source": (peaks["source"] + " (sustained bf16 cuBLAS; the timed region lasts seconds)") if nn_mode == "tensor"
+                               else "nominal fp32 FMA pipe: 148 SMs x 128 lanes x 2 x 1.965 GHz",
+                "frac_of_burst_peak": achieved / peaks["bf16_tflops"] if nn_mode == "tensor" else None,
+                "launches_per_step": nn_n, "avg_launch_ms": nn_ms / nn_n,
+                "share_of_step": nn_ms / step_ms_prof if step_ms_prof else None,
+                "pipe": "tcgen05 split-fp16 (3 MMA per product)" if nn_mode == "tensor" else "fp32 FMA (CUDA cores)",
+                # the fp32-accurate split issues 3 half-precision MMAs per algorithmic product: what the tensor
+                # pipe actually executes, against the same measured peak
+                "issued_tflops": achieved * 3 if nn_mode == "tensor" else None,
+                "issued_frac": achieved * 3 / peak if nn_mode == "tensor" else None,
+                "step_hbm_gbs_algorithmic": S * F * BYTES_PER_FRAME / (ms_max / K * 1e-3) / 1e9,
+                "breakdown_ms": {k: round(v[0], 4) for k, v in prof.items()},
+                "breakdown_note": "one step on the serial schedule: every kernel alone on all 148 SMs",
+                "overlapped_breakdown_ms": overlapped_breakdown}
+
     # ---- second timed run at int16 amplitude scale (x 32768: what the reference's train() feeds the same API with) --
     # At the CLI's unit scale sum(Ex) < 0.1 for every frame, so the reference's `silence` flag is always set and
     # pitch_filter (src/denoise.cpp:436-485) never runs; at this scale it does.  Float input this far
     # above full scale is what PNB_CONV_WIDE (three-term conv operands) is for: the run uses an engine created with it.
     i16run = None
     if not args.no_int16_run:
-        eng.close()
+        if eng is not None:
+            eng.close()
         eng = api.Engine(S, F, model, flags | (api.CONV_WIDE if flags == api.NN_TENSOR else 0), device=local)
         for b in bufs:
             b.mul_(32768.0)
@@ -729,7 +736,8 @@ def main():
                             if flags == api.NN_TENSOR else "PNB_NN_FP32",
                   "network_domain": dom}
 
-    eng.close()
+    if eng is not None:
+        eng.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -343,10 +343,11 @@ extern "C" int pnb_create(pnb_engine **out, int n_streams, int max_frames, const
     for (int i = 0; i < 5; i++)
       for (int p = 0; p < 2; p++) CKD(dalloc(&e->h[i][p], S * e->gru[i].H));
   } else {
-    // fp32 path: hop-slot buffers of one chunk of at most kF32ChainMaxHops hops.  Slot 0.. of the fc / conv1 buffers hold
+    // fp32 path: hop-slot buffers of one chunk of at most f32_chunk = min(max_frames, 32) hops.  Slot 0.. of the fc / conv1 buffers hold
     // the conv histories (oldest first), slot 0 of every state buffer the state before the chunk's first hop; the
     // chunk's carry moves the last slots back there, so between calls the state lives at the front (par stays 0).
-    const size_t C = kF32ChainMaxHops;
+    e->f32_chunk = max_frames < kF32ChainMaxHops ? max_frames : kF32ChainMaxHops;
+    const size_t C = e->f32_chunk;
     e->f32_rt = S <= 64 ? 1 : 8;
     e->f32_rb = (int)((S + 16 * e->f32_rt - 1) / (16 * e->f32_rt));
     CKD(dalloc(&e->ring_fc, (C + 4) * S * 128));
@@ -453,13 +454,13 @@ extern "C" int pnb_reset(pnb_engine *e) {
     CK(cudaDeviceSynchronize());
     return PNB_OK;
   }
-  if (e->ring_fc) CK(cudaMemset(e->ring_fc, 0, (kF32ChainMaxHops + 4) * S * 128 * sizeof(float)));
-  if (e->ring_c1) CK(cudaMemset(e->ring_c1, 0, (kF32ChainMaxHops + 2) * S * 512 * sizeof(float)));
+  if (e->ring_fc) CK(cudaMemset(e->ring_fc, 0, (size_t)(e->f32_chunk + 4) * S * 128 * sizeof(float)));
+  if (e->ring_c1) CK(cudaMemset(e->ring_c1, 0, (size_t)(e->f32_chunk + 2) * S * 512 * sizeof(float)));
   if (e->f32_cnt) CK(cudaMemset(e->f32_cnt, 0, (size_t)5 * e->f32_rb * sizeof(unsigned)));
   CK(cudaMemset(e->c2, 0, S * 512 * sizeof(float)));
   for (int i = 0; i < 5; i++)
     for (int p = 0; p < 2; p++)
-      if (e->h[i][p]) CK(cudaMemset(e->h[i][p], 0, ((e->flags & PNB_NN_TENSOR) ? 1 : kF32ChainMaxHops + 1) * S * e->gru[i].H * sizeof(float)));
+      if (e->h[i][p]) CK(cudaMemset(e->h[i][p], 0, (size_t)((e->flags & PNB_NN_TENSOR) ? 1 : e->f32_chunk + 1) * S * e->gru[i].H * sizeof(float)));
   for (int i = 0; i < 5; i++) e->par[i] = 0;
   int trc = tc_reset(e);
   if (trc) return trc;
@@ -547,7 +548,7 @@ static GemmSeg seg(const float *A, int lda, const float *B, int ldb, int K) {
   return s;
 }
 
-// The network of hops [h0, h0 + n) of a call (n <= kF32ChainMaxHops) in fp32 FMA (rnn.cpp:42-81): the non-recurrent layers
+// The network of hops [h0, h0 + n) of a call (n <= e->f32_chunk) in fp32 FMA (rnn.cpp:42-81): the non-recurrent layers
 // once over all n S rows, the five GRUs of all n hops in one persistent launch, the output layers over n S rows, and the
 // carry that moves the conv histories and the states back to the front of their slot buffers.
 static int nn_chunk_f32(pnb_engine *e, int h0, int n, cudaStream_t st) {
@@ -813,8 +814,8 @@ static int process_device_enqueue(pnb_engine *e, const float *d_in, const short 
       if ((k = tc_carry(e, F, st)) < 0) return k;
       n += k;
     } else {
-      for (int h0 = 0; h0 < F; h0 += kF32ChainMaxHops) {
-        const int q = nn_chunk_f32(e, h0, F - h0 < kF32ChainMaxHops ? F - h0 : kF32ChainMaxHops, st);
+      for (int h0 = 0; h0 < F; h0 += e->f32_chunk) {
+        const int q = nn_chunk_f32(e, h0, F - h0 < e->f32_chunk ? F - h0 : e->f32_chunk, st);
         if (q < 0) return q;
         n += q;
       }
@@ -1409,7 +1410,7 @@ extern "C" int pnb_launches_per_call(const pnb_engine *e, int n_frames) {
     const int C = (e->net_sms > 0 && n_frames >= 2 * e->chunk) ? (n_frames + e->chunk - 1) / e->chunk + 4 : 1;  // upper bound
     return 1 + C * (2 + tc_launches_per_chunk(e)) + 1;  // stage_in + per chunk (analysis, network, synthesis) + carry
   }
-  return 3 + 7 * ((n_frames + kF32ChainMaxHops - 1) / kF32ChainMaxHops);  // stage_in, analysis, synthesis + per chunk: fc, conv1, conv2, GRU chain, fc_gb, fc_rb, carry
+  return 3 + 7 * ((n_frames + e->f32_chunk - 1) / e->f32_chunk);  // stage_in, analysis, synthesis + per chunk: fc, conv1, conv2, GRU chain, fc_gb, fc_rb, carry
 }
 // Runtime switch for the chunked overlap schedule (an engine created without it cannot turn it on): profiling a
 // kernel class alone on all SMs needs the serial schedule.

@@ -53,6 +53,7 @@ struct pnb_engine {
   int par[5] = {0, 0, 0, 0, 0};
   float *c2_all = nullptr;   // fp32 path: [chunk][S][512] conv2 outputs of a chunk of hops
   unsigned *f32_cnt = nullptr;  // fp32 path: [5][f32_rb] dependency counters of the persistent GRU chain
+  int f32_chunk = 8;            // hops per chunk of the fp32 network = min(max_frames, kF32ChainMaxHops)
   int f32_rt = 8, f32_rb = 0;   // rows per thread of the chain kernel (8: 128-stream blocks, 1: 16-stream blocks); stream blocks
   long hop = 0;  // hops processed since reset
 

@@ -114,7 +114,7 @@ struct F32ChainLayer {
   int ldw, w_row0[2];         // 3H; first row of W for each input segment
   float *h;                   // [(n+1) slots][S][H]
 };
-constexpr int kF32ChainMaxHops = 8;
+constexpr int kF32ChainMaxHops = 32;  // hops per launch of the fp32 chain (longer chunks amortise the ramp diagonals)
 struct F32ChainArgs {
   F32ChainLayer L[5];
   int S, n_rb, n_units, n_lh;

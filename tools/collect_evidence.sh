@@ -7,8 +7,9 @@ python bench.py --steps 20 --warmup 5 > $O/ev2_bench_default.json 2> $O/ev2_benc
 PNB_OVERLAP=0 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-int16-run > $O/ev2_bench_serial.json 2>/dev/null
 python bench.py --frames 8 --steps 20 --warmup 5 --no-cpu-baseline > $O/ev2_bench_f8.json 2>/dev/null
 python bench.py --path xcorr --streams 65536 --steps 20 --warmup 5 > $O/ev2_bench_xcorr.json 2> $O/ev2_xcorr.err; cut -c1-200 $O/ev2_bench_xcorr.json
-python bench.py --streams 1024 --frames 8 --nn tensor --no-cpu-baseline > $O/ev2_bench_1024_tensor.json 2>/dev/null
-python bench.py --streams 1024 --frames 8 --nn fp32 --no-cpu-baseline > $O/ev2_bench_1024_fp32.json 2>/dev/null
+python bench.py --streams 1024 --frames 32 --nn tensor --no-cpu-baseline > $O/ev2_bench_1024_tensor.json 2>/dev/null
+python bench.py --streams 1024 --frames 32 --nn fp32 --no-cpu-baseline > $O/ev2_bench_1024_fp32.json 2>/dev/null
+python bench.py --streams 1024 --frames 8 --nn fp32 --no-cpu-baseline --no-int16-run > $O/ev2_bench_1024_fp32_f8.json 2>/dev/null
 python bench.py --streams 16384 --frames 8 --nn fp32 --no-cpu-baseline --no-int16-run > $O/ev2_bench_16384_fp32.json 2>/dev/null
 python bench.py --path traindata > $O/ev2_bench_traindata.json 2>/dev/null
 timeout 600 ncu --kernel-name-base mangled -k regex:pnb --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/ev2_launches.csv \
