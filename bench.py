@@ -637,8 +637,10 @@ def main():
         e2e["blocking_calls_timed"] = nb
 
     # ---- serial-schedule profile for the roofline.  With the overlapped schedule it runs on an engine of its own, created
-    # without the SM partition AFTER the partitioned engine is gone (with green contexts alive in the process, kernels on
-    # an ordinary stream were measured up to 40 % slower in the analysis kernel).
+    # without the SM partition after the partitioned engine is gone.  Coming straight after seconds at the board's power
+    # cap, this step still runs under the lowered clock ceiling the cap leaves behind: the power-capped network kernels
+    # are unaffected, the DSP kernels (which alone would boost to 1.9 GHz) show up to a third slower than in a run that
+    # uses the serial schedule throughout (profiles/r2_bench_serial.json).
     if sched["kind"] != "serial":
         eng.close()
         eng = None
@@ -699,7 +701,7 @@ def main():
                 "issued_frac": achieved * 3 / peak if nn_mode == "tensor" else None,
                 "step_hbm_gbs_algorithmic": S * F * BYTES_PER_FRAME / (ms_max / K * 1e-3) / 1e9,
                 "breakdown_ms": {k: round(v[0], 4) for k, v in prof.items()},
-                "breakdown_note": "one step on the serial schedule: every kernel alone on all 148 SMs",
+                "breakdown_note": "one step on the serial schedule (every kernel alone on all 148 SMs), taken right after the timed region: the DSP kernels still run under the clock ceiling the power cap left behind",
                 "overlapped_breakdown_ms": overlapped_breakdown}
 
     # ---- second timed run at int16 amplitude scale (x 32768: what the reference's train() feeds the same API with) --
