@@ -630,19 +630,8 @@ __device__ __forceinline__ PitchResult pitch_stage(WarpSmem &W, const float *src
           *reinterpret_cast<float4 *>(&W.p.yy[i + 3]) = o;
         }
       } else {
-        // The lanes' lags are arbitrary, so x[j - lag] read by all lanes at the same j collides on banks wherever two
-        // lags agree modulo 32 (3-4 wavefronts per load on average).  Skewed instead: at step s lane l works on
-        // j = s - sig_l with sig_l = (l - lag_l) mod 32, which puts its x[j - lag] on bank (s - l): all different; the
-        // x[j] operands then span 32 consecutive words (equal sig = equal address = broadcast).  Every lane still adds
-        // its terms in ascending j, 31 steps are idle at either end.
         float d = 0.f;
-        const int sig = (wlane - lag) & 31;
-        const float *xa = x - sig, *xb = x - sig - lag;
-        const bool on = lag >= 0;
-#pragma unroll 4
-        for (int s = 0; s < 512; s++) {
-          if (on && (unsigned)(s - sig) < 480u) d = d + xa[s] * xb[s];
-        }
+        if (lag >= 0) d = seq_dot4(x, x - lag, 480, 0.f);
         W.p.cand_xy[role] = d;
       }
     }
