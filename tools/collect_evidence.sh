@@ -27,4 +27,5 @@ timeout 600 ncu --kernel-name-base mangled -k regex:pnb --metrics gpu__time_dura
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gru_chain_f32_kernel --launch-skip 3 -c 1 -f -o $O/ev2_chain_f32 \
   python bench.py --streams 1024 --frames 8 --nn fp32 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-int16-run > $O/ev2_ncu_chain_f32.log 2>&1
 python tools/latency_single_stream.py > $O/ev2_latency.json 2>/dev/null
+python tools/timeline.py > $O/ev2_timeline.json 2>/dev/null
 ls -la $O/ev2_*
