@@ -895,26 +895,49 @@ constexpr int DENSE_STAGES = 3, DENSE_STAGES3 = 2, SMALL_BN = 48, SMALL_STAGES =
 constexpr int kConvTerms = 3;
 
 // fc 70 -> 128 relu in fp32 FMA (0.1 % of the MACs; K = 70 is no tensor-core shape), emitting the three bf16
-// terms conv1 consumes.  One block per 4 rows, one thread per output.
+// terms conv1 consumes.  One block per 16 rows, one thread per output: the 16 feature rows sit in shared memory and are
+// read four k at a time (one broadcast 128-bit load per row and four FMAs), the weight column comes through L1.
+// Every output is bias + sum over ascending k, one fmaf per term, like the fp32 path's fc kernel.
+constexpr int FC_ROWS = 16;
 __global__ void __launch_bounds__(128) fc_split_kernel(const float *__restrict__ feat, const float *__restrict__ W,
                                                        const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out,
                                                        int M, size_t plane_rows) {
-  __shared__ float f[4][72];
-  const int r0 = blockIdx.x * 4;
-  for (int i = threadIdx.x; i < 4 * 70; i += blockDim.x) {
-    int rr = i / 70, kk = i % 70;
-    f[rr][kk] = (r0 + rr < M) ? feat[(size_t)(r0 + rr) * 70 + kk] : 0.f;
+  __shared__ __align__(16) float f[FC_ROWS][72];
+  const int r0 = blockIdx.x * FC_ROWS;
+  for (int i = threadIdx.x; i < FC_ROWS * 72; i += blockDim.x) {
+    const int rr = i / 72, kk = i - rr * 72;
+    f[rr][kk] = (kk < 70 && r0 + rr < M) ? feat[(size_t)(r0 + rr) * 70 + kk] : 0.f;
   }
   __syncthreads();
   const int n = threadIdx.x;
-  float a[4] = {bias[n], bias[n], bias[n], bias[n]};
-  for (int k = 0; k < 70; k++) {
-    float w = __ldg(W + (size_t)k * 128 + n);
+  float a[FC_ROWS];
+  const float b0 = bias[n];
 #pragma unroll
-    for (int rr = 0; rr < 4; rr++) a[rr] = fmaf(w, f[rr][k], a[rr]);
+  for (int rr = 0; rr < FC_ROWS; rr++) a[rr] = b0;
+#pragma unroll 1
+  for (int k = 0; k < 68; k += 4) {
+    const float w0 = __ldg(W + (size_t)k * 128 + n), w1 = __ldg(W + (size_t)(k + 1) * 128 + n);
+    const float w2 = __ldg(W + (size_t)(k + 2) * 128 + n), w3 = __ldg(W + (size_t)(k + 3) * 128 + n);
+#pragma unroll
+    for (int rr = 0; rr < FC_ROWS; rr++) {
+      const float4 fv = *reinterpret_cast<const float4 *>(&f[rr][k]);
+      a[rr] = fmaf(w0, fv.x, a[rr]);
+      a[rr] = fmaf(w1, fv.y, a[rr]);
+      a[rr] = fmaf(w2, fv.z, a[rr]);
+      a[rr] = fmaf(w3, fv.w, a[rr]);
+    }
+  }
+  {
+    const float w0 = __ldg(W + (size_t)68 * 128 + n), w1 = __ldg(W + (size_t)69 * 128 + n);
+#pragma unroll
+    for (int rr = 0; rr < FC_ROWS; rr++) {
+      a[rr] = fmaf(w0, f[rr][68], a[rr]);
+      a[rr] = fmaf(w1, f[rr][69], a[rr]);
+    }
   }
   const size_t plane = plane_rows * 128;
-  for (int rr = 0; rr < 4; rr++) {
+#pragma unroll
+  for (int rr = 0; rr < FC_ROWS; rr++) {
     if (r0 + rr >= M) break;
     float v = a[rr] < 0.f ? 0.f : a[rr];
     __nv_bfloat16 t0 = __float2bfloat16_rn(v);
@@ -1359,7 +1382,7 @@ int tc_fc(pnb_engine *e, int h0, int n, cudaStream_t st) {
   pnb_tc_state *t = e->tc;
   const int S = e->S, Fm = e->Fmax, rows = n * S;
   ProfScope ps(e, PNB_K_TC_AUX, st);
-  fc_split_kernel<<<(rows + 3) / 4, 128, 0, st>>>(e->d_feat + (size_t)h0 * S * kFeat, e->fc.W, e->fc.b,
+  fc_split_kernel<<<(rows + FC_ROWS - 1) / FC_ROWS, 128, 0, st>>>(e->d_feat + (size_t)h0 * S * kFeat, e->fc.W, e->fc.b,
                                                   t->fc_all + (size_t)(4 + h0) * S * 128, rows, (size_t)(Fm + 4) * S);
   return 1;
 }
