@@ -195,7 +195,8 @@ int pnb_read_tap(pnb_engine *e, int what, void *dst, size_t dst_bytes);
  * CUDA events on the launching stream; pnb_profile_read waits for them and returns the accumulated
  * milliseconds and launch counts per class since the last read (arrays of PNB_NUM_KERNEL_CLASSES). */
 enum {
-  PNB_K_STAGE_IN = 0, PNB_K_ANALYSIS = 1, PNB_K_FC = 2, PNB_K_GEMM_F32 = 3, PNB_K_GRU_GATES = 4,
+  PNB_K_STAGE_IN = 0, PNB_K_ANALYSIS = 1, PNB_K_FC = 2, PNB_K_GEMM_F32 = 3, PNB_K_F32_CARRY = 4,  /* fp32 path: the per-chunk carry (was the GRU gate kernel before the gates were fused) */
+ 
   PNB_K_SYNTHESIS = 5, PNB_K_SLIDE = 6, PNB_K_TC_GEMM = 7, PNB_K_TC_AUX = 8, PNB_K_LABELS = 9,
   PNB_NUM_KERNEL_CLASSES = 10
 };

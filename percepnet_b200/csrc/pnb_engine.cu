@@ -628,7 +628,7 @@ static int nn_chunk_f32(pnb_engine *e, int h0, int n, cudaStream_t st) {
   for (int li = 0; li < 5; li++) cseg(e->h[li][0], (size_t)S * e->gru[li].H, 1, n);
   c.seg[ns++] = F32CarrySeg{reinterpret_cast<float4 *>(e->c2), reinterpret_cast<const float4 *>(e->c2_all + (size_t)(n - 1) * S * 512), (size_t)S * 512 / 4, 1};
   c.n_seg = ns; c.cnt = e->f32_cnt; c.n_cnt = 5 * e->f32_rb;
-  { ProfScope ps(e, PNB_K_GRU_GATES, st); nl += launch_f32_carry(c, st); }
+  { ProfScope ps(e, PNB_K_F32_CARRY, st); nl += launch_f32_carry(c, st); }
   return nl;
 }
 

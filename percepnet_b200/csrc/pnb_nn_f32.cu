@@ -4,7 +4,9 @@
 // (/root/reference/src/nnet.cpp:59-72, vec.h:102-135, rnn.cpp:42-81) and re-reads all 31.9 MB of
 // weights for every hop.  Here the rows of every contraction are the concurrent streams, so each
 // weight tile is reused across 128 streams from shared memory; activations use the reference's
-// tansig table approximation (vec.h:53-76).
+// tansig table approximation (vec.h:53-76).  Per chunk of hops: fc, conv1, conv2 over all rows of the chunk
+// (gemm_f32_kernel), the five GRUs of all its hops in one persistent launch (gru_chain_f32_kernel), the output layers,
+// and a carry; the schedule is nn_chunk_f32 in pnb_engine.cu.
 #include "pnb_kernels.h"
 #include "../../include/pnb_nnet_layout.h"
 
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(CH_THREADS, RT == 8 ? 2 : 4) gru_chain_f32_ker
     }
     cp_async_wait<0>();
 
-    // ---- gates and state update (nnet.cpp:120-180 with reset_after; same operation order as gru_gates_kernel)
+    // ---- gates and state update (nnet.cpp:120-180 with reset_after: z, r from the summed sums, n = tanh(b_n + (b'_n + U_n h) r + W_n x))
     {
       const float *b = L.bias;
       const int H = L.H;
